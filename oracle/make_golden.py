@@ -1,0 +1,214 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference from /root/reference.
+
+Run in the build container only (the reference does not travel to the GPU box):
+    python oracle/make_golden.py
+The reference modules are imported read-only through `oracle/ref_shim.py` (stub modules for the
+missing non-arithmetic imports).  Nothing from the reference is copied into this repo; only its
+numerical outputs on seeded synthetic inputs are stored.
+TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402  (puts /root/reference on sys.path with stubs)
+
+torch.autograd.set_detect_anomaly(False)
+from models.nerf_net import NeRFNet  # noqa: E402
+from utils.ray import get_persp_rays, get_persp_intrinsic  # noqa: E402
+from utils import image as ref_image  # noqa: E402
+
+OUT = os.path.join(HERE, "..", "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+CKPT = ("/root/reference/logs/flower_B8_P64_PS6_1corr0.18,1,0.46,1_0.01geoCorr0.5,1,3,1_noTrainSFM/"
+        "checkpoints/latest.ckpt")
+
+
+def llff_rays(n, seed=0, patch=None):
+    """get_persp_rays(756,1008,K(focal 815), [I|t]), t~U(-0.3,0.3)^3, seeded."""
+    g = torch.Generator().manual_seed(seed)
+    K = get_persp_intrinsic(756, 1008, 815.0)
+    t = torch.rand(3, generator=g) * 0.6 - 0.3
+    c2w = torch.cat([torch.eye(3), t[:, None]], 1)
+    rays = get_persp_rays(756, 1008, K, c2w)            # [2,H,W,3]
+    if patch is None:
+        idx = torch.randperm(756 * 1008, generator=g)[:n]
+        return rays.reshape(2, -1, 3)[:, idx].contiguous()
+    P, stride = patch
+    y0 = int(torch.randint(0, 756 - P * stride, (1,), generator=g))
+    x0 = int(torch.randint(0, 1008 - P * stride, (1,), generator=g))
+    return rays[:, y0:y0 + P * stride:stride, x0:x0 + P * stride:stride].contiguous()  # [2,P,P,3]
+
+
+class RecordRandom:
+    """Record every torch.rand / torch.randn draw made inside the reference (call order preserved)."""
+
+    def __enter__(self):
+        self.draws = []
+        self._rand, self._randn = torch.rand, torch.randn
+
+        def rand(*a, **k):
+            r = self._rand(*a, **k); self.draws.append(("rand", r.clone())); return r
+
+        def randn(*a, **k):
+            r = self._randn(*a, **k); self.draws.append(("randn", r.clone())); return r
+
+        torch.rand, torch.randn = rand, randn
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randn = self._rand, self._randn
+
+
+def npsd(model):
+    return {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def save(name, **arrs):
+    flat = {}
+    for k, v in arrs.items():
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                flat[f"{k}/{kk}"] = np.asarray(vv)
+        else:
+            flat[k] = np.asarray(v)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **flat)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, {len(flat)} arrays")
+
+
+def outs(ret):
+    return {k: v.detach().numpy() for k, v in ret.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+def cfg1():
+    """BASELINE config[0]: 512 rays, 64 coarse only, D=4 W=64, seeded default init, eval mode."""
+    torch.manual_seed(0)
+    net = NeRFNet(netdepth=4, netwidth=64, netdepth_fine=4, netwidth_fine=64, N_samples=64, N_importance=0,
+                  use_semantics=True, sem_with_coord=True)
+    net.eval()
+    rays = llff_rays(512, seed=1)
+    with torch.no_grad():
+        ret = net(rays, (1.2, 12.0))
+    save("cfg1_d4w64_eval", sd=npsd(net), rays=rays.numpy(), near=1.2, far=12.0, out=outs(ret))
+
+    # same tiny net, hierarchical (64+32), train mode with recorded randoms + full-parameter gradients
+    torch.manual_seed(1)
+    net = NeRFNet(netdepth=4, netwidth=64, netdepth_fine=4, netwidth_fine=64, N_samples=64, N_importance=32,
+                  use_semantics=True, sem_with_coord=True, perturb=1.0, raw_noise_std=1.0)
+    net.train()
+    rays = llff_rays(96, seed=2)
+    with RecordRandom() as rec:
+        ret = net(rays, (1.2, 12.0))
+    kinds = [k for k, _ in rec.draws]
+    assert kinds == ["rand", "randn", "rand", "randn"], kinds
+    rnd = dict(t_rand=rec.draws[0][1], noise0=rec.draws[1][1], u=rec.draws[2][1], noise1=rec.draws[3][1])
+    g = torch.Generator().manual_seed(3)
+    tgt = {k: torch.randn(ret[k].shape, generator=g) for k in ("rgb", "rgb0", "semantics", "semantics0", "acc", "depth0")}
+    loss = sum((ret[k] * tgt[k]).sum() for k in tgt)
+    loss.backward()
+    grads = {k: p.grad.numpy().copy() for k, p in net.named_parameters()}
+    save("cfg1_d4w64_train_grads", sd=npsd(net), rays=rays.numpy(), near=1.2, far=12.0, out=outs(ret),
+         rnd={k: v.numpy() for k, v in rnd.items()}, gout={k: v.numpy() for k, v in tgt.items()}, grads=grads,
+         loss=float(loss))
+
+
+def flower():
+    """BASELINE config[1] weights: shipped stage-2 flower checkpoint, D=8 W=256 + seg head, 64+128."""
+    ck = torch.load(CKPT, map_location="cpu")
+    kw = dict(N_samples=64, N_importance=128, use_semantics=True, sem_with_coord=True, sem_dim=2, sem_layer=2)
+    net = NeRFNet(perturb=1.0, raw_noise_std=1.0, **kw)
+    net.load_state_dict(ck["model"], strict=True)
+
+    # weights fixture (fp32, exact) -- shared by every 'flower' test, GPU parity tests and bench.py
+    save("flower_weights", sd=npsd(net), global_step=ck["global_step"])
+
+    # eval mode, 256 random LLFF rays + one 16x16 stride-6 patch; keep all intermediates
+    net.eval()
+    rays = llff_rays(256, seed=0)
+    with torch.no_grad():
+        ret = net(rays, (1.2, 12.0))
+        # stage-wise intermediates for the 'exact indices given identical cdf/u' contract
+        z = net.point_sampler(rays[0], rays[1], torch.tensor([[1.2, 12.0]]).expand(256, 2), zvals_only=True, perturb=0.0)
+        smp = net.importance_sampler
+        mid = .5 * (z[..., 1:] + z[..., :-1])
+        w = ret["weights0"][..., 1:-1] + 1e-5
+        pdf = w / torch.sum(w, -1, keepdim=True)
+        cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+        u = torch.linspace(0., 1., steps=128).expand(256, 128).contiguous()
+        inds = torch.searchsorted(cdf, u, right=True)
+        z_samples = smp.sample_pdf(mid, ret["weights0"][..., 1:-1], det=True)
+        z_fine, _ = torch.sort(torch.cat([z, z_samples], -1), -1)
+    save("flower_eval_256", rays=rays.numpy(), near=1.2, far=12.0, out=outs(ret),
+         stage=dict(z=z.numpy(), mid=mid.numpy(), cdf=cdf.numpy(), u=u.numpy(), inds=inds.numpy(),
+                    z_samples=z_samples.numpy(), z_fine=z_fine.numpy()))
+
+    # train mode (perturb=1, raw_noise_std=1, configs/flower_full.txt:14), 64 rays, recorded randoms,
+    # seg-head-only gradients as under --fix_backbone (run_nerf.py:307-318)
+    net.train()
+    for n, p in net.named_parameters():
+        p.requires_grad_("semantic_linear" in n)
+    rays = llff_rays(64, seed=5)
+    with RecordRandom() as rec:
+        ret = net(rays, (1.2, 12.0))
+    rnd = dict(t_rand=rec.draws[0][1], noise0=rec.draws[1][1], u=rec.draws[2][1], noise1=rec.draws[3][1])
+    g = torch.Generator().manual_seed(7)
+    tgt = {k: torch.randn(ret[k].shape, generator=g) for k in ("rgb", "rgb0", "semantics", "semantics0")}
+    loss = sum((ret[k] * tgt[k]).sum() for k in tgt)
+    loss.backward()
+    grads = {k: p.grad.numpy().copy() for k, p in net.named_parameters() if p.grad is not None}
+    keep = {k: v for k, v in outs(ret).items() if not k.startswith("raw")}
+    save("flower_train_64_semgrads", rays=rays.numpy(), near=1.2, far=12.0, out=keep,
+         rnd={k: v.numpy() for k, v in rnd.items()}, gout={k: v.numpy() for k, v in tgt.items()}, grads=grads,
+         loss=float(loss))
+
+
+class _Args:
+    rand_neg = False
+    self_corr_w = 1
+    use_sim_matrix = True
+    patch_stride = 6
+    app_corr_params = ["0.18", "1", "0.46", "1"]
+    geo_corr_params = ["0.5", "1", "3", "1"]
+
+
+def losses():
+    """CorrelationLoss / GeoCorrelationLoss (utils/image.py:263-482), small shapes, with code gradients."""
+    g = torch.Generator().manual_seed(11)
+    B, P = 4, 16
+    feat = torch.randn(B, 384, 14, 14, generator=g)
+    cls_ = torch.randn(B, 384, generator=g)
+    sim = ref_image.get_similarity_matrix(cls_)
+    code = torch.randn(B, 2, P, P, generator=g, requires_grad=True)
+    app = ref_image.CorrelationLoss(_Args())
+    with RecordRandom() as rec:
+        la = app(feat, code, sim)
+    la.backward()
+    coords1, coords2 = rec.draws[0][1], rec.draws[1][1]          # raw U[0,1) draws; the loss maps them to *2-1
+    ga = code.grad.clone(); code.grad = None
+
+    rays = torch.stack([llff_rays(0, seed=20 + b, patch=(P, 6)) for b in range(B)], 1)   # [2,B,P,P,3]
+    ray_o = rays[0].permute(0, 3, 1, 2).contiguous(); ray_d = rays[1].permute(0, 3, 1, 2).contiguous()
+    depth = (torch.rand(B, 1, P, P, generator=g) * 16.0 + 1.2)  # some values > max_depth=15 to hit the clip
+    geo = ref_image.GeoCorrelationLoss(_Args())
+    depth_in = depth.clone()
+    lg = geo(depth_in, code, [ray_o, ray_d, None], sim)
+    lg.backward()
+    gg = code.grad.clone()
+    save("losses_b4_p16", feat=feat.numpy(), cls=cls_.numpy(), sim=sim.numpy(), code=code.detach().numpy(),
+         rand1=coords1.numpy(), rand2=coords2.numpy(), app_loss=float(la), app_gcode=ga.numpy(),
+         ray_o=ray_o.numpy(), ray_d=ray_d.numpy(), depth=depth.numpy(), depth_clipped=depth_in.numpy(),
+         geo_loss=float(lg), geo_gcode=gg.numpy(),
+         app_params=np.array([0.18, 1, 0.46, 1.0]), geo_params=np.array([0.5, 1, 3, 1.0]))
+
+
+if __name__ == "__main__":
+    cfg1()
+    flower()
+    losses()
