@@ -1,0 +1,43 @@
+// Library-internal interfaces between the translation units of libnerfsos.so.
+#pragma once
+#include "common.cuh"
+
+namespace nsos {
+
+// simt_render.cu
+size_t simt_render_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays);
+int simt_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, const float* rays_o, const float* rays_d,
+                    const float* near, const float* far, const NsosRandoms* rnd, uint64_t seed, const NsosRenderOut& out,
+                    void* workspace, size_t workspace_bytes, int64_t n_rays, cudaStream_t st);
+size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays);
+int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, const float* rays_o, const float* rays_d,
+                    const float* z_vals0, const float* z_vals, const NsosRandoms* rnd, uint64_t seed, const float* g_maps,
+                    float* grads_c, float* grads_f, int trunk, void* workspace, size_t workspace_bytes, int64_t n_rays,
+                    cudaStream_t st);
+int simt_invert_cdf(const float* bins, const float* cdf, const float* u, float* samples, int64_t* inds, int64_t n_rays, int M, int K,
+                    cudaStream_t st);
+size_t simt_mlp_workspace_bytes(const NetGeom& g, int64_t P);
+int simt_mlp_query(const NetGeom& g, const float* prm, const float* pts, const float* viewdirs, float* raw, void* workspace,
+                   size_t workspace_bytes, int64_t P, cudaStream_t st);
+
+// tc_render.cu (tcgen05 / TMEM / bulk-copy path)
+size_t tc_packed_bytes(const NsosNetDesc& net, int mode);
+int tc_pack_weights(const NsosNetDesc& net, const float* params, void* packed, int mode, cudaStream_t st);
+size_t tc_render_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays);
+int tc_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, const void* packed_c, const void* packed_f,
+                  const float* rays_o, const float* rays_d, const float* near, const float* far, const NsosRandoms* rnd,
+                  uint64_t seed, const NsosRenderOut& out, void* workspace, size_t workspace_bytes, int64_t n_rays,
+                  cudaStream_t st);
+int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,
+                cudaStream_t st);
+
+// corr_loss.cu
+size_t geo_corr_workspace_bytes(int B, int C, int M);
+int geo_corr_loss(const float* xyz, const float* code, const int64_t* neg_idx, const float* params, float* loss, float* g_code,
+                  int B, int C, int M, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t app_corr_workspace_bytes(int B, int Cf, int C, int S);
+int app_corr_loss(const float* feats, const float* nfeats, const float* code, const float* ncode, const float* params, float* loss,
+                  float* g_code, float* g_ncode, int B, int Cf, int C, int S, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st);
+
+}  // namespace nsos

@@ -1,0 +1,810 @@
+// Kernel A on the 5th-gen tensor cores: fused hierarchical render for sm_100a.
+//
+// One persistent CTA per SM walks ray PAIRS.  Per pair: coarse tile(s) -> composite + inverse-CDF
+// resampling + sort (warp per ray, in shared memory) -> fine tiles -> composite -> one write of the
+// per-ray maps.  A tile is 128 sample points = the 128 TMEM lanes; the whole MLP of a tile runs without
+// leaving the SM:
+//   * activations live in TENSOR MEMORY as the MMA A operand (fp16 hi plane cols 256..383, lo plane cols
+//     384..511), the fp32 accumulator D in cols 0..255;  tcgen05.mma kind::f16, M=128, N<=256, K=16;
+//   * weights stream from L2 through a ring of 32 KB shared-memory slots with cp.async.bulk (TMA engine,
+//     mbarrier complete_tx), pre-swizzled at pack time into the canonical K-major SWIZZLE_128B slabs;
+//   * NSOS_MODE_TC_EXACT splits activations and weights into fp16 hi+lo and issues A_hi.W_hi + A_lo.W_hi
+//     + A_hi.W_lo (fp32-equivalent: ~22 mantissa bits, measured 1e-6 on composited maps);
+//     NSOS_MODE_TC_FAST issues the hi.hi product only;
+//   * the positional encoding gamma(x) is written by the row threads straight into a swizzled smem tile
+//     and used as an SMEM A operand (layer 0, the skip layer, the semantic head);
+//   * the N<=3 heads (sigma, rgb, semantic logits) and the per-ray view-direction half of views_linears
+//     are evaluated in fp32 on CUDA cores inside the epilogues, directly on the TMEM read-out.
+// Warp roles: warps 0-3 = row workers (setup, epilogues, compositing), warp 4 = MMA issuer (one lane),
+// warp 5 = bulk-copy producer (one lane).
+//
+// Reference semantics: models/nerf_net.py:71-130 and the modules it calls (see include/nerfsos.h).
+#include <algorithm>
+#include <cstdlib>
+
+#include "internal.h"
+#include "render_device.cuh"
+#include "tc_ptx.cuh"
+
+namespace nsos {
+namespace {
+using namespace ptx;
+
+constexpr int kSlotBytes = 32768;      // one weight slab plane: N(<=256) rows x 64 fp16
+constexpr int kMaxSlots = 6;
+constexpr int kWorkers = 128;
+constexpr int kThreads = 192;
+constexpr float kActScale = 16.f;      // activations are stored as fp16(16*a): keeps the lo plane out of fp16 subnormals
+constexpr int kMaxStages = 13;
+constexpr int kMaxSlabs = 5;
+constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384, kTmemCols = 512;
+constexpr int kGBytes = 128 * 128;     // gamma tile plane: 128 rows x 64 fp16, SWIZZLE_128B
+constexpr int kHalfMax = 128;          // W/2 max
+constexpr int kSemMax = 4;
+constexpr int kHeadFloats = 256 + 4 + kSemMax * kHalfMax + 4 + 3 * kHalfMax + 4;
+
+enum EpiKind { EPI_HIDDEN = 0, EPI_HIDDEN_SIGMA = 1, EPI_SEM = 2, EPI_FEAT = 3, EPI_RGB = 4, EPI_RAW = 5 };
+constexpr int A_GAMMA = -1;
+
+// fp32 side data at the head of the packed image
+struct TcAux {
+  float inv_scale[16];          // per stage: 1 / (weight scale * kActScale)
+  uint32_t absmax_bits[16];     // per stage max |w| (float bits), scratch of the pack pass
+  float bias[16][256];          // per stage bias (zero padded)
+  float heads[kHeadFloats];     // w_alpha[256] b_alpha[4] w_s2[4][128] b_s2[4] w_rgb[3][128] b_rgb[4]
+  float w_vdir[kHalfMax][28];   // views_linears.0.weight[:, W:W+encv]
+};
+constexpr size_t kAuxBytes = (sizeof(TcAux) + 1023) / 1024 * 1024;
+constexpr int kHeadWAlpha = 0, kHeadBAlpha = 256, kHeadWS2 = 260, kHeadBS2 = 260 + kSemMax * kHalfMax,
+              kHeadWRgb = kHeadBS2 + 4, kHeadBRgb = kHeadWRgb + 3 * kHalfMax;
+
+struct TcStage {
+  int n;                 // MMA N (multiple of 16)
+  int nslab;             // K slabs of 64
+  int epi;               // EpiKind
+  int asrc[kMaxSlabs];   // A_GAMMA or TMEM K-slab index
+};
+struct TcProg {
+  int nst, W, Lp, Lv, enc, encv, sem_dim, H2;
+  TcStage st[kMaxStages];
+};
+
+// host-side plan used by the pack kernels
+struct PackSlab { int64_t w_off; int ld, col0, kvalid, nvalid, n, stage; int64_t dst_hi, dst_lo; };
+struct PackPlan {
+  int nslab, nst;
+  PackSlab s[kMaxStages * kMaxSlabs];
+  int64_t st_w_off[kMaxStages]; int st_rows[kMaxStages], st_ld[kMaxStages];  // tensor extents for absmax
+  int64_t st_b_off[kMaxStages]; int st_nb[kMaxStages];                       // bias source
+  int64_t total_bytes;
+};
+
+bool tc_supported(const NetGeom& g, const char** why) {
+  static const char* w;
+  auto fail = [&](const char* m) { w = m; if (why) *why = w; return false; };
+  if (!g.use_viewdirs) return fail("use_viewdirs=0 is only implemented by NSOS_MODE_SIMT_FP32");
+  if (g.W % 64 != 0 || g.W < 64 || g.W > 256) return fail("tcgen05 path needs W in {64,128,192,256}");
+  if (g.D > 10) return fail("tcgen05 path needs D <= 10");
+  if (g.enc > 63 || g.encv > 27) return fail("tcgen05 path needs multires<=10, multires_views<=4");
+  if (g.sem_dim > kSemMax) return fail("tcgen05 path needs sem_dim <= 4");
+  return true;
+}
+
+void build_prog(const NetGeom& g, bool exact, TcProg& p, PackPlan& plan) {
+  memset(&p, 0, sizeof(p)); memset(&plan, 0, sizeof(plan));
+  p.W = g.W; p.Lp = g.Lp; p.Lv = g.Lv; p.enc = g.enc; p.encv = g.encv; p.sem_dim = g.sem_dim; p.H2 = g.W / 2;
+  const int ks = g.W / 64;
+  int64_t off = (int64_t)kAuxBytes;
+  auto add_stage = [&](int n, int nvalid, int epi, int64_t w_off, int ld, int64_t b_off, int nb, int col_gamma_first,
+                       int col_h0, bool has_h, bool gamma_first, bool gamma_last, int col_gamma_last) {
+    TcStage& s = p.st[p.nst];
+    s.n = n; s.epi = epi; s.nslab = 0;
+    auto add_slab = [&](int asrc, int col0, int kvalid) {
+      s.asrc[s.nslab++] = asrc;
+      PackSlab& ps = plan.s[plan.nslab++];
+      ps.w_off = w_off; ps.ld = ld; ps.col0 = col0; ps.kvalid = kvalid; ps.nvalid = nvalid; ps.n = n; ps.stage = p.nst;
+      ps.dst_hi = off; off += (int64_t)n * 128;
+      ps.dst_lo = -1;
+      if (exact) { ps.dst_lo = off; off += (int64_t)n * 128; }
+    };
+    if (gamma_first) add_slab(A_GAMMA, col_gamma_first, g.enc);
+    if (has_h) for (int j = 0; j < ks; ++j) add_slab(j, col_h0 + 64 * j, 64);
+    if (gamma_last) add_slab(A_GAMMA, col_gamma_last, g.enc);
+    plan.st_w_off[p.nst] = w_off; plan.st_rows[p.nst] = nvalid; plan.st_ld[p.nst] = ld;
+    plan.st_b_off[p.nst] = b_off; plan.st_nb[p.nst] = nb;
+    ++p.nst;
+  };
+  for (int i = 0; i < g.D; ++i) {
+    int epi = (i == g.D - 1) ? EPI_HIDDEN_SIGMA : EPI_HIDDEN;
+    if (i == 0) add_stage(g.W, g.W, epi, g.w_pts[i], g.enc, g.b_pts[i], g.W, 0, 0, false, true, false, 0);
+    else if (g.in_pts[i] == g.W) add_stage(g.W, g.W, epi, g.w_pts[i], g.W, g.b_pts[i], g.W, 0, 0, true, false, false, 0);
+    else add_stage(g.W, g.W, epi, g.w_pts[i], g.W + g.enc, g.b_pts[i], g.W, 0, g.enc, true, true, false, 0);  // [enc, h]
+  }
+  if (g.use_sem)  // semantic_linear.0 on [h, enc]
+    add_stage(g.W / 2, g.W / 2, EPI_SEM, g.w_s0, g.sem_in, g.b_s0, g.W / 2, 0, 0, true, false, g.sem_coord != 0, g.W);
+  add_stage(g.W, g.W, EPI_FEAT, g.w_feat, g.W, g.b_feat, g.W, 0, 0, true, false, false, 0);
+  add_stage(g.W / 2, g.W / 2, EPI_RGB, g.w_views, g.W + g.encv, g.b_views, g.W / 2, 0, 0, true, false, false, 0);
+  plan.nst = p.nst;
+  plan.total_bytes = off;
+}
+
+// ---- pack kernels -----------------------------------------------------------------------------------
+__global__ void k_pack_absmax(const float* __restrict__ prm, TcAux* aux, const PackPlan plan) {
+  int st = blockIdx.y;
+  int64_t n = (int64_t)plan.st_rows[st] * plan.st_ld[st];
+  const float* w = prm + plan.st_w_off[st];
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&aux->absmax_bits[st], __float_as_uint(m));
+}
+__device__ __forceinline__ float stage_scale(const TcAux* aux, int st) {
+  float amax = __uint_as_float(aux->absmax_bits[st]);
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);                      // amax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 15 - e);            // amax*scale in [2^14, 2^15)
+}
+__global__ void k_pack_aux(const float* __restrict__ prm, TcAux* aux, const PackPlan plan, const NetGeom g) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int nt = gridDim.x * blockDim.x;
+  for (int st = t; st < 16; st += nt) aux->inv_scale[st] = (st < plan.nst) ? 1.f / (stage_scale(aux, st) * kActScale) : 0.f;
+  for (int i = t; i < 16 * 256; i += nt) {
+    int st = i / 256, c = i % 256;
+    aux->bias[st][c] = (st < plan.nst && c < plan.st_nb[st]) ? prm[plan.st_b_off[st] + c] : 0.f;
+  }
+  const int H = g.W / 2;
+  for (int i = t; i < kHeadFloats; i += nt) {
+    float v = 0.f;
+    if (i < kHeadBAlpha) { if (i < g.W) v = prm[g.w_alpha + i]; }
+    else if (i < kHeadWS2) { if (i == kHeadBAlpha) v = prm[g.b_alpha]; }
+    else if (i < kHeadBS2) { int s = (i - kHeadWS2) / kHalfMax, c = (i - kHeadWS2) % kHalfMax; if (s < g.sem_dim && c < H) v = prm[g.w_s2 + (int64_t)s * H + c]; }
+    else if (i < kHeadWRgb) { int s = i - kHeadBS2; if (s < g.sem_dim) v = prm[g.b_s2 + s]; }
+    else if (i < kHeadBRgb) { int k = (i - kHeadWRgb) / kHalfMax, c = (i - kHeadWRgb) % kHalfMax; if (c < H) v = prm[g.w_rgb + (int64_t)k * H + c]; }
+    else { int k = i - kHeadBRgb; if (k < 3) v = prm[g.b_rgb + k]; }
+    aux->heads[i] = v;
+  }
+  for (int i = t; i < kHalfMax * 28; i += nt) {
+    int r = i / 28, c = i % 28;
+    aux->w_vdir[r][c] = (r < H && c < g.encv) ? prm[g.w_views + (int64_t)r * (g.W + g.encv) + g.W + c] : 0.f;
+  }
+}
+__global__ void k_fix_scale(TcAux* aux) { aux->inv_scale[0] = 1.f / (stage_scale(aux, 0) * kActScale); }
+// one block per (slab, 64-row group): writes the hi (and lo) SWIZZLE_128B K-major image of the slab
+__global__ void k_pack_slabs(const float* __restrict__ prm, uint8_t* __restrict__ img, const PackPlan plan) {
+  const PackSlab ps = plan.s[blockIdx.x];
+  const TcAux* aux = reinterpret_cast<const TcAux*>(img);
+  const float scale = stage_scale(aux, ps.stage);
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < ps.n * 64; e += gridDim.y * blockDim.x) {
+    int n = e >> 6, k = e & 63;
+    float w = 0.f;
+    if (n < ps.nvalid && k < ps.kvalid) w = prm[ps.w_off + (int64_t)n * ps.ld + ps.col0 + k] * scale;
+    __half h = __float2half_rn(w);
+    size_t byte = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+    *reinterpret_cast<__half*>(img + ps.dst_hi + byte) = h;
+    if (ps.dst_lo >= 0) *reinterpret_cast<__half*>(img + ps.dst_lo + byte) = __float2half_rn(w - __half2float(h));
+  }
+}
+
+// ---- render kernel ------------------------------------------------------------------------------------
+struct TcParams {
+  TcProg prog[2];
+  const uint8_t* packed[2];
+  const float *rays_o, *rays_d, *near, *far;
+  NsosRandoms rnd;
+  unsigned long long seed;
+  NsosRenderOut out;
+  long long n_rays;
+  int Sc, K, Sf;
+  float perturb, noise_std;
+  int white_bkgd, exact, fine, C, sem_dim, C6, ML, nslots;
+};
+
+struct Smem {
+  uint8_t* ring; uint8_t* g_hi; uint8_t* g_lo;
+  float *rawbuf, *zc, *w0, *cdf, *bins, *zall, *zf, *dirbias, *sbias, *heads, *rayp, *encv;
+  uint64_t *full, *empty, *acc_full, *a_ready;
+  uint32_t* tmem_ptr;
+};
+constexpr int kRayP = 16;  // per ray: o[3] d[3] near far dnorm valid
+
+__host__ __device__ inline size_t carve_smem(uint8_t* base, int nslots, int Sc, int Sf, int C, Smem* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; size_t o = off; off += bytes; return o; };
+  size_t o_ring = take((size_t)nslots * kSlotBytes, 1024);
+  size_t o_ghi = take(kGBytes, 1024), o_glo = take(kGBytes, 1024);
+  size_t o_raw = take(sizeof(float) * 2 * Sf * C, 16);
+  size_t o_zc = take(sizeof(float) * 2 * Sc, 16), o_w0 = take(sizeof(float) * 2 * Sc, 16), o_cdf = take(sizeof(float) * 2 * Sc, 16),
+         o_bins = take(sizeof(float) * 2 * Sc, 16);
+  size_t o_zall = take(sizeof(float) * 2 * Sf, 16), o_zf = take(sizeof(float) * 2 * Sf, 16);
+  size_t o_db = take(sizeof(float) * 2 * 2 * kHalfMax, 16), o_sb = take(sizeof(float) * 2 * 256, 16);
+  size_t o_heads = take(sizeof(float) * 2 * kHeadFloats, 16), o_rayp = take(sizeof(float) * 2 * kRayP, 16),
+         o_encv = take(sizeof(float) * 2 * 28, 16);
+  size_t o_bar = take(sizeof(uint64_t) * (2 * kMaxSlots + 2), 8), o_tp = take(16, 16);
+  if (s) {
+    s->ring = base + o_ring; s->g_hi = base + o_ghi; s->g_lo = base + o_glo;
+    s->rawbuf = (float*)(base + o_raw); s->zc = (float*)(base + o_zc); s->w0 = (float*)(base + o_w0);
+    s->cdf = (float*)(base + o_cdf); s->bins = (float*)(base + o_bins); s->zall = (float*)(base + o_zall);
+    s->zf = (float*)(base + o_zf); s->dirbias = (float*)(base + o_db); s->sbias = (float*)(base + o_sb);
+    s->heads = (float*)(base + o_heads); s->rayp = (float*)(base + o_rayp); s->encv = (float*)(base + o_encv);
+    s->full = (uint64_t*)(base + o_bar); s->empty = s->full + kMaxSlots; s->acc_full = s->empty + kMaxSlots;
+    s->a_ready = s->acc_full + 1; s->tmem_ptr = (uint32_t*)(base + o_tp);
+  }
+  return off;
+}
+
+// ---- producer: stream one tile's worth of weight planes through the ring -------------------------------
+// Called by all 32 lanes of the producer warp; the elected lane issues the bulk copies.
+__device__ __forceinline__ void producer_tile(const TcProg& pg, const uint8_t* img, bool exact, const Smem& sm, int nslots,
+                                              uint32_t& chunk) {
+  const uint8_t* src = img + kAuxBytes;
+  for (int st = 0; st < pg.nst; ++st) {
+    const uint32_t bytes = (uint32_t)pg.st[st].n * 128u;
+    const int planes = pg.st[st].nslab * (exact ? 2 : 1);
+    for (int c = 0; c < planes; ++c) {
+      const uint32_t slot = chunk % nslots, par = (chunk / nslots) & 1u;
+      mbar_wait(smem_u32(&sm.empty[slot]), par ^ 1u, 100 + (int)slot);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(smem_u32(&sm.full[slot]), bytes);
+        bulk_g2s(smem_u32(sm.ring + (size_t)slot * kSlotBytes), src, bytes, smem_u32(&sm.full[slot]));
+      }
+      __syncwarp();
+      src += bytes;
+      ++chunk;
+    }
+  }
+}
+
+// ---- MMA issuer: all stages of one tile ------------------------------------------------------------------
+// Called by all 32 lanes of the MMA warp (uniform control flow); the elected lane issues every
+// tcgen05.mma and tcgen05.commit so that the commits track that lane's MMAs.
+__device__ __forceinline__ void mma_tile(const TcProg& pg, bool exact, const Smem& sm, int nslots, uint32_t tm, uint32_t& chunk,
+                                         uint32_t& it) {
+  const uint32_t g_hi = smem_u32(sm.g_hi), g_lo = smem_u32(sm.g_lo);
+  for (int st = 0; st < pg.nst; ++st) {
+    const TcStage& S = pg.st[st];
+    mbar_wait(smem_u32(sm.a_ready), it & 1u, 200 + st);
+    ++it;
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(S.n);
+    uint32_t accum = 0;
+    for (int j = 0; j < S.nslab; ++j) {
+      const int asrc = S.asrc[j];
+      {  // W_hi plane: A_hi.W_hi (+ A_lo.W_hi)
+        const uint32_t slot = chunk % nslots, par = (chunk / nslots) & 1u;
+        mbar_wait(smem_u32(&sm.full[slot]), par, 300 + (int)slot);
+        tc_fence_after();
+        const uint32_t b = smem_u32(sm.ring + (size_t)slot * kSlotBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bd = make_sw128_desc(b + ks * 32);
+            const uint32_t acc = (ks == 0) ? accum : 1u;
+            if (asrc == A_GAMMA) {
+              umma_ss(tm + kColD, make_sw128_desc(g_hi + ks * 32), bd, idesc, acc);
+              if (exact) umma_ss(tm + kColD, make_sw128_desc(g_lo + ks * 32), bd, idesc, 1);
+            } else {
+              umma_ts(tm + kColD, tm + kColAhi + asrc * 32 + ks * 8, bd, idesc, acc);
+              if (exact) umma_ts(tm + kColD, tm + kColAlo + asrc * 32 + ks * 8, bd, idesc, 1);
+            }
+          }
+          umma_commit(smem_u32(&sm.empty[slot]));
+        }
+        __syncwarp();
+        accum = 1;
+        ++chunk;
+      }
+      if (exact) {  // W_lo plane: A_hi.W_lo
+        const uint32_t slot = chunk % nslots, par = (chunk / nslots) & 1u;
+        mbar_wait(smem_u32(&sm.full[slot]), par, 400 + (int)slot);
+        tc_fence_after();
+        const uint32_t b = smem_u32(sm.ring + (size_t)slot * kSlotBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bd = make_sw128_desc(b + ks * 32);
+            if (asrc == A_GAMMA) umma_ss(tm + kColD, make_sw128_desc(g_hi + ks * 32), bd, idesc, 1);
+            else umma_ts(tm + kColD, tm + kColAhi + asrc * 32 + ks * 8, bd, idesc, 1);
+          }
+          umma_commit(smem_u32(&sm.empty[slot]));
+        }
+        __syncwarp();
+        ++chunk;
+      }
+    }
+    if (elect_one()) umma_commit(smem_u32(sm.acc_full));
+    __syncwarp();
+  }
+}
+
+// ---- worker helpers -----------------------------------------------------------------------------------------
+// write one row (64 fp16, hi and lo planes) of a K-major SWIZZLE_128B tile from fp32 values (already x kActScale)
+__device__ __forceinline__ void store_row_sw128(uint8_t* hi_tile, uint8_t* lo_tile, int row, const float* v, bool exact) {
+  const size_t rbase = (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a0 = v[8 * j + 2 * q], a1 = v[8 * j + 2 * q + 1];
+      __half2 hh = __floats2half2_rn(a0, a1);
+      float2 hf = __half22float2(hh);
+      __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+      h[q] = *reinterpret_cast<uint32_t*>(&hh);
+      l[q] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    const size_t off = rbase + (size_t)((j ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (exact) *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// One 32-column chunk of an epilogue.  Reads D, applies x = acc*inv + bias (+relu), feeds the fp32 head
+// accumulators and/or writes the next A operand (fp16 hi/lo planes) back to TMEM.
+template <int KIND, bool EXACT>
+__device__ __forceinline__ void epi_chunk(uint32_t tm_lane, int c0, float inv, const float* __restrict__ bias,
+                                          const float* __restrict__ hw, int sem_dim, float* hacc, float* __restrict__ gout) {
+  uint32_t v[32];
+  tmem_ld32(tm_lane + kColD + c0, v);
+  tmem_wait_ld();
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float x0 = fmaf(__uint_as_float(v[j]), inv, bias[c0 + j]);
+    float x1 = fmaf(__uint_as_float(v[j + 1]), inv, bias[c0 + j + 1]);
+    if (KIND != EPI_FEAT && KIND != EPI_RAW) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+    if (KIND == EPI_HIDDEN_SIGMA) {
+      hacc[0] = fmaf(hw[kHeadWAlpha + c0 + j], x0, hacc[0]);
+      hacc[0] = fmaf(hw[kHeadWAlpha + c0 + j + 1], x1, hacc[0]);
+    } else if (KIND == EPI_SEM) {
+#pragma unroll
+      for (int s = 0; s < kSemMax; ++s)
+        if (s < sem_dim) {
+          hacc[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j], x0, hacc[s]);
+          hacc[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j + 1], x1, hacc[s]);
+        }
+    } else if (KIND == EPI_RGB) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        hacc[k] = fmaf(hw[kHeadWRgb + k * kHalfMax + c0 + j], x0, hacc[k]);
+        hacc[k] = fmaf(hw[kHeadWRgb + k * kHalfMax + c0 + j + 1], x1, hacc[k]);
+      }
+    } else if (KIND == EPI_RAW) {
+      gout[c0 + j] = x0; gout[c0 + j + 1] = x1;
+    }
+    if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FEAT) {
+      float a0 = x0 * kActScale, a1 = x1 * kActScale;
+      __half2 hh = __floats2half2_rn(a0, a1);
+      hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+      if (EXACT) {
+        float2 hf = __half22float2(hh);
+        __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        lo[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
+      }
+    }
+  }
+  if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FEAT) {
+    tmem_st16(tm_lane + kColAhi + (c0 >> 1), hi);
+    if (EXACT) tmem_st16(tm_lane + kColAlo + (c0 >> 1), lo);
+  }
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void epilogue(int kind, int n, uint32_t tm_lane, float inv, const float* bias, const float* hw, int sem_dim,
+                                         float* hacc, float* gout) {
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    switch (kind) {
+      case EPI_HIDDEN: epi_chunk<EPI_HIDDEN, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
+      case EPI_HIDDEN_SIGMA: epi_chunk<EPI_HIDDEN_SIGMA, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
+      case EPI_SEM: epi_chunk<EPI_SEM, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
+      case EPI_FEAT: epi_chunk<EPI_FEAT, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
+      case EPI_RGB: epi_chunk<EPI_RGB, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
+      default: epi_chunk<EPI_RAW, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
+    }
+  }
+}
+
+__device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int warp, int lane) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nslots; ++i) { mbar_init(smem_u32(&sm.full[i]), 1); mbar_init(smem_u32(&sm.empty[i]), 1); }
+    mbar_init(smem_u32(sm.acc_full), 1);
+    mbar_init(smem_u32(sm.a_ready), kWorkers);
+    fence_mbar_init();
+  }
+  if (warp == 4) { tmem_alloc(smem_u32(sm.tmem_ptr), kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Smem sm;
+  carve_smem(base, P.nslots, P.Sc, P.Sf, P.C, &sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+  init_pipeline(sm, P.nslots, warp, lane);
+  const uint32_t tm = *sm.tmem_ptr;
+  const long long n_pairs = (P.n_rays + 1) / 2;
+  const int npass = P.fine ? 2 : 1;
+
+  if (warp == 5) {
+    // ================= producer =================
+    {
+      uint32_t chunk = 0;
+      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int pass = 0; pass < npass; ++pass) {
+          const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
+          for (int tile = 0; tile < ntiles; ++tile) producer_tile(P.prog[pass], P.packed[pass], EXACT, sm, P.nslots, chunk);
+        }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer =================
+    {
+      uint32_t chunk = 0, it = 0;
+      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int pass = 0; pass < npass; ++pass) {
+          const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
+          for (int tile = 0; tile < ntiles; ++tile) mma_tile(P.prog[pass], EXACT, sm, P.nslots, tm, chunk, it);
+        }
+    }
+  } else {
+    // ================= row workers (128 threads = 128 TMEM lanes) =================
+    const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16);
+    uint32_t it_acc = 0, it_bias = 0;
+    // head weights of both nets -> smem (constant for the launch)
+    for (int net = 0; net < npass; ++net) {
+      const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[net]);
+      for (int i = t; i < kHeadFloats; i += kWorkers) sm.heads[net * kHeadFloats + i] = __ldg(&aux->heads[i]);
+    }
+    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      named_bar_sync(1, kWorkers);   // previous pair's compositing has finished with the shared buffers
+      // ---- per-pair ray setup: o, d, near, far, |d|, gamma_v(d/|d|)
+      if (t < 2) {
+        long long r = pair * 2 + t;
+        bool valid = r < P.n_rays;
+        long long rr = valid ? r : pair * 2;
+        float* rp = sm.rayp + t * kRayP;
+        float d0 = P.rays_d[rr * 3], d1 = P.rays_d[rr * 3 + 1], d2 = P.rays_d[rr * 3 + 2];
+        rp[0] = P.rays_o[rr * 3]; rp[1] = P.rays_o[rr * 3 + 1]; rp[2] = P.rays_o[rr * 3 + 2];
+        rp[3] = d0; rp[4] = d1; rp[5] = d2; rp[6] = P.near[rr]; rp[7] = P.far[rr];
+        float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+        rp[8] = nrm; rp[9] = valid ? 1.f : 0.f;
+        float vd[3] = {__fdiv_rn(d0, nrm), __fdiv_rn(d1, nrm), __fdiv_rn(d2, nrm)};
+        float e[3 + 6 * 4 + 1];
+        encode3(vd, P.prog[0].Lv, e);
+        for (int c = 0; c < 28; ++c) sm.encv[t * 28 + c] = (c < P.prog[0].encv) ? e[c] : 0.f;
+      }
+      named_bar_sync(1, kWorkers);
+      // view-direction half of views_linears.0 folded into a per-ray bias (fp32): dirbias[net][ray][j]
+      for (int idx = t; idx < npass * 2 * kHalfMax; idx += kWorkers) {
+        int net = idx / (2 * kHalfMax), rl = (idx / kHalfMax) & 1, j = idx % kHalfMax;
+        const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[net]);
+        const TcProg& pg = P.prog[net];
+        float acc = 0.f;
+        if (j < pg.H2) {
+          acc = __ldg(&aux->bias[pg.nst - 1][j]);
+          for (int c = 0; c < pg.encv; ++c) acc = fmaf(__ldg(&aux->w_vdir[j][c]), sm.encv[rl * 28 + c], acc);
+        }
+        sm.dirbias[idx] = acc;
+      }
+      named_bar_sync(1, kWorkers);
+
+      for (int pass = 0; pass < npass; ++pass) {
+        const TcProg& pg = P.prog[pass];
+        const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[pass]);
+        const float* hw = sm.heads + pass * kHeadFloats;
+        const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
+        for (int tile = 0; tile < ntiles; ++tile) {
+          // ---- tile setup: sample position, point, gamma(x) -> swizzled smem A tile
+          const int q = tile * 128 + t;
+          const bool rowvalid = q < 2 * S;
+          const int rl = rowvalid ? q / S : 0, i = rowvalid ? q % S : 0;
+          const float* rp = sm.rayp + rl * kRayP;
+          const long long ray = pair * 2 + rl;
+          {
+            float z;
+            if (pass == 0) {
+              const bool pert = P.perturb > 0.f;
+              float tr = 0.f;
+              if (pert) tr = (P.rnd.t_rand && rp[9] > 0.f) ? P.rnd.t_rand[ray * P.Sc + i] : rng_uniform(P.seed, ray, RNG_T_RAND, i);
+              z = z_stratified(rp[6], rp[7], i, S, pert, tr);
+              if (rowvalid) sm.zc[rl * P.Sc + i] = z;
+            } else {
+              z = sm.zf[rl * P.Sf + i];
+            }
+            float x[3] = {pt_coord(rp[0], rp[3], z), pt_coord(rp[1], rp[4], z), pt_coord(rp[2], rp[5], z)};
+            float e[64];
+            encode3(x, pg.Lp, e);
+#pragma unroll
+            for (int c = 0; c < 64; ++c) e[c] = (rowvalid && c < pg.enc) ? e[c] * kActScale : 0.f;
+            store_row_sw128(sm.g_hi, sm.g_lo, t, e, EXACT);
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(smem_u32(sm.a_ready));
+
+          float sigma = 0.f, semv[kSemMax] = {0.f, 0.f, 0.f, 0.f}, rgbv[3] = {0.f, 0.f, 0.f};
+          for (int st = 0; st < pg.nst; ++st) {
+            const TcStage& Sg = pg.st[st];
+            // stage bias -> smem (double buffered), except the view layer whose bias is the per-ray dirbias
+            float* sb = sm.sbias + (it_bias & 1u) * 256;
+            ++it_bias;
+            for (int c = t; c < 256; c += kWorkers) sb[c] = __ldg(&aux->bias[st][c]);
+            const float inv = __ldg(&aux->inv_scale[st]);
+            named_bar_sync(1, kWorkers);
+            const float* bias = (Sg.epi == EPI_RGB) ? (sm.dirbias + (pass * 2 + rl) * kHalfMax) : sb;
+            mbar_wait(smem_u32(sm.acc_full), it_acc & 1u, 500 + st);
+            ++it_acc;
+            tc_fence_after();
+            float* hacc = (Sg.epi == EPI_HIDDEN_SIGMA) ? &sigma : (Sg.epi == EPI_SEM) ? semv : rgbv;
+            epilogue<EXACT>(Sg.epi, Sg.n, tm_lane, inv, bias, hw, P.sem_dim, hacc, nullptr);
+            if (st + 1 < pg.nst) {
+              if (Sg.epi != EPI_SEM) tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(smem_u32(sm.a_ready));
+            }
+          }
+          // ---- raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
+          if (rowvalid) {
+            float* rw = sm.rawbuf + (size_t)q * P.C;
+            rw[0] = rgbv[0] + hw[kHeadBRgb]; rw[1] = rgbv[1] + hw[kHeadBRgb + 1]; rw[2] = rgbv[2] + hw[kHeadBRgb + 2];
+            rw[3] = sigma + hw[kHeadBAlpha];
+            for (int s = 0; s < P.sem_dim; ++s) rw[4 + s] = semv[s] + hw[kHeadBS2 + s];
+            float* graw = (pass == 0 && P.fine) ? P.out.raw0 : P.out.raw;
+            if (graw && rp[9] > 0.f) {
+              float* g = graw + ((size_t)ray * S + i) * P.C;
+              for (int c = 0; c < P.C; ++c) g[c] = rw[c];
+            }
+          }
+        }
+        // ---- compositing (+ resampling after the coarse pass): warp r owns ray r of the pair
+        named_bar_sync(1, kWorkers);
+        if (warp < 2) {
+          const float* rp = sm.rayp + warp * kRayP;
+          const long long ray = pair * 2 + warp;
+          const bool valid = rp[9] > 0.f;
+          const bool coarse_of_two = (pass == 0 && P.fine);
+          RayPass rpx;
+          rpx.raw = sm.rawbuf + (size_t)warp * S * P.C;
+          rpx.z = pass ? sm.zf + warp * P.Sf : sm.zc + warp * P.Sc;
+          const float* nz = pass ? P.rnd.noise1 : P.rnd.noise0;
+          rpx.noise = (nz && valid) ? nz + ray * S : nullptr;
+          rpx.noise_std = P.noise_std; rpx.seed = P.seed; rpx.ray = ray; rpx.rng_stream = pass ? RNG_NOISE1 : RNG_NOISE0;
+          rpx.dnorm = rp[8]; rpx.S = S; rpx.C = P.C; rpx.sem_dim = P.sem_dim; rpx.white_bkgd = P.white_bkgd;
+          float scratch_maps[6 + kSemMax];
+          float* maps = valid ? P.out.maps + (size_t)ray * P.ML + (coarse_of_two ? P.C6 : 0) : nullptr;
+          float* wsm = sm.w0 + warp * P.Sc;   // coarse weights stay in smem for the resampling
+          float* gw = coarse_of_two ? P.out.weights0 : P.out.weights;
+          float* wout = (pass == 0) ? wsm : ((gw && valid) ? gw + ray * S : nullptr);
+          warp_composite(rpx, lane, maps ? maps : scratch_maps, wout);
+          __syncwarp();
+          if (pass == 0) {
+            if (gw && valid) for (int k = lane; k < S; k += 32) gw[ray * S + k] = wsm[k];
+            float* gz = coarse_of_two ? P.out.z_vals0 : P.out.z_vals;
+            if (gz && valid) for (int k = lane; k < S; k += 32) gz[ray * S + k] = rpx.z[k];
+            if (P.fine) {
+              ImportanceIO io;
+              io.z0 = rpx.z; io.w0 = wsm; io.cdf = sm.cdf + warp * P.Sc; io.bins = sm.bins + warp * P.Sc;
+              io.zall = sm.zall + warp * P.Sf; io.zsorted = sm.zf + warp * P.Sf;
+              io.u = (P.rnd.u && valid) ? P.rnd.u + ray * P.K : nullptr;
+              io.z_samples = (P.out.z_samples && valid) ? P.out.z_samples + ray * P.K : nullptr;
+              io.inds = (P.out.inds && valid) ? P.out.inds + ray * P.K : nullptr;
+              io.z_std = valid ? P.out.maps + (size_t)ray * P.ML + 2 * P.C6 : nullptr;
+              io.Sc = P.Sc; io.K = P.K; io.det = !(P.perturb > 0.f); io.seed = P.seed; io.ray = ray;
+              warp_importance(io, lane);
+              if (P.out.z_vals && valid) for (int k = lane; k < P.Sf; k += 32) P.out.z_vals[ray * P.Sf + k] = io.zsorted[k];
+            }
+          }
+        }
+        named_bar_sync(1, kWorkers);
+      }
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tm, kTmemCols);
+}
+
+// ---- self test: D[128,N] = A[128,K] . W[N,K]^T through the same producer / MMA / epilogue code ----------------
+struct SelfParams {
+  TcProg prog;
+  const uint8_t* packed;
+  const float* a;
+  float* d;
+  int K, N, a_in_tmem, nslots;
+};
+template <bool EXACT>
+__global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant__ SelfParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Smem sm;
+  carve_smem(base, P.nslots, 2, 2, 8, &sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+  init_pipeline(sm, P.nslots, warp, lane);
+  const uint32_t tm = *sm.tmem_ptr;
+  if (warp == 5) {
+    uint32_t chunk = 0;
+    producer_tile(P.prog, P.packed, EXACT, sm, P.nslots, chunk);
+  } else if (warp == 4) {
+    uint32_t chunk = 0, it = 0;
+    mma_tile(P.prog, EXACT, sm, P.nslots, tm, chunk, it);
+  } else {
+    const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16);
+    const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed);
+    if (P.a_in_tmem) {
+      for (int c0 = 0; c0 < P.K; c0 += 32) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a0 = P.a[(size_t)t * P.K + c0 + j] * kActScale, a1 = P.a[(size_t)t * P.K + c0 + j + 1] * kActScale;
+          __half2 hh = __floats2half2_rn(a0, a1);
+          float2 hf = __half22float2(hh);
+          __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+          hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          lo[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
+        }
+        tmem_st16(tm_lane + kColAhi + (c0 >> 1), hi);
+        if (EXACT) tmem_st16(tm_lane + kColAlo + (c0 >> 1), lo);
+      }
+      tmem_wait_st();
+    } else {
+      float e[64];
+      for (int c = 0; c < 64; ++c) e[c] = (c < P.K) ? P.a[(size_t)t * P.K + c] * kActScale : 0.f;
+      store_row_sw128(sm.g_hi, sm.g_lo, t, e, EXACT);
+      fence_proxy_async_smem();
+    }
+    for (int c = t; c < 256; c += kWorkers) sm.sbias[c] = 0.f;
+    named_bar_sync(1, kWorkers);
+    tc_fence_before();
+    mbar_arrive(smem_u32(sm.a_ready));
+    mbar_wait(smem_u32(sm.acc_full), 0, 600);
+    tc_fence_after();
+    float dummy[4];
+    epilogue<EXACT>(EPI_RAW, P.N, tm_lane, __ldg(&aux->inv_scale[0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)t * P.N);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tm, kTmemCols);
+}
+
+int run_pack(const PackPlan& plan, const NetGeom* g, const float* params, void* packed, cudaStream_t st) {
+  TcAux* aux = reinterpret_cast<TcAux*>(packed);
+  NSOS_CHECK_CUDA(cudaMemsetAsync(aux->absmax_bits, 0, sizeof(aux->absmax_bits), st));
+  k_pack_absmax<<<dim3(32, plan.nst), 256, 0, st>>>(params, aux, plan);
+  if (g) k_pack_aux<<<16, 256, 0, st>>>(params, aux, plan, *g);
+  k_pack_slabs<<<dim3(plan.nslab, 8), 256, 0, st>>>(params, reinterpret_cast<uint8_t*>(packed), plan);
+  NSOS_CHECK_CUDA(cudaGetLastError());
+  return NSOS_OK;
+}
+
+int max_optin_smem() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+  return v;
+}
+
+}  // namespace
+
+// ---- library-internal entry points ---------------------------------------------------------------------------
+size_t tc_packed_bytes(const NsosNetDesc& net, int mode) {
+  NetGeom g;
+  if (!make_geom(net, g) || !tc_supported(g, nullptr)) return 0;
+  TcProg p; PackPlan plan;
+  build_prog(g, mode == NSOS_MODE_TC_EXACT, p, plan);
+  return (size_t)plan.total_bytes;
+}
+
+int tc_pack_weights(const NsosNetDesc& net, const float* params, void* packed, int mode, cudaStream_t st) {
+  NetGeom g;
+  NSOS_REQUIRE(make_geom(net, g), NSOS_ERR_UNSUPPORTED, "invalid net descriptor");
+  const char* why = "";
+  NSOS_REQUIRE(tc_supported(g, &why), NSOS_ERR_UNSUPPORTED, "%s", why);
+  TcProg p; PackPlan plan;
+  build_prog(g, mode == NSOS_MODE_TC_EXACT, p, plan);
+  return run_pack(plan, &g, params, packed, st);
+}
+
+size_t tc_render_workspace_bytes(const NsosRenderCfg&, int64_t) { return 256; }
+
+int tc_render_fwd(const NsosRenderCfg& cfg, const float* /*pc*/, const float* /*pf*/, const void* packed_c, const void* packed_f,
+                  const float* rays_o, const float* rays_d, const float* near, const float* far, const NsosRandoms* rnd,
+                  uint64_t seed, const NsosRenderOut& out, void* /*workspace*/, size_t /*workspace_bytes*/, int64_t n_rays,
+                  cudaStream_t st) {
+  NetGeom gc, gf;
+  NSOS_REQUIRE(make_geom(cfg.coarse, gc), NSOS_ERR_UNSUPPORTED, "invalid coarse net descriptor");
+  const bool fine = cfg.n_importance > 0;
+  if (fine) NSOS_REQUIRE(make_geom(cfg.fine, gf), NSOS_ERR_UNSUPPORTED, "invalid fine net descriptor"); else gf = gc;
+  const char* why = "";
+  NSOS_REQUIRE(tc_supported(gc, &why) && tc_supported(gf, &why), NSOS_ERR_UNSUPPORTED, "%s", why);
+  NSOS_REQUIRE(gc.C == gf.C && gc.Lv == gf.Lv, NSOS_ERR_UNSUPPORTED, "coarse and fine nets must share output channels and multires_views");
+  const int Sc = cfg.n_samples, K = cfg.n_importance, Sf = Sc + K;
+  NSOS_REQUIRE(Sc >= 2 && Sc <= 128 && Sf <= kMaxS, NSOS_ERR_UNSUPPORTED, "tcgen05 path needs 2<=n_samples<=128 and n_samples+n_importance<=256");
+  const bool exact = cfg.mode == NSOS_MODE_TC_EXACT;
+  TcParams P;
+  memset(&P, 0, sizeof(P));
+  PackPlan plan;
+  build_prog(gc, exact, P.prog[0], plan);
+  build_prog(gf, exact, P.prog[1], plan);
+  P.packed[0] = (const uint8_t*)packed_c; P.packed[1] = (const uint8_t*)packed_f;
+  P.rays_o = rays_o; P.rays_d = rays_d; P.near = near; P.far = far;
+  if (rnd) P.rnd = *rnd;
+  P.seed = seed; P.out = out; P.n_rays = n_rays; P.Sc = Sc; P.K = K; P.Sf = fine ? Sf : Sc;
+  P.perturb = cfg.perturb; P.noise_std = cfg.raw_noise_std; P.white_bkgd = cfg.white_bkgd; P.exact = exact; P.fine = fine;
+  P.C = gc.C; P.sem_dim = gc.sem_dim; P.C6 = 6 + gc.sem_dim; P.ML = 2 * P.C6 + 1;
+  const int smem_max = max_optin_smem();
+  NSOS_REQUIRE(smem_max >= 200 * 1024, NSOS_ERR_DEVICE, "device offers only %d B of opt-in shared memory", smem_max);
+  int nslots = kMaxSlots;
+  size_t need = 0;
+  for (; nslots >= 2; --nslots) {
+    need = carve_smem(nullptr, nslots, Sc, P.Sf, P.C, nullptr) + 1024;
+    if ((int)need <= smem_max) break;
+  }
+  NSOS_REQUIRE(nslots >= 2, NSOS_ERR_UNSUPPORTED, "shared memory budget exceeded");
+  P.nslots = nslots;
+  int dev = 0, sms = 0;
+  NSOS_CHECK_CUDA(cudaGetDevice(&dev));
+  NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long n_pairs = (n_rays + 1) / 2;
+  const int grid = (int)std::min<long long>(n_pairs, sms);
+  NSOS_CHECK_CUDA(cudaMemsetAsync(out.maps, 0, sizeof(float) * n_rays * P.ML, st));
+  if (exact) {
+    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    k_render_tc<true><<<grid, kThreads, need, st>>>(P);
+  } else {
+    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    k_render_tc<false><<<grid, kThreads, need, st>>>(P);
+  }
+  NSOS_CHECK_CUDA(cudaGetLastError());
+  return NSOS_OK;
+}
+
+int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,
+                cudaStream_t st) {
+  NSOS_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256, NSOS_ERR_BAD_ARG, "selftest: N must be a multiple of 32 in [32,256]");
+  NSOS_REQUIRE(a_in_tmem ? (K % 64 == 0 && K >= 64 && K <= 256) : (K >= 1 && K <= 64), NSOS_ERR_BAD_ARG,
+               "selftest: K must be 64..256 step 64 (TMEM A) or <=64 (SMEM A)");
+  const bool exact = mode == NSOS_MODE_TC_EXACT;
+  SelfParams P;
+  memset(&P, 0, sizeof(P));
+  PackPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  P.prog.nst = 1; P.prog.W = N;
+  TcStage& S = P.prog.st[0];
+  S.n = N; S.epi = EPI_RAW; S.nslab = 0;
+  int64_t off = (int64_t)kAuxBytes;
+  const int nsl = a_in_tmem ? K / 64 : 1;
+  for (int j = 0; j < nsl; ++j) {
+    S.asrc[S.nslab++] = a_in_tmem ? j : A_GAMMA;
+    PackSlab& ps = plan.s[plan.nslab++];
+    ps.w_off = 0; ps.ld = K; ps.col0 = 64 * j; ps.kvalid = a_in_tmem ? 64 : K; ps.nvalid = N; ps.n = N; ps.stage = 0;
+    ps.dst_hi = off; off += (int64_t)N * 128;
+    ps.dst_lo = -1;
+    if (exact) { ps.dst_lo = off; off += (int64_t)N * 128; }
+  }
+  plan.nst = 1; plan.st_w_off[0] = 0; plan.st_rows[0] = N; plan.st_ld[0] = K; plan.st_b_off[0] = 0; plan.st_nb[0] = 0;
+  plan.total_bytes = off;
+  NSOS_REQUIRE(scratch_bytes >= (size_t)off, NSOS_ERR_WORKSPACE, "selftest scratch too small: need %lld", (long long)off);
+  NSOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, kAuxBytes, st));
+  int rc = run_pack(plan, nullptr, w, scratch, st);
+  if (rc) return rc;
+  // inv_scale for the single stage (k_pack_aux is skipped: no net geometry here)
+  k_fix_scale<<<1, 1, 0, st>>>(reinterpret_cast<TcAux*>(scratch));
+  P.packed = (const uint8_t*)scratch; P.a = a; P.d = d; P.K = K; P.N = N; P.a_in_tmem = a_in_tmem; P.nslots = 4;
+  size_t need = carve_smem(nullptr, P.nslots, 2, 2, 8, nullptr) + 1024;
+  if (exact) {
+    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_selftest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    k_selftest<true><<<1, kThreads, need, st>>>(P);
+  } else {
+    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_selftest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    k_selftest<false><<<1, kThreads, need, st>>>(P);
+  }
+  NSOS_CHECK_CUDA(cudaGetLastError());
+  return NSOS_OK;
+}
+
+}  // namespace nsos

@@ -1,0 +1,254 @@
+"""Drop-in for models/nerf_net.py of the reference: same ctor (nerf_net.py:22-24), same
+forward(ray_batch, bound_batch, **kwargs) -> dict (:132-195), same render_rays (:71-130), same
+state_dict keys; the body is one call into libnerfsos.so per forward (nsos_render_fwd) and one per
+backward (nsos_render_bwd).
+
+Extra, non-reference keyword arguments (all optional):
+    mode     'auto' | 'exact' | 'fast' | 'simt'   (ctor or forward kwarg; env NSOS_MODE)
+             exact = tcgen05 fp16 hi/lo split (fp32-equivalent), fast = single fp16 pass,
+             simt = fp32 CUDA-core path, auto = exact when the geometry is covered else simt
+    randoms  dict(t_rand, noise0, u, noise1) of CUDA tensors: inject the four random draws the reference
+             makes (parity tests); default is the in-kernel Philox stream seeded from torch's CPU generator
+    retz     also return 'z_vals'/'z_vals0', 'z_samples', 'inds'
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .nerf_mlp import NeRFMLP
+
+_MAP_KEYS = ("rgb", "disp", "acc", "depth")
+
+
+def _cfg(net: "NeRFNet", n_samples, n_importance, perturb, raw_noise_std, mode) -> _lib.RenderCfg:
+    return _lib.RenderCfg(net.nerf.desc(), net.nerf_fine.desc(), int(n_samples), int(n_importance), float(perturb),
+                          float(raw_noise_std), int(bool(net.white_bkgd)), int(mode))
+
+
+class _RenderFn(torch.autograd.Function):
+    """Kernel A forward/backward as one autograd node.  Inputs after `ctx_args` are the parameters of the
+    coarse net then the fine net (flat-buffer order) so autograd routes gradients to the nn.Parameters."""
+
+    @staticmethod
+    def forward(ctx, net, cfg, rays_o, rays_d, near, far, rnd, seed, want, n_coarse_params, *params):
+        L = _lib.lib()
+        dev = rays_o.device
+        N = rays_o.shape[0]
+        fine = cfg.n_importance > 0
+        Sc, K = cfg.n_samples, cfg.n_importance
+        Sf = Sc + K
+        sem = net.nerf.mlp.sem_dim if net.nerf.mlp.use_semantics else 0
+        Cr, C6 = 4 + sem, 6 + sem
+        f32 = dict(dtype=torch.float32, device=dev)
+        maps = torch.empty(N, 2 * C6 + 1, **f32)
+        S_last = Sf if fine else Sc
+        out = dict(maps=maps, weights=torch.empty(N, S_last, **f32))
+        if fine:
+            out["weights0"] = torch.empty(N, Sc, **f32)
+        if want["raw"]:
+            out["raw"] = torch.empty(N, S_last, Cr, **f32)
+            if fine:
+                out["raw0"] = torch.empty(N, Sc, Cr, **f32)
+        need_z = want["z"] or any(p.requires_grad for p in params)
+        if need_z:
+            out["z_vals"] = torch.empty(N, S_last, **f32)
+            if fine:
+                out["z_vals0"] = torch.empty(N, Sc, **f32)
+        if want["z"] and fine:
+            out["z_samples"] = torch.empty(N, K, **f32)
+            out["inds"] = torch.empty(N, K, dtype=torch.int64, device=dev)
+        ro = _lib.RenderOut(*[_lib.ptr(out.get(k)) for k in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
+                                                             "z_samples", "inds")])
+        rs = _lib.Randoms(*[_lib.ptr(rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
+        flat_c, flat_f = net.nerf.flat_params(), net.nerf_fine.flat_params()
+        pk_c = net.nerf.packed(cfg.mode, force=net.training)
+        pk_f = net.nerf_fine.packed(cfg.mode, force=net.training) if fine else pk_c
+        wsz = L.nsos_render_workspace_bytes(cfg, N)
+        ws = net._workspace(wsz, dev)
+        _lib.check(L.nsos_render_fwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
+                                     _lib.ptr(rays_d), _lib.ptr(near), _lib.ptr(far), C.byref(rs), seed, C.byref(ro), _lib.ptr(ws),
+                                     ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_fwd")
+        ctx.net, ctx.cfg, ctx.rnd, ctx.seed, ctx.n_coarse = net, cfg, rnd, seed, n_coarse_params
+        ctx.shapes = [p.shape for p in params]
+        ctx.req = [p.requires_grad for p in params]
+        ctx.save_for_backward(rays_o, rays_d, out.get("z_vals0"), out.get("z_vals"))
+        ctx.names = list(out.keys())
+        outs = tuple(out[k] for k in ctx.names)
+        ctx.mark_non_differentiable(*[o for k, o in zip(ctx.names, outs) if k != "maps"])
+        ctx.set_materialize_grads(False)
+        want["names"] = ctx.names          # read back by render_rays (a Function may only return tensors cleanly)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        g_maps = gouts[ctx.names.index("maps")]
+        n_fixed = 10
+        if g_maps is None or not any(ctx.req):
+            return (None,) * (n_fixed + len(ctx.req))
+        L = _lib.lib()
+        net, cfg = ctx.net, ctx.cfg
+        rays_o, rays_d, z0, z1 = ctx.saved_tensors
+        dev = rays_o.device
+        N = rays_o.shape[0]
+        fine = cfg.n_importance > 0
+        flat_c, flat_f = net.nerf.flat_params(), net.nerf_fine.flat_params()
+        g_c = torch.zeros_like(flat_c)
+        g_f = torch.zeros_like(flat_f) if fine else g_c
+        names_c = [n for n, _ in net.nerf.mlp.named_parameters()]
+        # trunk gradients are needed iff any non-semantic parameter requires grad (run_nerf.py:307-318)
+        plist = list(net.nerf._flat.params) + (list(net.nerf_fine._flat.params) if fine else [])
+        sem_ids = set()
+        for m in ([net.nerf.mlp] + ([net.nerf_fine.mlp] if fine else [])):
+            if m.use_semantics:
+                sem_ids |= {id(p) for p in m.semantic_linear.parameters()}
+        trunk = int(any(r and id(p) not in sem_ids for p, r in zip(plist, ctx.req)))
+        rs = _lib.Randoms(*[_lib.ptr(ctx.rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
+        wsz = L.nsos_render_bwd_workspace_bytes(cfg, N)
+        ws = net._workspace(wsz, dev)
+        _lib.check(L.nsos_render_bwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(z0),
+                                     _lib.ptr(z1), C.byref(rs), ctx.seed, _lib.ptr(g_maps.contiguous()), _lib.ptr(g_c), _lib.ptr(g_f),
+                                     trunk, _lib.ptr(ws), ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_bwd")
+        grads = []
+        offs = list(net.nerf._flat.offsets) + (list(net.nerf_fine._flat.offsets) if fine else [])
+        for i, (shape, req) in enumerate(zip(ctx.shapes, ctx.req)):
+            if not req:
+                grads.append(None)
+                continue
+            g = g_c if i < ctx.n_coarse else g_f
+            n = 1
+            for s in shape:
+                n *= s
+            grads.append(g[offs[i]:offs[i] + n].view(shape))
+        return (None,) * n_fixed + tuple(grads)
+
+
+class NeRFNet(nn.Module):
+
+    def __init__(self, netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, N_samples=64, N_importance=64,
+                 viewdirs=True, use_embed=True, multires=10, multires_views=4, conv_embed=False, ray_chunk=1024 * 32,
+                 pts_chuck=1024 * 64, perturb=1., raw_noise_std=0., white_bkgd=False, use_semantics=False, sem_layer=2,
+                 sem_dim=2, sem_with_coord=False, sem_with_geo=False, mode=None):
+        super().__init__()
+        self.use_semantics = use_semantics
+        self.N_samples, self.N_importance = N_samples, N_importance
+        self.white_bkgd = white_bkgd
+        self.chunk = ray_chunk            # accepted for compatibility; results never depended on it
+        self.use_viewdirs = viewdirs
+        self.mode = mode or os.environ.get("NSOS_MODE", "auto")
+        kw = dict(input_dim=3, output_dim=4, skips=[4], viewdirs=viewdirs, use_embed=use_embed, multires=multires,
+                  multires_views=multires_views, conv_embed=conv_embed, netchunk=pts_chuck, use_semantics=use_semantics,
+                  sem_with_coord=sem_with_coord, sem_layer=sem_layer, sem_dim=sem_dim, sem_with_geo=sem_with_geo)
+        self.nerf = NeRFMLP(net_depth=netdepth, net_width=netwidth, **kw)
+        self.nerf_fine = self.nerf                                                    # nerf_net.py:49
+        if N_importance > 0:
+            self.nerf_fine = NeRFMLP(net_depth=netdepth_fine, net_width=netwidth_fine, **kw)
+        self.render_kwargs_train = {'N_importance': N_importance, 'N_samples': N_samples, 'perturb': perturb,
+                                    'raw_noise_std': raw_noise_std, 'retraw': True, 'retpts': False}
+        self.render_kwargs_test = self.render_kwargs_train.copy()
+        self.render_kwargs_test['perturb'] = 0.
+        self.render_kwargs_test['raw_noise_std'] = 0.
+        self._ws = None
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    def _workspace(self, nbytes, device):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+            self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        return self._ws
+
+    def resolve_mode(self, mode=None, n_samples=None, n_importance=None) -> int:
+        mode = mode or self.mode
+        if mode != "auto":
+            return _lib.MODES[mode]
+        L = _lib.lib()
+        ns = self.N_samples if n_samples is None else n_samples
+        ni = self.N_importance if n_importance is None else n_importance
+        ok = (L.nsos_packed_bytes(self.nerf.desc(), _lib.MODE_TC_EXACT) > 0
+              and L.nsos_packed_bytes(self.nerf_fine.desc(), _lib.MODE_TC_EXACT) > 0
+              and 2 <= ns <= 128 and ns + ni <= 256)
+        return _lib.MODE_TC_EXACT if ok else _lib.MODE_SIMT
+
+    # ---- render_rays (nerf_net.py:71-130) ---------------------------------------------------------------
+    def render_rays(self, rays_o, rays_d, near, far, viewdirs=None, raw_noise_std=0., verbose=False, retraw=False,
+                    retpts=False, pytest=False, **kwargs):
+        """viewdirs is accepted and ignored: the kernel forms d/|d| itself exactly as NeRFNet.forward does."""
+        if retpts:
+            raise NotImplementedError("retpts=True is never used by the reference callers")
+        dev = rays_o.device
+        if dev.type != "cuda":
+            raise _lib.NsosError("nerfsos_b200.NeRFNet renders on CUDA only (no CPU fallback)")
+        N = rays_o.shape[0]
+        n_samples = kwargs.get('N_samples', self.N_samples)                     # sampler.py:41
+        n_imp_gate = kwargs.get('N_importance', self.N_importance)            # nerf_net.py:104 (gate only)
+        n_importance = self.N_importance if (self.N_importance > 0 and n_imp_gate > 0) else 0   # sampler.py:100
+        perturb = kwargs.get('perturb', self.render_kwargs_train['perturb'])
+        mode = self.resolve_mode(kwargs.get('mode'), n_samples, n_importance)
+        cfg = _cfg(self, n_samples, n_importance, perturb, raw_noise_std, mode)
+        f = lambda t: t.reshape(N, -1).to(dev, torch.float32).contiguous()
+        rays_o, rays_d = f(rays_o), f(rays_d)
+        near, far = f(near).reshape(N), f(far).reshape(N)
+        rnd = {k: v.to(dev, torch.float32).contiguous() for k, v in (kwargs.get('randoms') or {}).items()}
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (perturb > 0 or raw_noise_std > 0) else 0
+        want = dict(raw=bool(retraw), z=bool(kwargs.get('retz', False)))
+        fine = n_importance > 0
+        pc = list(self.nerf._flat.params)
+        pf = list(self.nerf_fine._flat.params) if fine else []
+        self.nerf.flat_params()
+        self.nerf_fine.flat_params()
+        tensors = _RenderFn.apply(self, cfg, rays_o, rays_d, near, far, rnd, seed, want, len(pc), *(pc + pf))
+        out = dict(zip(want["names"], tensors))
+        maps = out.pop("maps")
+        sem = self.nerf.mlp.sem_dim if self.nerf.mlp.use_semantics else 0
+        C6 = 6 + sem
+
+        def block(b, sfx, ret):
+            o = b * C6
+            ret['rgb' + sfx] = maps[:, o:o + 3]
+            ret['disp' + sfx] = maps[:, o + 3:o + 4]
+            ret['acc' + sfx] = maps[:, o + 4:o + 5]
+            ret['depth' + sfx] = maps[:, o + 5:o + 6]
+            if sem:
+                ret['semantics' + sfx] = maps[:, o + 6:o + 6 + sem]
+
+        ret = {}
+        block(0, '', ret)
+        ret['weights'] = out['weights']
+        if retraw:
+            ret['raw'] = out['raw']
+        if fine:
+            ret['z_std'] = maps[:, 2 * C6]
+            block(1, '0', ret)
+            ret['weights0'] = out['weights0']
+            if retraw:
+                ret['raw0'] = out['raw0']
+        if want["z"]:
+            for k in ("z_vals", "z_vals0", "z_samples", "inds"):
+                if k in out:
+                    ret[k] = out[k]
+        return ret
+
+    # ---- forward (nerf_net.py:132-195) ----------------------------------------------------------------------
+    def forward(self, ray_batch, bound_batch, **kwargs):
+        render_kwargs = (self.render_kwargs_train if self.training else self.render_kwargs_test).copy()
+        render_kwargs.update(kwargs)
+        rays_o, rays_d = ray_batch
+        assert rays_o.shape == rays_d.shape                                  # :155
+        old_shape = rays_d.shape
+        rays_o = torch.reshape(rays_o, [-1, rays_o.shape[-1]]).float()
+        rays_d = torch.reshape(rays_d, [-1, rays_d.shape[-1]]).float()
+        near, far = bound_batch
+        if isinstance(near, (int, float)):
+            near = near * torch.ones_like(rays_d[..., :1], dtype=torch.float)
+        if isinstance(far, (int, float)):
+            far = far * torch.ones_like(rays_d[..., :1], dtype=torch.float)
+        if rays_o.shape[0] == 0:
+            raise ValueError("empty ray batch")                              # the reference fails in torch.cat here too
+        # one fused launch instead of the serial ray_chunk loop (:177-188)
+        ret = self.render_rays(rays_o, rays_d, near, far, **render_kwargs)
+        for k in ret:                                                        # :191-193 unflatten
+            ret[k] = torch.reshape(ret[k], list(old_shape[:-1]) + list(ret[k].shape[1:]))
+        return ret

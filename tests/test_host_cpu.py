@@ -1,0 +1,97 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/nerfsos.h declares,
+the flat parameter layout matches the reference state_dict, the drop-in keeps the reference's
+checkpoint keys / seeded initialisation, and the product path refuses to run without CUDA."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+import nerfsos_b200  # noqa: F401
+from nerfsos_b200 import _lib
+from nerfsos_b200.models.nerf_net import NeRFNet
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nerfsos.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(nsos_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.nsos_abi_version() == 1
+
+
+def test_param_layout_matches_reference_state_dict():
+    sd = load_golden("flower_weights")["sd"]
+    L = _lib.lib()
+    d = _lib.NetDesc(8, 256, 4, 10, 4, 1, 1, 2, 1)
+    n = L.nsos_param_count(d)
+    keys = [k for k in sd if k.startswith("nerf.mlp.")]
+    assert n == sum(sd[k].size for k in keys) == 637062
+    import ctypes as C
+    cap = 64
+    offs = (C.c_int64 * cap)(); rows = (C.c_int32 * cap)(); cols = (C.c_int32 * cap)()
+    cnt = L.nsos_param_layout(d, offs, rows, cols, cap)
+    assert cnt == len(keys)
+    off = 0
+    for i, k in enumerate(keys):                      # state_dict order == flat order
+        shape = sd[k].shape
+        assert offs[i] == off, k
+        assert rows[i] == shape[0] and cols[i] == (shape[1] if len(shape) == 2 else 1), k
+        off += sd[k].size
+    # config[0] net and the packed-image sizes the tcgen05 path reports
+    d1 = _lib.NetDesc(4, 64, 4, 10, 4, 1, 1, 2, 1)
+    g = load_golden("cfg1_d4w64_eval")["sd"]
+    assert L.nsos_param_count(d1) == sum(v.size for k, v in g.items() if k.startswith("nerf.mlp."))
+    assert L.nsos_packed_bytes(d, _lib.MODE_TC_EXACT) > L.nsos_packed_bytes(d, _lib.MODE_TC_FAST) > 0
+    assert L.nsos_packed_bytes(d, _lib.MODE_SIMT) == 0
+    # invalid: D == skip+1 (the reference cannot run it either) and W not covered by the tcgen05 path
+    assert L.nsos_param_count(_lib.NetDesc(5, 256, 4, 10, 4, 1, 1, 2, 1)) < 0
+    assert L.nsos_packed_bytes(_lib.NetDesc(8, 100, 4, 10, 4, 1, 1, 2, 1), _lib.MODE_TC_EXACT) == 0
+
+
+def test_dropin_keeps_reference_keys_and_seeded_init():
+    g = load_golden("cfg1_d4w64_eval")
+    torch.manual_seed(0)
+    net = NeRFNet(netdepth=4, netwidth=64, netdepth_fine=4, netwidth_fine=64, N_samples=64, N_importance=0,
+                  use_semantics=True, sem_with_coord=True)
+    sd = net.state_dict()
+    assert list(sd) == list(g["sd"])
+    for k in sd:                                       # same construction order => bit-identical default init
+        assert np.array_equal(sd[k].numpy(), g["sd"][k]), k
+    net2 = NeRFNet(N_samples=64, N_importance=128, use_semantics=True, sem_with_coord=True, sem_dim=2)
+    fl = load_golden("flower_weights")["sd"]
+    assert list(net2.state_dict()) == list(fl)
+    net2.load_state_dict({k: torch.from_numpy(v) for k, v in fl.items()}, strict=True)
+    # stage-1 checkpoints have no semantic head: strict=False load leaves exactly those 8 keys missing
+    stage1 = {k: torch.from_numpy(v) for k, v in fl.items() if "semantic_linear" not in k}
+    r = net2.load_state_dict(stage1, strict=False)
+    assert len(r.missing_keys) == 8 and all("semantic_linear" in k for k in r.missing_keys) and not r.unexpected_keys
+    assert net2.nerf is not net2.nerf_fine
+    assert NeRFNet(netdepth=2, netwidth=64, N_samples=8, N_importance=0).nerf_fine is not None
+    n0 = NeRFNet(netdepth=2, netwidth=64, N_samples=8, N_importance=0)
+    assert n0.nerf_fine is n0.nerf                      # nerf_net.py:49
+    assert net2.render_kwargs_test["perturb"] == 0. and net2.render_kwargs_test["raw_noise_std"] == 0.
+
+
+def test_no_cpu_fallback():
+    net = NeRFNet(netdepth=2, netwidth=64, netdepth_fine=2, netwidth_fine=64, N_samples=8, N_importance=0)
+    with pytest.raises(_lib.NsosError):
+        net(torch.zeros(2, 4, 3), (1.0, 2.0))
+    with pytest.raises(_lib.NsosError):
+        net.nerf(torch.zeros(4, 3), viewdirs=torch.zeros(4, 3))
+
+
+def test_product_path_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under nerf-sos_b200/ may import or call it."""
+    pkg = os.path.join(ROOT, "nerf-sos_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "nerf_oracle" not in src, f

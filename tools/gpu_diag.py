@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""GPU bring-up diagnostics (run on the B200 box): exercises each layer of the stack separately and
+prints numbers instead of asserting, so one gpurun call yields maximal information."""
+import os, sys, time, traceback
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import nerfsos_b200
+from nerfsos_b200 import _lib
+from nerfsos_b200.models.nerf_net import NeRFNet
+from conftest import load_golden
+
+dev = torch.device("cuda:0")
+L = _lib.lib()
+print("device:", torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0), flush=True)
+
+
+SEL = sys.argv[1] if len(sys.argv) > 1 else None
+STEPS = []
+
+
+def step(name):
+    def deco(fn):
+        STEPS.append(name)
+        if SEL is None or SEL == "--all" or SEL not in name:
+            return
+        print(f"\n=== {name} ===", flush=True)
+        t0 = time.time()
+        try:
+            fn()
+        except Exception:
+            traceback.print_exc()
+        torch.cuda.synchronize()
+        print(f"--- {name}: {time.time() - t0:.2f}s", flush=True)
+    return deco
+
+
+def cmp(name, a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    d = np.abs(a - b)
+    print(f"  {name:12s} max|d|={d.max():.3e} med={np.median(d):.3e} ref_max={np.abs(b).max():.3e} nan={np.isnan(a).sum()}", flush=True)
+
+
+for _tm in (1, 0):
+  @step(f"selftest umma a_in_tmem={_tm}")
+  def _(_tm=_tm):
+    g = torch.Generator().manual_seed(0)
+    for mode, mname in ((1, "exact"), (2, "fast")):
+        for a_in_tmem, N, K in ((1, 256, 64), (1, 256, 256), (1, 128, 128), (1, 32, 64), (1, 192, 192), (0, 256, 64), (0, 256, 63), (0, 128, 64), (0, 32, 20)):
+            if a_in_tmem != _tm:
+                continue
+            a = (torch.rand(128, K, generator=g) * 4).to(dev)
+            w = (torch.randn(N, K, generator=g) * 0.3).to(dev)
+            d = torch.full((128, N), float("nan"), device=dev)
+            scratch = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
+            rc = L.nsos_selftest_umma(_lib.ptr(a), _lib.ptr(w), _lib.ptr(d), N, K, a_in_tmem, mode, _lib.ptr(scratch), scratch.numel(), None)
+            torch.cuda.synchronize()
+            ref = a.double() @ w.double().T
+            err = (d.double() - ref).abs()
+            print(f"  mode={mname} a_in_tmem={a_in_tmem} N={N} K={K} rc={rc} max_err={err.max().item():.3e} "
+                  f"rel={err.max().item() / ref.abs().max().item():.3e} nan={torch.isnan(d).sum().item()}", flush=True)
+            if err.max().item() > 1e-2 * ref.abs().max().item() and not torch.isnan(d).any():
+                # locate the error pattern
+                bad = (err > 1e-2 * ref.abs().max()).nonzero()
+                print("    first bad (row,col):", bad[:8].tolist(), " rows bad:", len(set(bad[:, 0].tolist())), " cols bad:", len(set(bad[:, 1].tolist())))
+
+
+def make_net(kind, mode):
+    if kind == "cfg1":
+        g = load_golden("cfg1_d4w64_eval")
+        net = NeRFNet(netdepth=4, netwidth=64, netdepth_fine=4, netwidth_fine=64, N_samples=64, N_importance=0,
+                      use_semantics=True, sem_with_coord=True, mode=mode)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in g["sd"].items()})
+        return net.to(dev).eval(), g
+    g = load_golden("flower_eval_256")
+    sd = load_golden("flower_weights")["sd"]
+    net = NeRFNet(N_samples=64, N_importance=128, use_semantics=True, sem_with_coord=True, sem_dim=2, mode=mode)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return net.to(dev).eval(), g
+
+
+for kind in ("cfg1", "flower"):
+    for mode in ("simt", "exact", "fast"):
+        @step(f"forward {kind} mode={mode}")
+        def _():
+            net, g = make_net(kind, mode)
+            rays = torch.from_numpy(g["rays"]).to(dev)
+            with torch.no_grad():
+                ret = net(rays, (1.2, 12.0), retz=True)
+            torch.cuda.synchronize()
+            for k in ("rgb", "acc", "depth", "semantics", "weights", "raw", "rgb0", "semantics0", "weights0", "raw0", "z_std"):
+                if k in ret and k in g["out"]:
+                    cmp(k, ret[k].cpu().numpy(), g["out"][k])
+            if "inds" in ret:
+                fl = ret["inds"].cpu().numpy() != g["stage"]["inds"]
+                print(f"  index flip rate {fl.mean():.2e} (rays {fl.any(-1).mean():.2e})")
+
+
+@step("throughput 4096 rays flower (exact/fast/simt)")
+def _():
+    for mode in ("exact", "fast", "simt"):
+        net, g = make_net("flower", mode)
+        rays = torch.from_numpy(np.tile(g["rays"], (1, 16, 1))).to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                net(rays, (1.2, 12.0))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n = 5
+            for _ in range(n):
+                net(rays, (1.2, 12.0))
+            e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        print(f"  mode={mode}: {ms:.3f} ms / 4096 rays -> {4096 / ms * 1e3:.0f} rays/s, {4096 * 324.86e6 / ms / 1e9:.1f} TFLOP/s algorithmic", flush=True)
+
+
+if SEL == "--all":
+    import subprocess
+    for name in STEPS:
+        r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=600)
+        print(r.stdout[-6000:]); print(r.stderr[-1500:] if r.returncode else "", flush=True)
