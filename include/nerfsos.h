@@ -155,15 +155,16 @@ int nsos_mlp_query(const NsosNetDesc* net, const float* params, const float* pts
 /* ---- kernel B: patch-wise correlation losses ------------------------------------------------- */
 /* GeoCorrelationLoss.forward (utils/image.py:448-482) without materialising the P^2 x P^2 pair
  * matrices.  xyz [B,3,M] (= ray_o + ray_d*depth after the caller's depth clip, :455/:443),
- * code [B,C,M], neg_idx [B] (argmin of the similarity matrix, :354), params = (self_shift,
- * self_weight, neg_shift, neg_weight).  Writes loss[0] and, if g_code != NULL, d(loss)/d(code)
+ * code [B,C,M], neg_idx [B] (argmin of the similarity matrix, :354), params = HOST array (self_shift,
+ * self_weight, neg_shift, neg_weight) in the order of --geo_corr_params.  Writes loss[0] and, if g_code != NULL, d(loss)/d(code)
  * [B,C,M] (overwritten).  workspace: nsos_geo_corr_workspace_bytes(). */
 size_t nsos_geo_corr_workspace_bytes(int32_t B, int32_t C, int32_t M);
 int nsos_geo_corr_loss(const float* xyz, const float* code, const int64_t* neg_idx, const float* params,
                        float* loss, float* g_code, int32_t B, int32_t C, int32_t M, void* workspace,
                        size_t workspace_bytes, void* stream);
 /* CorrelationLoss.forward (utils/image.py:335-370) on already-sampled tensors: feats [B,Cf,S],
- * nfeats [B,Cf,S] (negatives sampled at coords2), code/ncode [B,C,S] (S = 11*11).  The bilinear
+ * nfeats [B,Cf,S] (negatives sampled at coords2), code/ncode [B,C,S] (S = 11*11), params = HOST array
+ * as above (--app_corr_params); g_code/g_ncode [B,C,S] may both be NULL.  The bilinear
  * grid_sample (:303-304) stays in the caller (torch) so autograd routes g_code/g_ncode back. */
 size_t nsos_app_corr_workspace_bytes(int32_t B, int32_t Cf, int32_t C, int32_t S);
 int nsos_app_corr_loss(const float* feats, const float* nfeats, const float* code, const float* ncode,

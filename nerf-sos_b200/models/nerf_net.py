@@ -10,6 +10,7 @@ Extra, non-reference keyword arguments (all optional):
     randoms  dict(t_rand, noise0, u, noise1) of CUDA tensors: inject the four random draws the reference
              makes (parity tests); default is the in-kernel Philox stream seeded from torch's CPU generator
     retz     also return 'z_vals'/'z_vals0', 'z_samples', 'inds'
+    retmaps  also return 'maps', the packed [N, 2*(6+sem_dim)+1] per-ray output row the kernel writes
 """
 from __future__ import annotations
 
@@ -225,6 +226,8 @@ class NeRFNet(nn.Module):
             ret['weights0'] = out['weights0']
             if retraw:
                 ret['raw0'] = out['raw0']
+        if kwargs.get('retmaps', False):
+            ret['maps'] = maps        # the kernel's single per-ray output row: [fine 6+sem | coarse 6+sem | z_std]
         if want["z"]:
             for k in ("z_vals", "z_vals0", "z_samples", "inds"):
                 if k in out:

@@ -1,0 +1,185 @@
+"""Drop-ins for the loss side of utils/image.py of the reference (same class names, ctor `args`
+attributes and forward signatures); the all-pairs arithmetic runs in libnerfsos.so (kernel B).
+
+    img2mse / mse2psnr / get_similarity_matrix   <-> utils/image.py:125-137, 187-190   (tiny torch ops)
+    CorrelationLoss(args)(feats, code, sim)                           <-> utils/image.py:263-370
+    GeoCorrelationLoss(args)(depth, code, [ray_o, ray_d, gt], sim)    <-> utils/image.py:373-482
+
+What stays in torch (host glue, autograd-visible): the random sample coordinates and F.grid_sample
+(image.py:343-362), argmin over the similarity matrix (:354), the in-place depth clip (:455) and
+XYZ = o + d*depth (:443).  Extra kwargs for tests: coords=(coords1, coords2) injects the two random draws.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+
+
+def img2mse(x, y, reduction='mean'):
+    diff = torch.mean((x - y) ** 2, -1)
+    if reduction == 'mean':
+        return torch.mean(diff)
+    if reduction == 'sum':
+        return torch.sum(diff)
+    return diff
+
+
+def mse2psnr(x):
+    if isinstance(x, float):
+        x = torch.tensor([x])
+    return -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))
+
+
+def get_similarity_matrix(x):
+    return F.cosine_similarity(x.unsqueeze(0), x.unsqueeze(1), dim=2)
+
+
+_WS = {}
+
+
+def _workspace(nbytes, device):
+    ws = _WS.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = _WS[device] = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+    return ws
+
+
+def _params4(p):
+    return (C.c_float * 4)(*[float(v) for v in p])
+
+
+class _GeoCorrFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, code, neg_idx, params):
+        if xyz.device.type != "cuda":
+            raise _lib.NsosError("GeoCorrelationLoss runs on CUDA only (no CPU fallback)")
+        L = _lib.lib()
+        B, Cc = code.shape[0], code.shape[1]
+        M = code.shape[2] * code.shape[3]
+        xyz_f = xyz.detach().reshape(B, 3, M).float().contiguous()
+        code_f = code.detach().reshape(B, Cc, M).float().contiguous()
+        neg = neg_idx.to(torch.int64).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=code.device)
+        need_g = code.requires_grad
+        g = torch.empty_like(code_f) if need_g else None
+        nb = L.nsos_geo_corr_workspace_bytes(B, Cc, M)
+        if nb == 0:
+            raise _lib.NsosError("geo correlation loss: unsupported sizes")
+        ws = _workspace(nb, code.device)
+        _lib.check(L.nsos_geo_corr_loss(_lib.ptr(xyz_f), _lib.ptr(code_f), _lib.ptr(neg), _params4(params), _lib.ptr(loss), _lib.ptr(g),
+                                        B, Cc, M, _lib.ptr(ws), ws.numel(), _lib.cur_stream(code.device)), "nsos_geo_corr_loss")
+        ctx.g, ctx.shape = g, code.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gl):
+        g = None if ctx.g is None else (ctx.g * gl).reshape(ctx.shape)
+        return None, g, None, None
+
+
+class _AppCorrFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, nfeats, code, ncode, params):
+        if code.device.type != "cuda":
+            raise _lib.NsosError("CorrelationLoss runs on CUDA only (no CPU fallback)")
+        L = _lib.lib()
+        B, Cf, Cc = feats.shape[0], feats.shape[1], code.shape[1]
+        S = feats.shape[2] * feats.shape[3]
+        f = lambda t, c: t.detach().reshape(B, c, S).float().contiguous()
+        f1, f2, c1, c2 = f(feats, Cf), f(nfeats, Cf), f(code, Cc), f(ncode, Cc)
+        loss = torch.empty(1, dtype=torch.float32, device=code.device)
+        need_g = code.requires_grad or ncode.requires_grad
+        g1 = torch.empty_like(c1) if need_g else None
+        g2 = torch.empty_like(c2) if need_g else None
+        ws = _workspace(L.nsos_app_corr_workspace_bytes(B, Cf, Cc, S), code.device)
+        _lib.check(L.nsos_app_corr_loss(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(c1), _lib.ptr(c2), _params4(params), _lib.ptr(loss),
+                                        _lib.ptr(g1), _lib.ptr(g2), B, Cf, Cc, S, _lib.ptr(ws), ws.numel(),
+                                        _lib.cur_stream(code.device)), "nsos_app_corr_loss")
+        ctx.g1, ctx.g2, ctx.shape = g1, g2, code.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gl):
+        if ctx.g1 is None:
+            return None, None, None, None, None
+        return None, None, (ctx.g1 * gl).reshape(ctx.shape), (ctx.g2 * gl).reshape(ctx.shape), None
+
+
+class CorrelationLoss(nn.Module):
+    """STEGO-style feature-correspondence loss between DINO features and the rendered semantic code."""
+
+    def __init__(self, args=None):
+        super().__init__()
+        self.feature_samples = 11
+        self.self_shift, self.self_weight, self.neg_shift, self.neg_weight = 0.18, 0.67, 0.46, 0.63
+        self.verbose = False
+        self.rand_neg = args.rand_neg
+        self.self_corr_w = args.self_corr_w
+        self.use_sim_matrix = args.use_sim_matrix
+        self.self_shift, self.self_weight, self.neg_shift, self.neg_weight = [float(x) for x in args.app_corr_params]
+
+    def sample(self, t, coords):
+        return F.grid_sample(t, coords.permute(0, 2, 1, 3), padding_mode='border', align_corners=True)
+
+    def super_perm(self, size, device):
+        perm = torch.randperm(size, device=device, dtype=torch.long)
+        perm[perm == torch.arange(size, device=device)] += 1
+        return perm % size
+
+    def _neg_index(self, sim_matrix, n, device):
+        if sim_matrix is None:
+            neg = self.super_perm(n, device)
+        else:
+            assert len(sim_matrix.shape) == 2
+            neg = torch.min(sim_matrix, dim=0)[1]
+        if self.rand_neg:
+            neg = torch.randperm(sim_matrix.shape[0], device=device, dtype=torch.long)
+        return neg
+
+    def forward(self, orig_feats, orig_code, sim_matrix, coords=None):
+        B = orig_feats.shape[0]
+        shape = [B, self.feature_samples, self.feature_samples, 2]
+        if coords is None:
+            coords1 = torch.rand(shape, device=orig_feats.device) * 2 - 1
+            coords2 = torch.rand(shape, device=orig_feats.device) * 2 - 1
+        else:
+            coords1, coords2 = coords
+        with torch.no_grad():
+            feats = self.sample(orig_feats, coords1)
+        code = self.sample(orig_code, coords1)
+        neg = self._neg_index(sim_matrix, B, orig_feats.device)
+        with torch.no_grad():
+            neg_feats = self.sample(orig_feats[neg], coords2)
+        neg_code = self.sample(orig_code[neg], coords2)
+        params = (self.self_shift, self.self_weight, self.neg_shift, self.neg_weight)
+        return _AppCorrFn.apply(feats, neg_feats, code, neg_code, params)
+
+
+class GeoCorrelationLoss(CorrelationLoss):
+    """Same loss with inverse-L1 proximity of back-projected 3-D points as the (gradient-free) target."""
+
+    def __init__(self, args=None):
+        super().__init__(args)
+        self.max_depth = 15
+        self.ps = args.patch_stride
+        self.self_shift, self.self_weight, self.neg_shift, self.neg_weight = [float(x) for x in args.geo_corr_params]
+
+    def depth2pts(self, depth, batch_rays):
+        ray_o, ray_d = batch_rays[0], batch_rays[1]
+        return ray_o + ray_d * depth
+
+    def forward(self, orig_feats, orig_code, batch_rays, sim_matrix):
+        depth = orig_feats
+        with torch.no_grad():
+            far = depth > self.max_depth
+            if bool(far.any()):
+                depth[far] = depth[depth < self.max_depth].max()          # in place, like image.py:455
+            xyz = self.depth2pts(depth, batch_rays)
+        neg = self._neg_index(sim_matrix, orig_code.shape[0], orig_code.device)
+        params = (self.self_shift, self.self_weight, self.neg_shift, self.neg_weight)
+        return _GeoCorrFn.apply(xyz, orig_code, neg, params)

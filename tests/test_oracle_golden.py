@@ -124,3 +124,15 @@ def test_losses_match_reference():
     assert abs(lg - float(g["geo_loss"])) <= 1e-4 * max(1, abs(float(g["geo_loss"])))
     close(dclip, g["depth_clipped"], rtol=1e-6, atol=1e-6)
     close(O.similarity_matrix(g["cls"]), g["sim"], rtol=1e-5, atol=1e-6)
+
+
+def test_torch_port_matches_reference(flower_sd):
+    """The CPU-baseline port (oracle/torch_port.py) issues the reference's own ATen ops: near bit-exact."""
+    import torch
+    from oracle import torch_port as TP
+    g = load_golden("flower_eval_256")
+    sd = {k: torch.from_numpy(v) for k, v in flower_sd.items()}
+    rays = torch.from_numpy(g["rays"][:, :96])
+    out = TP.render_eval(sd, rays[0], rays[1], 1.2, 12.0)
+    for k in ("rgb", "rgb0", "acc", "semantics", "semantics0", "depth", "weights0", "z_std"):
+        close(out[k].numpy(), g["out"][k][:96], rtol=1e-5, atol=2e-5)
