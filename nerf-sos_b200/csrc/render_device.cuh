@@ -232,11 +232,13 @@ struct ImportanceIO {
   int Sc, K;
   bool det;          // perturb == 0
   uint64_t seed; int64_t ray;
+  long long* dbg = nullptr;   // optional clock64 stamps (lane 0): [0] start [1] cdf done [2] search done [3] std done [4] sort done
 };
 
 // ImportanceSampler.forward (sampler.py:136-170) for one ray.  All lanes must call.
 __device__ inline void warp_importance(const ImportanceIO& io, int lane) {
   const int M = io.Sc - 1;   // bins (z_vals_mid)
+  if (io.dbg && lane == 0) io.dbg[0] = clock64();
   const int Mw = io.Sc - 2;  // weights[..., 1:-1]
   for (int i = lane; i < M; i += 32) io.bins[i] = __fmul_rn(0.5f, __fadd_rn(io.z0[i + 1], io.z0[i]));  // :157
   for (int i = lane; i < io.Sc; i += 32) io.zall[i] = io.z0[i];
@@ -255,6 +257,7 @@ __device__ inline void warp_importance(const ImportanceIO& io, int lane) {
     }
   }
   __syncwarp();
+  if (io.dbg && lane == 0) io.dbg[1] = clock64();
   double s1 = 0.0;
   for (int j = lane; j < io.K; j += 32) {
     float u = io.det ? lin01(j, io.K) : (io.u ? io.u[j] : rng_uniform(io.seed, io.ray, RNG_U, j));  // :98-103
@@ -265,6 +268,7 @@ __device__ inline void warp_importance(const ImportanceIO& io, int lane) {
     if (io.inds) io.inds[j] = ind;
     s1 += (double)zs;
   }
+  if (io.dbg && lane == 0) io.dbg[2] = clock64();
   // z_std = population std of the K new samples (nerf_net.py:124)
   double mean = warp_sum(s1) / (double)io.K;
   __syncwarp();
@@ -275,6 +279,7 @@ __device__ inline void warp_importance(const ImportanceIO& io, int lane) {
   }
   s2 = warp_sum(s2);
   if (lane == 0 && io.z_std) *io.z_std = (float)sqrt(s2 / (double)io.K);
+  if (io.dbg && lane == 0) io.dbg[3] = clock64();
   // sort(cat([z, z_samples])) (:161) by stable rank
   const int n = io.Sc + io.K;
   for (int e = lane; e < n; e += 32) {
@@ -287,6 +292,7 @@ __device__ inline void warp_importance(const ImportanceIO& io, int lane) {
     io.zsorted[rank] = v;
   }
   __syncwarp();
+  if (io.dbg && lane == 0) io.dbg[4] = clock64();
 }
 
 }  // namespace nsos

@@ -24,6 +24,7 @@
 
 #include "internal.h"
 #include "render_device.cuh"
+#include "render_group.cuh"
 #include "tc_ptx.cuh"
 
 namespace nsos {
@@ -32,8 +33,10 @@ using namespace ptx;
 
 constexpr int kSlotBytes = 32768;      // one weight slab plane: N(<=256) rows x 64 fp16
 constexpr int kMaxSlots = 6;
-constexpr int kWorkers = 128;
-constexpr int kThreads = 192;
+constexpr int kWorkers = 256;          // 8 row-worker warps: warp w -> TMEM lane quarter w%4, column half w/4
+constexpr int kMmaWarp = 8, kProducerWarp = 9;   // producer warps: kProducerWarp .. kProducerWarp + kNumProducers - 1
+constexpr int kNumProducers = 2;                // one thread can issue only ~1 bulk copy per 680 cycles (tools/bulk_rate.cu)
+constexpr int kThreads = 32 * (kProducerWarp + kNumProducers);
 constexpr float kActScale = 16.f;      // activations are stored as fp16(16*a): keeps the lo plane out of fp16 subnormals
 constexpr int kMaxStages = 13;
 constexpr int kMaxSlabs = 5;
@@ -149,19 +152,20 @@ __device__ __forceinline__ float stage_scale(const TcAux* aux, int st) {
 __global__ void k_pack_aux(const float* __restrict__ prm, TcAux* aux, const PackPlan plan, const NetGeom g) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int nt = gridDim.x * blockDim.x;
-  for (int st = t; st < 16; st += nt) aux->inv_scale[st] = (st < plan.nst) ? 1.f / (stage_scale(aux, st) * kActScale) : 0.f;
+  for (int st = t; st < 16; st += nt) aux->inv_scale[st] = (st < plan.nst) ? 1.f / stage_scale(aux, st) : 0.f;   // acc -> 16*x
   for (int i = t; i < 16 * 256; i += nt) {
     int st = i / 256, c = i % 256;
-    aux->bias[st][c] = (st < plan.nst && c < plan.st_nb[st]) ? prm[plan.st_b_off[st] + c] : 0.f;
+    aux->bias[st][c] = (st < plan.nst && c < plan.st_nb[st]) ? prm[plan.st_b_off[st] + c] * kActScale : 0.f;   // 16*b
   }
   const int H = g.W / 2;
   for (int i = t; i < kHeadFloats; i += nt) {
     float v = 0.f;
-    if (i < kHeadBAlpha) { if (i < g.W) v = prm[g.w_alpha + i]; }
+    const float hs = 1.f / kActScale;          // head weights act on 16*x
+    if (i < kHeadBAlpha) { if (i < g.W) v = prm[g.w_alpha + i] * hs; }
     else if (i < kHeadWS2) { if (i == kHeadBAlpha) v = prm[g.b_alpha]; }
-    else if (i < kHeadBS2) { int s = (i - kHeadWS2) / kHalfMax, c = (i - kHeadWS2) % kHalfMax; if (s < g.sem_dim && c < H) v = prm[g.w_s2 + (int64_t)s * H + c]; }
+    else if (i < kHeadBS2) { int s = (i - kHeadWS2) / kHalfMax, c = (i - kHeadWS2) % kHalfMax; if (s < g.sem_dim && c < H) v = prm[g.w_s2 + (int64_t)s * H + c] * hs; }
     else if (i < kHeadWRgb) { int s = i - kHeadBS2; if (s < g.sem_dim) v = prm[g.b_s2 + s]; }
-    else if (i < kHeadBRgb) { int k = (i - kHeadWRgb) / kHalfMax, c = (i - kHeadWRgb) % kHalfMax; if (c < H) v = prm[g.w_rgb + (int64_t)k * H + c]; }
+    else if (i < kHeadBRgb) { int k = (i - kHeadWRgb) / kHalfMax, c = (i - kHeadWRgb) % kHalfMax; if (c < H) v = prm[g.w_rgb + (int64_t)k * H + c] * hs; }
     else { int k = i - kHeadBRgb; if (k < 3) v = prm[g.b_rgb + k]; }
     aux->heads[i] = v;
   }
@@ -170,7 +174,7 @@ __global__ void k_pack_aux(const float* __restrict__ prm, TcAux* aux, const Pack
     aux->w_vdir[r][c] = (r < H && c < g.encv) ? prm[g.w_views + (int64_t)r * (g.W + g.encv) + g.W + c] : 0.f;
   }
 }
-__global__ void k_fix_scale(TcAux* aux) { aux->inv_scale[0] = 1.f / (stage_scale(aux, 0) * kActScale); }
+__global__ void k_fix_scale(TcAux* aux) { aux->inv_scale[0] = 1.f / stage_scale(aux, 0); }
 // one block per (slab, 64-row group): writes the hi (and lo) SWIZZLE_128B K-major image of the slab
 __global__ void k_pack_slabs(const float* __restrict__ prm, uint8_t* __restrict__ img, const PackPlan plan) {
   const PackSlab ps = plan.s[blockIdx.x];
@@ -199,11 +203,13 @@ struct TcParams {
   int Sc, K, Sf;
   float perturb, noise_std;
   int white_bkgd, exact, fine, C, sem_dim, C6, ML, nslots;
+  long long* trace;   // optional timeline buffer (NSOS_TRACE=1): clock64 stamps of CTA 0, see tools/trace_report.py
 };
+constexpr int kTraceTiles = 16, kTraceStamps = 6;   // [tile][stage][stamp]
 
 struct Smem {
   uint8_t* ring; uint8_t* g_hi; uint8_t* g_lo;
-  float *rawbuf, *zc, *w0, *cdf, *bins, *zall, *zf, *dirbias, *sbias, *heads, *rayp, *encv;
+  float *rawbuf, *hpart, *zc, *w0, *cdf, *bins, *zall, *zf, *dirbias, *sbias, *heads, *rayp, *encv;
   uint64_t *full, *empty, *acc_full, *a_ready;
   uint32_t* tmem_ptr;
 };
@@ -215,6 +221,7 @@ __host__ __device__ inline size_t carve_smem(uint8_t* base, int nslots, int Sc, 
   size_t o_ring = take((size_t)nslots * kSlotBytes, 1024);
   size_t o_ghi = take(kGBytes, 1024), o_glo = take(kGBytes, 1024);
   size_t o_raw = take(sizeof(float) * 2 * Sf * C, 16);
+  size_t o_hp = take(sizeof(float) * 128 * 8, 16);
   size_t o_zc = take(sizeof(float) * 2 * Sc, 16), o_w0 = take(sizeof(float) * 2 * Sc, 16), o_cdf = take(sizeof(float) * 2 * Sc, 16),
          o_bins = take(sizeof(float) * 2 * Sc, 16);
   size_t o_zall = take(sizeof(float) * 2 * Sf, 16), o_zf = take(sizeof(float) * 2 * Sf, 16);
@@ -224,7 +231,7 @@ __host__ __device__ inline size_t carve_smem(uint8_t* base, int nslots, int Sc, 
   size_t o_bar = take(sizeof(uint64_t) * (2 * kMaxSlots + 2), 8), o_tp = take(16, 16);
   if (s) {
     s->ring = base + o_ring; s->g_hi = base + o_ghi; s->g_lo = base + o_glo;
-    s->rawbuf = (float*)(base + o_raw); s->zc = (float*)(base + o_zc); s->w0 = (float*)(base + o_w0);
+    s->rawbuf = (float*)(base + o_raw); s->hpart = (float*)(base + o_hp); s->zc = (float*)(base + o_zc); s->w0 = (float*)(base + o_w0);
     s->cdf = (float*)(base + o_cdf); s->bins = (float*)(base + o_bins); s->zall = (float*)(base + o_zall);
     s->zf = (float*)(base + o_zf); s->dirbias = (float*)(base + o_db); s->sbias = (float*)(base + o_sb);
     s->heads = (float*)(base + o_heads); s->rayp = (float*)(base + o_rayp); s->encv = (float*)(base + o_encv);
@@ -235,19 +242,26 @@ __host__ __device__ inline size_t carve_smem(uint8_t* base, int nslots, int Sc, 
 }
 
 // ---- producer: stream one tile's worth of weight planes through the ring -------------------------------
-// Called by all 32 lanes of the producer warp; the elected lane issues the bulk copies.
+// Called by all 32 lanes of the producer warp; the elected lane issues the bulk copies.  In a cluster of
+// `csize` CTAs every CTA fetches 1/csize of each plane and multicasts it into the same ring slot of all CTAs,
+// so each weight byte crosses L2 -> SM once per cluster instead of once per CTA.
 __device__ __forceinline__ void producer_tile(const TcProg& pg, const uint8_t* img, bool exact, const Smem& sm, int nslots,
-                                              uint32_t& chunk) {
+                                              uint32_t& chunk, uint32_t crank, uint32_t csize, uint32_t pidx) {
   const uint8_t* src = img + kAuxBytes;
+  const uint16_t mask = (uint16_t)((1u << csize) - 1u);
   for (int st = 0; st < pg.nst; ++st) {
     const uint32_t bytes = (uint32_t)pg.st[st].n * 128u;
+    const uint32_t share = bytes / csize;
     const int planes = pg.st[st].nslab * (exact ? 2 : 1);
     for (int c = 0; c < planes; ++c) {
+      if (chunk % kNumProducers != pidx) { src += bytes; ++chunk; continue; }   // chunks alternate between the producer warps
       const uint32_t slot = chunk % nslots, par = (chunk / nslots) & 1u;
-      mbar_wait(smem_u32(&sm.empty[slot]), par ^ 1u, 100 + (int)slot);
+      mbar_wait(smem_u32(&sm.empty[slot]), par ^ 1u, 100 + (int)slot);     // released by every CTA of the cluster
       if (elect_one()) {
         mbar_arrive_expect_tx(smem_u32(&sm.full[slot]), bytes);
-        bulk_g2s(smem_u32(sm.ring + (size_t)slot * kSlotBytes), src, bytes, smem_u32(&sm.full[slot]));
+        const uint32_t dst = smem_u32(sm.ring + (size_t)slot * kSlotBytes) + crank * share;
+        if (csize == 1) bulk_g2s(dst, src, bytes, smem_u32(&sm.full[slot]));
+        else bulk_g2s_multicast(dst, src + (size_t)crank * share, share, smem_u32(&sm.full[slot]), mask);
       }
       __syncwarp();
       src += bytes;
@@ -257,77 +271,88 @@ __device__ __forceinline__ void producer_tile(const TcProg& pg, const uint8_t* i
 }
 
 // ---- MMA issuer: all stages of one tile ------------------------------------------------------------------
-// Called by all 32 lanes of the MMA warp (uniform control flow); the elected lane issues every
-// tcgen05.mma and tcgen05.commit so that the commits track that lane's MMAs.
-__device__ __forceinline__ void mma_tile(const TcProg& pg, bool exact, const Smem& sm, int nslots, uint32_t tm, uint32_t& chunk,
-                                         uint32_t& it) {
+// Called by all 32 lanes of the MMA warp (uniform control flow); the elected lane issues every tcgen05.mma and
+// tcgen05.commit so that the commits track that lane's MMAs.
+//
+// Issue-side latency matters: the warp leaves an elect block only when the block's MMAs have been dispatched to
+// the tensor pipe (the reconvergence point waits on their scoreboards), so whatever runs between two blocks is a
+// pipe bubble unless it is shorter than one MMA (~130 cycles).  Therefore (measured with tools/umma_queue.cu and
+// the NSOS_TRACE timeline): the ring position is tracked incrementally (no division), and the mbarrier wait for
+// the NEXT weight chunk is issued by the elected lane inside the current block, before its last MMA, where it
+// overlaps with the MMAs already queued (the queue holds ~10).
+struct RingPos {
+  uint32_t slot, par;
+  __device__ __forceinline__ void advance(uint32_t nslots) { if (++slot == nslots) { slot = 0; par ^= 1u; } }
+};
+
+__device__ __forceinline__ void mma_tile(const TcProg& pg, bool exact, const Smem& sm, int nslots, uint32_t tm, RingPos& pos,
+                                         uint32_t& it, uint32_t csize, bool last_tile, long long* trace = nullptr) {
   const uint32_t g_hi = smem_u32(sm.g_hi), g_lo = smem_u32(sm.g_lo);
+  const uint32_t ring = smem_u32(sm.ring), full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
+  const uint16_t mask = (uint16_t)((1u << csize) - 1u);
+  const int nplanes = exact ? 2 : 1;
   for (int st = 0; st < pg.nst; ++st) {
     const TcStage& S = pg.st[st];
     mbar_wait(smem_u32(sm.a_ready), it & 1u, 200 + st);
     ++it;
     tc_fence_after();
+    if (trace) trace[st * kTraceStamps + 3] = clock64();        // a_ready observed by the MMA warp
     const uint32_t idesc = make_idesc_f16(S.n);
-    uint32_t accum = 0;
-    for (int j = 0; j < S.nslab; ++j) {
-      const int asrc = S.asrc[j];
-      {  // W_hi plane: A_hi.W_hi (+ A_lo.W_hi)
-        const uint32_t slot = chunk % nslots, par = (chunk / nslots) & 1u;
-        mbar_wait(smem_u32(&sm.full[slot]), par, 300 + (int)slot);
-        tc_fence_after();
-        const uint32_t b = smem_u32(sm.ring + (size_t)slot * kSlotBytes);
-        if (elect_one()) {
+    const int nchunks = S.nslab * nplanes;
+    if (elect_one()) {
+      // The whole stage is issued by the elected lane inside ONE block: no reconvergence (= no wait for the MMA
+      // scoreboards) between chunks, so the tensor pipe queue never drains inside a stage.
+      RingPos cur = pos;
+      uint32_t accum = 0;
+      for (int j = 0; j < S.nslab; ++j) {
+        const int asrc = S.asrc[j];
+        for (int plane = 0; plane < nplanes; ++plane) {
+          // full[cur.slot] of THIS chunk was already waited for (inside the previous chunk, or before the first tile)
+          const uint32_t b = ring + cur.slot * kSlotBytes;
+          const uint32_t my_empty = empty0 + cur.slot * 8u;
+          RingPos nxt = cur;
+          nxt.advance(nslots);
+          const bool has_next = !(last_tile && st == pg.nst - 1 && j == S.nslab - 1 && plane == nplanes - 1);
+          const bool two = exact && plane == 0;     // plane 0 (W_hi): A_hi.W_hi (+ A_lo.W_hi);  plane 1 (W_lo): A_hi.W_lo
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t bd = make_sw128_desc(b + ks * 32);
             const uint32_t acc = (ks == 0) ? accum : 1u;
-            if (asrc == A_GAMMA) {
-              umma_ss(tm + kColD, make_sw128_desc(g_hi + ks * 32), bd, idesc, acc);
-              if (exact) umma_ss(tm + kColD, make_sw128_desc(g_lo + ks * 32), bd, idesc, 1);
-            } else {
-              umma_ts(tm + kColD, tm + kColAhi + asrc * 32 + ks * 8, bd, idesc, acc);
-              if (exact) umma_ts(tm + kColD, tm + kColAlo + asrc * 32 + ks * 8, bd, idesc, 1);
+            if (ks == 3 && !two && has_next) { mbar_wait(full0 + nxt.slot * 8u, nxt.par, 300 + (int)nxt.slot); tc_fence_after(); }
+            if (asrc == A_GAMMA) umma_ss(tm + kColD, make_sw128_desc(g_hi + ks * 32), bd, idesc, acc);
+            else umma_ts(tm + kColD, tm + kColAhi + asrc * 32 + ks * 8, bd, idesc, acc);
+            if (two) {
+              if (ks == 3 && has_next) { mbar_wait(full0 + nxt.slot * 8u, nxt.par, 300 + (int)nxt.slot); tc_fence_after(); }
+              if (asrc == A_GAMMA) umma_ss(tm + kColD, make_sw128_desc(g_lo + ks * 32), bd, idesc, 1);
+              else umma_ts(tm + kColD, tm + kColAlo + asrc * 32 + ks * 8, bd, idesc, 1);
             }
           }
-          umma_commit(smem_u32(&sm.empty[slot]));
+          if (csize == 1) umma_commit(my_empty);
+          else umma_commit_multicast(my_empty, mask);
+          accum = 1;
+          cur = nxt;
         }
-        __syncwarp();
-        accum = 1;
-        ++chunk;
       }
-      if (exact) {  // W_lo plane: A_hi.W_lo
-        const uint32_t slot = chunk % nslots, par = (chunk / nslots) & 1u;
-        mbar_wait(smem_u32(&sm.full[slot]), par, 400 + (int)slot);
-        tc_fence_after();
-        const uint32_t b = smem_u32(sm.ring + (size_t)slot * kSlotBytes);
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t bd = make_sw128_desc(b + ks * 32);
-            if (asrc == A_GAMMA) umma_ss(tm + kColD, make_sw128_desc(g_hi + ks * 32), bd, idesc, 1);
-            else umma_ts(tm + kColD, tm + kColAhi + asrc * 32 + ks * 8, bd, idesc, 1);
-          }
-          umma_commit(smem_u32(&sm.empty[slot]));
-        }
-        __syncwarp();
-        ++chunk;
-      }
+      umma_commit(smem_u32(sm.acc_full));
     }
-    if (elect_one()) umma_commit(smem_u32(sm.acc_full));
     __syncwarp();
+    for (int c = 0; c < nchunks; ++c) pos.advance(nslots);      // all lanes track the ring position
+    if (trace) trace[st * kTraceStamps + 4] = clock64();        // all MMAs of the stage issued
   }
 }
 
 // ---- worker helpers -----------------------------------------------------------------------------------------
-// write one row (64 fp16, hi and lo planes) of a K-major SWIZZLE_128B tile from fp32 values (already x kActScale)
-__device__ __forceinline__ void store_row_sw128(uint8_t* hi_tile, uint8_t* lo_tile, int row, const float* v, bool exact) {
+// Four 16-byte chunks (32 fp16) of one row of a K-major SWIZZLE_128B tile: columns [32*half, 32*half+32).
+// v holds the 32 fp32 values (already x kActScale).
+__device__ __forceinline__ void store_halfrow_sw128(uint8_t* hi_tile, uint8_t* lo_tile, int row, int half, const float* v, bool exact) {
   const size_t rbase = (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = half * 4 + jj;
     uint32_t h[4], l[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float a0 = v[8 * j + 2 * q], a1 = v[8 * j + 2 * q + 1];
+      float a0 = v[8 * jj + 2 * q], a1 = v[8 * jj + 2 * q + 1];
       __half2 hh = __floats2half2_rn(a0, a1);
       float2 hf = __half22float2(hh);
       __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
@@ -340,19 +365,43 @@ __device__ __forceinline__ void store_row_sw128(uint8_t* hi_tile, uint8_t* lo_ti
   }
 }
 
-// One 32-column chunk of an epilogue.  Reads D, applies x = acc*inv + bias (+relu), feeds the fp32 head
-// accumulators and/or writes the next A operand (fp16 hi/lo planes) back to TMEM.
-template <int KIND, bool EXACT>
-__device__ __forceinline__ void epi_chunk(uint32_t tm_lane, int c0, float inv, const float* __restrict__ bias,
-                                          const float* __restrict__ hw, int sem_dim, float* hacc, float* __restrict__ gout) {
-  uint32_t v[32];
-  tmem_ld32(tm_lane + kColD + c0, v);
-  tmem_wait_ld();
-  uint32_t hi[16], lo[16];
+// gamma(x) columns [32*HALF, 32*HALF+32) (embedder.py:34-48), scaled by kActScale, zero beyond `enc`
+template <int HALF>
+__device__ __forceinline__ void encode_half(const float x[3], int L, int enc, bool valid, float* e) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float x0 = fmaf(__uint_as_float(v[j]), inv, bias[c0 + j]);
-    float x1 = fmaf(__uint_as_float(v[j + 1]), inv, bias[c0 + j + 1]);
+  for (int c = 0; c < 32; ++c) e[c] = 0.f;
+  if (HALF == 0) { e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; }
+  constexpr int lo = 32 * HALF, hi = lo + 32;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    // frequency k occupies columns [3+6k, 9+6k)
+    if (3 + 6 * k < hi && 9 + 6 * k > lo && k < L) {
+      const float f = (float)(1 << k);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float s, c;
+        sincosf(__fmul_rn(x[a], f), &s, &c);
+        const int cs = 3 + 6 * k + a, cc = cs + 3;
+        if (cs >= lo && cs < hi) e[cs - lo] = s;
+        if (cc >= lo && cc < hi) e[cc - lo] = c;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) e[c] = (valid && lo + c < enc) ? e[c] * kActScale : 0.f;
+}
+
+// One 16-column chunk of an epilogue.  v = D read-out (already waited for).  x16 = 16*x = acc*inv16 + bias16
+// (+relu) feeds the fp32 head accumulators (head weights are pre-divided by 16) and/or becomes the next A operand.
+constexpr int kCW = 16;   // epilogue chunk width in columns
+template <int KIND, bool EXACT>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
+                                          const float* __restrict__ hw, int sem_dim, float* hacc, float* __restrict__ gout) {
+  uint32_t hi[kCW / 2], lo[kCW / 2];
+#pragma unroll
+  for (int j = 0; j < kCW; j += 2) {
+    float x0 = fmaf(__uint_as_float(v[j]), inv16, bias[c0 + j]);
+    float x1 = fmaf(__uint_as_float(v[j + 1]), inv16, bias[c0 + j + 1]);
     if (KIND != EPI_FEAT && KIND != EPI_RAW) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
     if (KIND == EPI_HIDDEN_SIGMA) {
       hacc[0] = fmaf(hw[kHeadWAlpha + c0 + j], x0, hacc[0]);
@@ -371,50 +420,76 @@ __device__ __forceinline__ void epi_chunk(uint32_t tm_lane, int c0, float inv, c
         hacc[k] = fmaf(hw[kHeadWRgb + k * kHalfMax + c0 + j + 1], x1, hacc[k]);
       }
     } else if (KIND == EPI_RAW) {
-      gout[c0 + j] = x0; gout[c0 + j + 1] = x1;
+      gout[c0 + j] = x0 * (1.f / kActScale); gout[c0 + j + 1] = x1 * (1.f / kActScale);
     }
     if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FEAT) {
-      float a0 = x0 * kActScale, a1 = x1 * kActScale;
-      __half2 hh = __floats2half2_rn(a0, a1);
+      __half2 hh = __floats2half2_rn(x0, x1);
       hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
       if (EXACT) {
         float2 hf = __half22float2(hh);
-        __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
         lo[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
       }
     }
   }
   if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FEAT) {
-    tmem_st16(tm_lane + kColAhi + (c0 >> 1), hi);
-    if (EXACT) tmem_st16(tm_lane + kColAlo + (c0 >> 1), lo);
+    tmem_st8(tm_lane + kColAhi + (c0 >> 1), hi);
+    if (EXACT) tmem_st8(tm_lane + kColAlo + (c0 >> 1), lo);
   }
 }
 
-template <bool EXACT>
-__device__ __forceinline__ void epilogue(int kind, int n, uint32_t tm_lane, float inv, const float* bias, const float* hw, int sem_dim,
+template <int KIND, bool EXACT>
+__device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw, int sem_dim,
                                          float* hacc, float* gout) {
-  for (int c0 = 0; c0 < n; c0 += 32) {
-    switch (kind) {
-      case EPI_HIDDEN: epi_chunk<EPI_HIDDEN, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
-      case EPI_HIDDEN_SIGMA: epi_chunk<EPI_HIDDEN_SIGMA, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
-      case EPI_SEM: epi_chunk<EPI_SEM, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
-      case EPI_FEAT: epi_chunk<EPI_FEAT, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
-      case EPI_RGB: epi_chunk<EPI_RGB, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
-      default: epi_chunk<EPI_RAW, EXACT>(tm_lane, c0, inv, bias, hw, sem_dim, hacc, gout); break;
+  // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+  uint32_t va[kCW], vb[kCW];
+  if (cb >= ce) return;
+  tmem_ld16(tm_lane + kColD + cb * kCW, va);
+  tmem_wait_ld_fence16(va);
+  for (int c = cb; c < ce; c += 2) {
+    if (c + 1 < ce) tmem_ld16(tm_lane + kColD + (c + 1) * kCW, vb);
+    epi_chunk<KIND, EXACT>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, hacc, gout);
+    if (c + 1 < ce) {
+      tmem_wait_ld_fence16(vb);
+      if (c + 2 < ce) tmem_ld16(tm_lane + kColD + (c + 2) * kCW, va);
+      epi_chunk<KIND, EXACT>(vb, tm_lane, (c + 1) * kCW, inv16, bias, hw, sem_dim, hacc, gout);
+      if (c + 2 < ce) tmem_wait_ld_fence16(va);
     }
   }
 }
 
-__device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int warp, int lane) {
+// 16-column chunks [cb, ce) of a stage
+template <bool EXACT>
+__device__ __forceinline__ void epilogue(int kind, int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw,
+                                         int sem_dim, float* hacc, float* gout) {
+  switch (kind) {
+    case EPI_HIDDEN: epi_kind<EPI_HIDDEN, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_HIDDEN_SIGMA: epi_kind<EPI_HIDDEN_SIGMA, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_SEM: epi_kind<EPI_SEM, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_FEAT: epi_kind<EPI_FEAT, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_RGB: epi_kind<EPI_RGB, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    default: epi_kind<EPI_RAW, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+  }
+}
+
+// chunk range (units of kCW columns) of worker half `hf` for a stage of n columns
+__device__ __forceinline__ void chunk_range(int n, int hf, int& cb, int& ce) {
+  const int nch = n / kCW, mid = (nch + 1) >> 1;
+  cb = hf ? mid : 0;
+  ce = hf ? nch : mid;
+}
+
+__device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int warp, uint32_t csize) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nslots; ++i) { mbar_init(smem_u32(&sm.full[i]), 1); mbar_init(smem_u32(&sm.empty[i]), 1); }
+    for (int i = 0; i < nslots; ++i) { mbar_init(smem_u32(&sm.full[i]), 1); mbar_init(smem_u32(&sm.empty[i]), csize); }
     mbar_init(smem_u32(sm.acc_full), 1);
     mbar_init(smem_u32(sm.a_ready), kWorkers);
     fence_mbar_init();
   }
-  if (warp == 4) { tmem_alloc(smem_u32(sm.tmem_ptr), kTmemCols); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc(smem_u32(sm.tmem_ptr), kTmemCols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync();          // peers' barriers must be initialised before any multicast signal
   tc_fence_after();
 }
 
@@ -425,47 +500,61 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
   Smem sm;
   carve_smem(base, P.nslots, P.Sc, P.Sf, P.C, &sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
-  init_pipeline(sm, P.nslots, warp, lane);
+  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
+  init_pipeline(sm, P.nslots, warp, csize);
   const uint32_t tm = *sm.tmem_ptr;
   const long long n_pairs = (P.n_rays + 1) / 2;
+  // every CTA runs the same number of pair iterations (cluster peers stream the weights in lock step);
+  // iterations past the end render a dummy pair whose outputs are suppressed
+  const long long iters = (n_pairs + gridDim.x - 1) / gridDim.x;
   const int npass = P.fine ? 2 : 1;
 
-  if (warp == 5) {
-    // ================= producer =================
-    {
-      uint32_t chunk = 0;
-      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-        for (int pass = 0; pass < npass; ++pass) {
-          const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
-          for (int tile = 0; tile < ntiles; ++tile) producer_tile(P.prog[pass], P.packed[pass], EXACT, sm, P.nslots, chunk);
+  if (warp >= kProducerWarp) {
+    uint32_t chunk = 0;
+    for (long long itp = 0; itp < iters; ++itp)
+      for (int pass = 0; pass < npass; ++pass) {
+        const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
+        for (int tile = 0; tile < ntiles; ++tile)
+          producer_tile(P.prog[pass], P.packed[pass], EXACT, sm, P.nslots, chunk, crank, csize, warp - kProducerWarp);
+      }
+  } else if (warp == kMmaWarp) {
+    uint32_t it = 0;
+    RingPos pos{0u, 0u};
+    int ntile_seen = 0;
+    mbar_wait(smem_u32(&sm.full[0]), 0u, 299);                  // first weight chunk; later ones are pre-waited inside the blocks
+    tc_fence_after();
+    for (long long itp = 0; itp < iters; ++itp)
+      for (int pass = 0; pass < npass; ++pass) {
+        const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
+        for (int tile = 0; tile < ntiles; ++tile) {
+          long long* tr = nullptr;
+          if (P.trace && blockIdx.x == 0 && lane == 0 && ntile_seen < kTraceTiles - 1) tr = P.trace + (size_t)ntile_seen * 16 * kTraceStamps;
+          ++ntile_seen;
+          const bool last_tile = (itp == iters - 1) && (pass == npass - 1) && (tile == ntiles - 1);
+          mma_tile(P.prog[pass], EXACT, sm, P.nslots, tm, pos, it, csize, last_tile, tr);
         }
-    }
-  } else if (warp == 4) {
-    // ================= MMA issuer =================
-    {
-      uint32_t chunk = 0, it = 0;
-      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-        for (int pass = 0; pass < npass; ++pass) {
-          const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
-          for (int tile = 0; tile < ntiles; ++tile) mma_tile(P.prog[pass], EXACT, sm, P.nslots, tm, chunk, it);
-        }
-    }
+      }
   } else {
-    // ================= row workers (128 threads = 128 TMEM lanes) =================
-    const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16);
+    // ================= row workers: 8 warps; warp w owns TMEM lanes 32*(w%4).. and column half w/4 =================
+    const int q4 = warp & 3, hf = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
     uint32_t it_acc = 0, it_bias = 0;
-    // head weights of both nets -> smem (constant for the launch)
+    int ntile_seen = 0;
     for (int net = 0; net < npass; ++net) {
       const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[net]);
       for (int i = t; i < kHeadFloats; i += kWorkers) sm.heads[net * kHeadFloats + i] = __ldg(&aux->heads[i]);
     }
-    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      named_bar_sync(1, kWorkers);   // previous pair's compositing has finished with the shared buffers
+    for (long long itp = 0; itp < iters; ++itp) {
+      const long long pair_raw = (long long)blockIdx.x + itp * gridDim.x;
+      const bool pair_valid = pair_raw < n_pairs;
+      const long long pair = pair_valid ? pair_raw : 0;
+      named_bar_sync(1, kWorkers);
       // ---- per-pair ray setup: o, d, near, far, |d|, gamma_v(d/|d|)
       if (t < 2) {
         long long r = pair * 2 + t;
-        bool valid = r < P.n_rays;
-        long long rr = valid ? r : pair * 2;
+        bool valid = pair_valid && r < P.n_rays;
+        long long rr = (r < P.n_rays) ? r : pair * 2;
         float* rp = sm.rayp + t * kRayP;
         float d0 = P.rays_d[rr * 3], d1 = P.rays_d[rr * 3 + 1], d2 = P.rays_d[rr * 3 + 2];
         rp[0] = P.rays_o[rr * 3]; rp[1] = P.rays_o[rr * 3 + 1]; rp[2] = P.rays_o[rr * 3 + 2];
@@ -478,15 +567,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
         for (int c = 0; c < 28; ++c) sm.encv[t * 28 + c] = (c < P.prog[0].encv) ? e[c] : 0.f;
       }
       named_bar_sync(1, kWorkers);
-      // view-direction half of views_linears.0 folded into a per-ray bias (fp32): dirbias[net][ray][j]
+      // view-direction half of views_linears.0 folded into a per-ray bias (fp32, x16): dirbias[net][ray][j]
       for (int idx = t; idx < npass * 2 * kHalfMax; idx += kWorkers) {
         int net = idx / (2 * kHalfMax), rl = (idx / kHalfMax) & 1, j = idx % kHalfMax;
         const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[net]);
         const TcProg& pg = P.prog[net];
         float acc = 0.f;
         if (j < pg.H2) {
-          acc = __ldg(&aux->bias[pg.nst - 1][j]);
-          for (int c = 0; c < pg.encv; ++c) acc = fmaf(__ldg(&aux->w_vdir[j][c]), sm.encv[rl * 28 + c], acc);
+          acc = __ldg(&aux->bias[pg.nst - 1][j]);                     // 16 * b_views
+          float d = 0.f;
+#pragma unroll
+          for (int c = 0; c < 28; ++c) d = fmaf(__ldg(&aux->w_vdir[j][c]), sm.encv[rl * 28 + c], d);   // zero padded beyond encv
+          acc = fmaf(d, kActScale, acc);
         }
         sm.dirbias[idx] = acc;
       }
@@ -498,8 +590,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
         const float* hw = sm.heads + pass * kHeadFloats;
         const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
         for (int tile = 0; tile < ntiles; ++tile) {
-          // ---- tile setup: sample position, point, gamma(x) -> swizzled smem A tile
-          const int q = tile * 128 + t;
+          // ---- tile setup: sample position, point, gamma(x) -> swizzled smem A tile (each half-warp-group writes 32 columns)
+          const int q = tile * 128 + row;
           const bool rowvalid = q < 2 * S;
           const int rl = rowvalid ? q / S : 0, i = rowvalid ? q % S : 0;
           const float* rp = sm.rayp + rl * kRayP;
@@ -511,48 +603,59 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               float tr = 0.f;
               if (pert) tr = (P.rnd.t_rand && rp[9] > 0.f) ? P.rnd.t_rand[ray * P.Sc + i] : rng_uniform(P.seed, ray, RNG_T_RAND, i);
               z = z_stratified(rp[6], rp[7], i, S, pert, tr);
-              if (rowvalid) sm.zc[rl * P.Sc + i] = z;
+              if (rowvalid && hf == 0) sm.zc[rl * P.Sc + i] = z;
             } else {
               z = sm.zf[rl * P.Sf + i];
             }
             float x[3] = {pt_coord(rp[0], rp[3], z), pt_coord(rp[1], rp[4], z), pt_coord(rp[2], rp[5], z)};
-            float e[64];
-            encode3(x, pg.Lp, e);
-#pragma unroll
-            for (int c = 0; c < 64; ++c) e[c] = (rowvalid && c < pg.enc) ? e[c] * kActScale : 0.f;
-            store_row_sw128(sm.g_hi, sm.g_lo, t, e, EXACT);
+            float e[32];
+            if (hf == 0) encode_half<0>(x, pg.Lp, pg.enc, rowvalid, e); else encode_half<1>(x, pg.Lp, pg.enc, rowvalid, e);
+            store_halfrow_sw128(sm.g_hi, sm.g_lo, row, hf, e, EXACT);
           }
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(smem_u32(sm.a_ready));
+          long long* tr = nullptr;
+          if (P.trace && blockIdx.x == 0 && t == 0 && ntile_seen < kTraceTiles - 1) tr = P.trace + (size_t)ntile_seen * 16 * kTraceStamps;
+          ++ntile_seen;
 
-          float sigma = 0.f, semv[kSemMax] = {0.f, 0.f, 0.f, 0.f}, rgbv[3] = {0.f, 0.f, 0.f};
+          float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0] sigma, [1..3] rgb, [4..7] sem (partial over my columns)
           for (int st = 0; st < pg.nst; ++st) {
             const TcStage& Sg = pg.st[st];
-            // stage bias -> smem (double buffered), except the view layer whose bias is the per-ray dirbias
             float* sb = sm.sbias + (it_bias & 1u) * 256;
             ++it_bias;
-            for (int c = t; c < 256; c += kWorkers) sb[c] = __ldg(&aux->bias[st][c]);
-            const float inv = __ldg(&aux->inv_scale[st]);
+            sb[t] = __ldg(&aux->bias[st][t]);                            // kWorkers == 256 == bias row length
+            const float inv16 = __ldg(&aux->inv_scale[st]);
             named_bar_sync(1, kWorkers);
             const float* bias = (Sg.epi == EPI_RGB) ? (sm.dirbias + (pass * 2 + rl) * kHalfMax) : sb;
+            int cb, ce;
+            chunk_range(Sg.n, hf, cb, ce);
+            if (tr) tr[st * kTraceStamps + 0] = clock64();                 // worker starts waiting for the accumulator
             mbar_wait(smem_u32(sm.acc_full), it_acc & 1u, 500 + st);
             ++it_acc;
             tc_fence_after();
-            float* hacc = (Sg.epi == EPI_HIDDEN_SIGMA) ? &sigma : (Sg.epi == EPI_SEM) ? semv : rgbv;
-            epilogue<EXACT>(Sg.epi, Sg.n, tm_lane, inv, bias, hw, P.sem_dim, hacc, nullptr);
+            if (tr) tr[st * kTraceStamps + 1] = clock64();                 // accumulator ready
+            float* ha = (Sg.epi == EPI_HIDDEN_SIGMA) ? &hacc[0] : (Sg.epi == EPI_SEM) ? &hacc[4] : &hacc[1];
+            epilogue<EXACT>(Sg.epi, cb, ce, tm_lane, inv16, bias, hw, P.sem_dim, ha, nullptr);
+            if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
             if (st + 1 < pg.nst) {
               if (Sg.epi != EPI_SEM) tmem_wait_st();
               tc_fence_before();
               mbar_arrive(smem_u32(sm.a_ready));
             }
           }
-          // ---- raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
-          if (rowvalid) {
+          // ---- combine the two column halves and emit the raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
+          if (hf == 1) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sm.hpart[row * 8 + c] = hacc[c];
+          }
+          named_bar_sync(1, kWorkers);
+          if (hf == 0 && rowvalid) {
+            const float* hp = sm.hpart + row * 8;
             float* rw = sm.rawbuf + (size_t)q * P.C;
-            rw[0] = rgbv[0] + hw[kHeadBRgb]; rw[1] = rgbv[1] + hw[kHeadBRgb + 1]; rw[2] = rgbv[2] + hw[kHeadBRgb + 2];
-            rw[3] = sigma + hw[kHeadBAlpha];
-            for (int s = 0; s < P.sem_dim; ++s) rw[4 + s] = semv[s] + hw[kHeadBS2 + s];
+            rw[0] = hacc[1] + hp[1] + hw[kHeadBRgb]; rw[1] = hacc[2] + hp[2] + hw[kHeadBRgb + 1]; rw[2] = hacc[3] + hp[3] + hw[kHeadBRgb + 2];
+            rw[3] = hacc[0] + hp[0] + hw[kHeadBAlpha];
+            for (int s = 0; s < P.sem_dim; ++s) rw[4 + s] = hacc[4 + s] + hp[4 + s] + hw[kHeadBS2 + s];
             float* graw = (pass == 0 && P.fine) ? P.out.raw0 : P.out.raw;
             if (graw && rp[9] > 0.f) {
               float* g = graw + ((size_t)ray * S + i) * P.C;
@@ -560,44 +663,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             }
           }
         }
-        // ---- compositing (+ resampling after the coarse pass): warp r owns ray r of the pair
+        // ---- compositing (+ resampling after the coarse pass): 4 warps (128 threads) per ray of the pair.
+        // The gamma tiles are idle between tiles (all MMAs of the tile have completed): their first bytes serve as
+        // reduction scratch here.
         named_bar_sync(1, kWorkers);
-        if (warp < 2) {
-          const float* rp = sm.rayp + warp * kRayP;
-          const long long ray = pair * 2 + warp;
+        {
+          const int gr = warp >> 2, gt = t & (kGroup - 1), gbar = 2 + gr;
+          long long* gdbg = (P.trace && blockIdx.x == 0 && itp == 0 && t == 0) ? P.trace + (size_t)(kTraceTiles - 1) * 16 * kTraceStamps + pass * 16 : nullptr;
+          if (gdbg) gdbg[8] = clock64();
+          GroupScratch gsc;
+          gsc.f = reinterpret_cast<float*>(sm.g_hi + gr * 512);
+          gsc.d = reinterpret_cast<double*>(sm.g_hi + 1024 + gr * 64);
+          const float* rp = sm.rayp + gr * kRayP;
+          const long long ray = pair * 2 + gr;
           const bool valid = rp[9] > 0.f;
           const bool coarse_of_two = (pass == 0 && P.fine);
           RayPass rpx;
-          rpx.raw = sm.rawbuf + (size_t)warp * S * P.C;
-          rpx.z = pass ? sm.zf + warp * P.Sf : sm.zc + warp * P.Sc;
+          rpx.raw = sm.rawbuf + (size_t)gr * S * P.C;
+          rpx.z = pass ? sm.zf + gr * P.Sf : sm.zc + gr * P.Sc;
           const float* nz = pass ? P.rnd.noise1 : P.rnd.noise0;
           rpx.noise = (nz && valid) ? nz + ray * S : nullptr;
           rpx.noise_std = P.noise_std; rpx.seed = P.seed; rpx.ray = ray; rpx.rng_stream = pass ? RNG_NOISE1 : RNG_NOISE0;
           rpx.dnorm = rp[8]; rpx.S = S; rpx.C = P.C; rpx.sem_dim = P.sem_dim; rpx.white_bkgd = P.white_bkgd;
           float scratch_maps[6 + kSemMax];
           float* maps = valid ? P.out.maps + (size_t)ray * P.ML + (coarse_of_two ? P.C6 : 0) : nullptr;
-          float* wsm = sm.w0 + warp * P.Sc;   // coarse weights stay in smem for the resampling
+          float* wsm = sm.w0 + gr * P.Sc;     // coarse weights stay in smem for the resampling
           float* gw = coarse_of_two ? P.out.weights0 : P.out.weights;
           float* wout = (pass == 0) ? wsm : ((gw && valid) ? gw + ray * S : nullptr);
-          warp_composite(rpx, lane, maps ? maps : scratch_maps, wout);
-          __syncwarp();
+          group_composite(rpx, gt, gbar, gsc, maps ? maps : scratch_maps, wout);
+          if (gdbg) gdbg[9] = clock64();
           if (pass == 0) {
-            if (gw && valid) for (int k = lane; k < S; k += 32) gw[ray * S + k] = wsm[k];
+            if (gw && valid) for (int k = gt; k < S; k += kGroup) gw[ray * S + k] = wsm[k];
             float* gz = coarse_of_two ? P.out.z_vals0 : P.out.z_vals;
-            if (gz && valid) for (int k = lane; k < S; k += 32) gz[ray * S + k] = rpx.z[k];
+            if (gz && valid) for (int k = gt; k < S; k += kGroup) gz[ray * S + k] = rpx.z[k];
             if (P.fine) {
               ImportanceIO io;
-              io.z0 = rpx.z; io.w0 = wsm; io.cdf = sm.cdf + warp * P.Sc; io.bins = sm.bins + warp * P.Sc;
-              io.zall = sm.zall + warp * P.Sf; io.zsorted = sm.zf + warp * P.Sf;
+              io.z0 = rpx.z; io.w0 = wsm; io.cdf = sm.cdf + gr * P.Sc; io.bins = sm.bins + gr * P.Sc;
+              io.zall = sm.zall + gr * P.Sf; io.zsorted = sm.zf + gr * P.Sf;
               io.u = (P.rnd.u && valid) ? P.rnd.u + ray * P.K : nullptr;
               io.z_samples = (P.out.z_samples && valid) ? P.out.z_samples + ray * P.K : nullptr;
               io.inds = (P.out.inds && valid) ? P.out.inds + ray * P.K : nullptr;
               io.z_std = valid ? P.out.maps + (size_t)ray * P.ML + 2 * P.C6 : nullptr;
               io.Sc = P.Sc; io.K = P.K; io.det = !(P.perturb > 0.f); io.seed = P.seed; io.ray = ray;
-              warp_importance(io, lane);
-              if (P.out.z_vals && valid) for (int k = lane; k < P.Sf; k += 32) P.out.z_vals[ray * P.Sf + k] = io.zsorted[k];
+              group_importance(io, gt, gbar, gsc);
+              if (P.out.z_vals && valid) for (int k = gt; k < P.Sf; k += kGroup) P.out.z_vals[ray * P.Sf + k] = io.zsorted[k];
             }
           }
+          if (gdbg) gdbg[10] = clock64();
         }
         named_bar_sync(1, kWorkers);
       }
@@ -606,7 +718,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tm, kTmemCols);
+  if (csize > 1) cluster_sync();           // no CTA may exit while a peer can still signal its barriers
+  if (warp == kMmaWarp) tmem_dealloc(tm, kTmemCols);
 }
 
 // ---- self test: D[128,N] = A[128,K] . W[N,K]^T through the same producer / MMA / epilogue code ----------------
@@ -624,51 +737,61 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
   Smem sm;
   carve_smem(base, P.nslots, 2, 2, 8, &sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
-  init_pipeline(sm, P.nslots, warp, lane);
+  init_pipeline(sm, P.nslots, warp, 1);
   const uint32_t tm = *sm.tmem_ptr;
-  if (warp == 5) {
+  if (warp >= kProducerWarp) {
     uint32_t chunk = 0;
-    producer_tile(P.prog, P.packed, EXACT, sm, P.nslots, chunk);
-  } else if (warp == 4) {
-    uint32_t chunk = 0, it = 0;
-    mma_tile(P.prog, EXACT, sm, P.nslots, tm, chunk, it);
+    producer_tile(P.prog, P.packed, EXACT, sm, P.nslots, chunk, 0, 1, warp - kProducerWarp);
+  } else if (warp == kMmaWarp) {
+    uint32_t it = 0;
+    RingPos pos{0u, 0u};
+    mbar_wait(smem_u32(&sm.full[0]), 0u, 299);
+    tc_fence_after();
+    mma_tile(P.prog, EXACT, sm, P.nslots, tm, pos, it, 1, true);
   } else {
-    const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16);
+    const int q4 = warp & 3, hf = warp >> 2, row = q4 * 32 + lane;
+    const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
     const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed);
     if (P.a_in_tmem) {
-      for (int c0 = 0; c0 < P.K; c0 += 32) {
-        uint32_t hi[16], lo[16];
+      // each worker half writes its half of the K columns (16-column chunks) of the A planes
+      int cb, ce;
+      chunk_range(P.K, hf, cb, ce);
+      for (int c = cb; c < ce; ++c) {
+        const int c0 = c * kCW;
+        uint32_t hi[kCW / 2], lo[kCW / 2];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a0 = P.a[(size_t)t * P.K + c0 + j] * kActScale, a1 = P.a[(size_t)t * P.K + c0 + j + 1] * kActScale;
+        for (int j = 0; j < kCW; j += 2) {
+          float a0 = P.a[(size_t)row * P.K + c0 + j] * kActScale, a1 = P.a[(size_t)row * P.K + c0 + j + 1] * kActScale;
           __half2 hh = __floats2half2_rn(a0, a1);
-          float2 hf = __half22float2(hh);
-          __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+          float2 hf2 = __half22float2(hh);
+          __half2 ll = __floats2half2_rn(a0 - hf2.x, a1 - hf2.y);
           hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
           lo[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
         }
-        tmem_st16(tm_lane + kColAhi + (c0 >> 1), hi);
-        if (EXACT) tmem_st16(tm_lane + kColAlo + (c0 >> 1), lo);
+        tmem_st8(tm_lane + kColAhi + (c0 >> 1), hi);
+        if (EXACT) tmem_st8(tm_lane + kColAlo + (c0 >> 1), lo);
       }
       tmem_wait_st();
     } else {
-      float e[64];
-      for (int c = 0; c < 64; ++c) e[c] = (c < P.K) ? P.a[(size_t)t * P.K + c] * kActScale : 0.f;
-      store_row_sw128(sm.g_hi, sm.g_lo, t, e, EXACT);
+      float e[32];
+      for (int c = 0; c < 32; ++c) { int col = hf * 32 + c; e[c] = (col < P.K) ? P.a[(size_t)row * P.K + col] * kActScale : 0.f; }
+      store_halfrow_sw128(sm.g_hi, sm.g_lo, row, hf, e, EXACT);
       fence_proxy_async_smem();
     }
-    for (int c = t; c < 256; c += kWorkers) sm.sbias[c] = 0.f;
+    sm.sbias[t] = 0.f;
     named_bar_sync(1, kWorkers);
     tc_fence_before();
     mbar_arrive(smem_u32(sm.a_ready));
     mbar_wait(smem_u32(sm.acc_full), 0, 600);
     tc_fence_after();
     float dummy[4];
-    epilogue<EXACT>(EPI_RAW, P.N, tm_lane, __ldg(&aux->inv_scale[0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)t * P.N);
+    int cb, ce;
+    chunk_range(P.N, hf, cb, ce);
+    epilogue<EXACT>(EPI_RAW, cb, ce, tm_lane, __ldg(&aux->inv_scale[0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)row * P.N);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tm, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tm, kTmemCols);
 }
 
 int run_pack(const PackPlan& plan, const NetGeom* g, const float* params, void* packed, cudaStream_t st) {
@@ -709,11 +832,11 @@ int tc_pack_weights(const NsosNetDesc& net, const float* params, void* packed, i
   return run_pack(plan, &g, params, packed, st);
 }
 
-size_t tc_render_workspace_bytes(const NsosRenderCfg&, int64_t) { return 256; }
+size_t tc_render_workspace_bytes(const NsosRenderCfg&, int64_t) { return sizeof(long long) * kTraceTiles * 16 * kTraceStamps + 256; }
 
 int tc_render_fwd(const NsosRenderCfg& cfg, const float* /*pc*/, const float* /*pf*/, const void* packed_c, const void* packed_f,
                   const float* rays_o, const float* rays_d, const float* near, const float* far, const NsosRandoms* rnd,
-                  uint64_t seed, const NsosRenderOut& out, void* /*workspace*/, size_t /*workspace_bytes*/, int64_t n_rays,
+                  uint64_t seed, const NsosRenderOut& out, void* workspace, size_t workspace_bytes, int64_t n_rays,
                   cudaStream_t st) {
   NetGeom gc, gf;
   NSOS_REQUIRE(make_geom(cfg.coarse, gc), NSOS_ERR_UNSUPPORTED, "invalid coarse net descriptor");
@@ -736,6 +859,10 @@ int tc_render_fwd(const NsosRenderCfg& cfg, const float* /*pc*/, const float* /*
   P.seed = seed; P.out = out; P.n_rays = n_rays; P.Sc = Sc; P.K = K; P.Sf = fine ? Sf : Sc;
   P.perturb = cfg.perturb; P.noise_std = cfg.raw_noise_std; P.white_bkgd = cfg.white_bkgd; P.exact = exact; P.fine = fine;
   P.C = gc.C; P.sem_dim = gc.sem_dim; P.C6 = 6 + gc.sem_dim; P.ML = 2 * P.C6 + 1;
+  if (getenv("NSOS_TRACE") && workspace && workspace_bytes >= tc_render_workspace_bytes(cfg, n_rays)) {
+    P.trace = reinterpret_cast<long long*>(workspace);
+    NSOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(long long) * kTraceTiles * 16 * kTraceStamps, st));
+  }
   const int smem_max = max_optin_smem();
   NSOS_REQUIRE(smem_max >= 200 * 1024, NSOS_ERR_DEVICE, "device offers only %d B of opt-in shared memory", smem_max);
   int nslots = kMaxSlots;
@@ -750,14 +877,28 @@ int tc_render_fwd(const NsosRenderCfg& cfg, const float* /*pc*/, const float* /*
   NSOS_CHECK_CUDA(cudaGetDevice(&dev));
   NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long n_pairs = (n_rays + 1) / 2;
-  const int grid = (int)std::min<long long>(n_pairs, sms);
+  // Thread-block clusters can share the weight stream (multicast bulk copies): NSOS_CLUSTER = 1 (default), 2 or 4.
+  // Measured on B200 (profiles/r01_notes.md): no gain -- the stream is bound by the per-thread bulk-copy issue rate and
+  // the per-SM ingest (~96 B/clk), not by L2, and multicast does not lower the bytes landing in each SM.
+  int csize = 1;
+  if (const char* e = getenv("NSOS_CLUSTER")) csize = atoi(e);
+  if (csize != 1 && csize != 2 && csize != 4) csize = 1;
+  while (csize > 1 && n_pairs < csize) csize >>= 1;
+  long long g = std::min<long long>((n_pairs + csize - 1) / csize * csize, (long long)(sms / csize) * csize);
+  const int grid = (int)g;
   NSOS_CHECK_CUDA(cudaMemsetAsync(out.maps, 0, sizeof(float) * n_rays * P.ML, st));
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = need; lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
   if (exact) {
     NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    k_render_tc<true><<<grid, kThreads, need, st>>>(P);
+    NSOS_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_render_tc<true>, P));
   } else {
     NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    k_render_tc<false><<<grid, kThreads, need, st>>>(P);
+    NSOS_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_render_tc<false>, P));
   }
   NSOS_CHECK_CUDA(cudaGetLastError());
   return NSOS_OK;

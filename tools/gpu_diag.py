@@ -100,7 +100,8 @@ for kind in ("cfg1", "flower"):
 
 @step("throughput 4096 rays flower (exact/fast/simt)")
 def _():
-    for mode in ("exact", "fast", "simt"):
+    print("  NSOS_CLUSTER =", os.environ.get("NSOS_CLUSTER", "default(2)"))
+    for mode in ("exact", "fast") + (() if os.environ.get("NSOS_CLUSTER") else ("simt",)):
         net, g = make_net("flower", mode)
         rays = torch.from_numpy(np.tile(g["rays"], (1, 16, 1))).to(dev)
         with torch.no_grad():

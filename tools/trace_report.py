@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Per-stage timeline of CTA 0 of kernel A (NSOS_TRACE=1): where the cycles of a tile go."""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ["NSOS_TRACE"] = "1"
+import nerfsos_b200
+from tools_common import make_net, load_golden   # noqa
+mode = sys.argv[1] if len(sys.argv) > 1 else "exact"
+net = make_net(mode)
+g = load_golden("flower_eval_256")
+rays = torch.from_numpy(np.tile(g["rays"], (1, 16, 1))).cuda()
+with torch.no_grad():
+    for _ in range(3):
+        net(rays, (1.2, 12.0))
+torch.cuda.synchronize()
+tr = net._ws[:16 * 16 * 6 * 8].view(torch.int64).reshape(16, 16, 6).cpu().numpy()
+print(f"mode={mode}: stamps of CTA 0 (cycles). per stage: acc_wait = worker waits for MMA; epi = epilogue (thread 0);")
+print("mma_lead = a_ready seen by MMA warp -> accumulator ready (MMA execution incl. issue); issue = MMA warp issue time")
+for tile in range(8):
+    t = tr[tile]
+    if t[0, 1] == 0: break
+    nst = int((t[:, 1] > 0).sum())
+    base = t[0, 0]
+    rows = []
+    for st in range(nst):
+        w0, acc, epi, ar, iss = t[st, 0], t[st, 1], t[st, 2], t[st, 3], t[st, 4]
+        rows.append((st, acc - w0, epi - acc, acc - ar, iss - ar))
+    tot = t[nst - 1, 2] - t[0, 0]
+    print(f"tile {tile}: {nst} stages, total {tot} cycles;  sum acc_wait {sum(r[1] for r in rows)}  sum epi {sum(r[2] for r in rows)}  sum mma_exec {sum(r[3] for r in rows)}")
+    if tile in (1, 2):
+        for r in rows: print(f"    stage {r[0]:2d}: acc_wait {r[1]:6d}  epi {r[2]:6d}  mma_exec {r[3]:6d}  issue {r[4]:6d}")
+    if tile + 1 < 16 and tr[tile + 1][0, 0] > 0:
+        print(f"    gap to next tile's first wait (setup/composite): {tr[tile + 1][0, 0] - t[nst - 1, 2]}")
+
+
+g = tr[15].reshape(-1)
+for ps, name in ((0, "coarse"), (1, "fine")):
+    d = g[ps * 16: ps * 16 + 16]
+    if d[8] == 0: continue
+    print(f"post-{name} phase (thread 0): composite {d[9]-d[8]}  total {d[10]-d[8]}")
