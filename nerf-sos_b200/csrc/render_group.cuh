@@ -157,17 +157,30 @@ __device__ inline void group_importance(const ImportanceIO& io, int tid, int bar
   for (int j = tid; j < io.K; j += kGroup) { double d = (double)io.zall[io.Sc + j] - mean; s2 += d * d; }
   s2 = group_sum(s2, tid, bar_id, gs.d);
   if (tid == 0 && io.z_std) *io.z_std = (float)sqrt(s2 / (double)io.K);
-  // sort(cat([z, z_samples])) (:161) by stable rank
+  // sort(cat([z, z_samples])) (:161) by stable rank.
   const int n = io.Sc + io.K;
-  for (int e = tid; e < n; e += kGroup) {
-    const float v = io.zall[e];
-    int rank = 0;
-#pragma unroll 8
-    for (int i = 0; i < n; ++i) {
-      float x = io.zall[i];
-      rank += (x < v) || (x == v && i < e);
+  if (io.det) {
+    // eval mode: u ascends, the inverse CDF is monotone, so both lists are already sorted -> merge by binary search:
+    //   rank(coarse i) = i + #{samples <  z_i}      rank(sample j) = j + #{coarse <= s_j}
+    const float* smp = io.zall + io.Sc;
+    for (int e = tid; e < n; e += kGroup) {
+      const float v = io.zall[e];
+      int lo = 0, hi, rank;
+      if (e < io.Sc) { hi = io.K; while (lo < hi) { int m = (lo + hi) >> 1; if (smp[m] < v) lo = m + 1; else hi = m; } rank = e + lo; }
+      else { hi = io.Sc; while (lo < hi) { int m = (lo + hi) >> 1; if (io.zall[m] <= v) lo = m + 1; else hi = m; } rank = (e - io.Sc) + lo; }
+      io.zsorted[rank] = v;
     }
-    io.zsorted[rank] = v;
+  } else {
+    for (int e = tid; e < n; e += kGroup) {
+      const float v = io.zall[e];
+      int rank = 0;
+#pragma unroll 8
+      for (int i = 0; i < n; ++i) {
+        float x = io.zall[i];
+        rank += (x < v) || (x == v && i < e);
+      }
+      io.zsorted[rank] = v;
+    }
   }
   group_bar(bar_id);
 }

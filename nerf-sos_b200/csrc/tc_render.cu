@@ -398,27 +398,47 @@ template <int KIND, bool EXACT>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
                                           const float* __restrict__ hw, int sem_dim, float* hacc, float* __restrict__ gout) {
   uint32_t hi[kCW / 2], lo[kCW / 2];
+  // bias and head weights of this chunk as 16-byte shared loads (c0 is a multiple of 16 floats; all bases 16 B aligned)
+  float bz[kCW], h0[kCW], h1[kCW], h2[kCW];
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+#pragma unroll
+    for (int q = 0; q < kCW / 4; ++q) { float4 t4 = b4[q]; bz[4 * q] = t4.x; bz[4 * q + 1] = t4.y; bz[4 * q + 2] = t4.z; bz[4 * q + 3] = t4.w; }
+    if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_RGB) {
+      const int o0 = (KIND == EPI_HIDDEN_SIGMA) ? kHeadWAlpha : (KIND == EPI_SEM) ? kHeadWS2 : kHeadWRgb;
+      const float4* w0 = reinterpret_cast<const float4*>(hw + o0 + c0);
+      const float4* w1 = reinterpret_cast<const float4*>(hw + o0 + kHalfMax + c0);
+      const float4* w2 = reinterpret_cast<const float4*>(hw + o0 + 2 * kHalfMax + c0);
+#pragma unroll
+      for (int q = 0; q < kCW / 4; ++q) {
+        float4 t4 = w0[q]; h0[4 * q] = t4.x; h0[4 * q + 1] = t4.y; h0[4 * q + 2] = t4.z; h0[4 * q + 3] = t4.w;
+        if (KIND != EPI_HIDDEN_SIGMA) { t4 = w1[q]; h1[4 * q] = t4.x; h1[4 * q + 1] = t4.y; h1[4 * q + 2] = t4.z; h1[4 * q + 3] = t4.w; }
+        if (KIND == EPI_RGB) { t4 = w2[q]; h2[4 * q] = t4.x; h2[4 * q + 1] = t4.y; h2[4 * q + 2] = t4.z; h2[4 * q + 3] = t4.w; }
+      }
+    }
+  }
 #pragma unroll
   for (int j = 0; j < kCW; j += 2) {
-    float x0 = fmaf(__uint_as_float(v[j]), inv16, bias[c0 + j]);
-    float x1 = fmaf(__uint_as_float(v[j + 1]), inv16, bias[c0 + j + 1]);
+    float x0 = fmaf(__uint_as_float(v[j]), inv16, bz[j]);
+    float x1 = fmaf(__uint_as_float(v[j + 1]), inv16, bz[j + 1]);
     if (KIND != EPI_FEAT && KIND != EPI_RAW) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
     if (KIND == EPI_HIDDEN_SIGMA) {
-      hacc[0] = fmaf(hw[kHeadWAlpha + c0 + j], x0, hacc[0]);
-      hacc[0] = fmaf(hw[kHeadWAlpha + c0 + j + 1], x1, hacc[0]);
+      hacc[0] = fmaf(h0[j], x0, hacc[0]);
+      hacc[0] = fmaf(h0[j + 1], x1, hacc[0]);
     } else if (KIND == EPI_SEM) {
+      // sem_dim <= 2 uses the vector-loaded rows; wider heads fall back to scalar shared loads
+      hacc[0] = fmaf(h0[j], x0, hacc[0]); hacc[0] = fmaf(h0[j + 1], x1, hacc[0]);
+      if (sem_dim > 1) { hacc[1] = fmaf(h1[j], x0, hacc[1]); hacc[1] = fmaf(h1[j + 1], x1, hacc[1]); }
 #pragma unroll
-      for (int s = 0; s < kSemMax; ++s)
+      for (int s = 2; s < kSemMax; ++s)
         if (s < sem_dim) {
           hacc[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j], x0, hacc[s]);
           hacc[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j + 1], x1, hacc[s]);
         }
     } else if (KIND == EPI_RGB) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        hacc[k] = fmaf(hw[kHeadWRgb + k * kHalfMax + c0 + j], x0, hacc[k]);
-        hacc[k] = fmaf(hw[kHeadWRgb + k * kHalfMax + c0 + j + 1], x1, hacc[k]);
-      }
+      hacc[0] = fmaf(h0[j], x0, hacc[0]); hacc[0] = fmaf(h0[j + 1], x1, hacc[0]);
+      hacc[1] = fmaf(h1[j], x0, hacc[1]); hacc[1] = fmaf(h1[j + 1], x1, hacc[1]);
+      hacc[2] = fmaf(h2[j], x0, hacc[2]); hacc[2] = fmaf(h2[j + 1], x1, hacc[2]);
     } else if (KIND == EPI_RAW) {
       gout[c0 + j] = x0 * (1.f / kActScale); gout[c0 + j + 1] = x1 * (1.f / kActScale);
     }
@@ -496,7 +516,7 @@ __device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int wa
 template <bool EXACT>
 __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   Smem sm;
   carve_smem(base, P.nslots, P.Sc, P.Sf, P.C, &sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
@@ -584,11 +604,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
       }
       named_bar_sync(1, kWorkers);
 
+#pragma unroll 1
       for (int pass = 0; pass < npass; ++pass) {
         const TcProg& pg = P.prog[pass];
         const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[pass]);
         const float* hw = sm.heads + pass * kHeadFloats;
         const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
+#pragma unroll 1
         for (int tile = 0; tile < ntiles; ++tile) {
           // ---- tile setup: sample position, point, gamma(x) -> swizzled smem A tile (each half-warp-group writes 32 columns)
           const int q = tile * 128 + row;
@@ -620,6 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           ++ntile_seen;
 
           float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0] sigma, [1..3] rgb, [4..7] sem (partial over my columns)
+#pragma unroll 1
           for (int st = 0; st < pg.nst; ++st) {
             const TcStage& Sg = pg.st[st];
             float* sb = sm.sbias + (it_bias & 1u) * 256;
@@ -733,7 +756,7 @@ struct SelfParams {
 template <bool EXACT>
 __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant__ SelfParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   Smem sm;
   carve_smem(base, P.nslots, 2, 2, 8, &sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
