@@ -133,9 +133,12 @@ int nsos_render_fwd(const NsosRenderCfg* cfg, const float* params_coarse, const 
  * importance samples are detached, sampler.py:159, so the two passes are independent); the randoms /
  * seed must equal the forward call's.  Gradients are ACCUMULATED into grads_* (flat layout of
  * nsos_param_layout); trunk_grads=0 computes only semantic_linear.{0,2} (--fix_backbone,
- * run_nerf.py:307-318).  Runs in fp32 on CUDA cores. */
-size_t nsos_render_bwd_workspace_bytes(const NsosRenderCfg* cfg, int64_t n_rays);
+ * run_nerf.py:307-318).  With trunk_grads=0 and a tcgen05 cfg->mode the trunk is recomputed on the tensor
+ * cores from packed_* (the images nsos_render_fwd used; may be NULL in NSOS_MODE_SIMT_FP32) and only the
+ * semantic-head GEMMs run in fp32 on CUDA cores; otherwise everything runs in fp32 on CUDA cores. */
+size_t nsos_render_bwd_workspace_bytes(const NsosRenderCfg* cfg, int64_t n_rays, int trunk_grads);
 int nsos_render_bwd(const NsosRenderCfg* cfg, const float* params_coarse, const float* params_fine,
+                    const void* packed_coarse, const void* packed_fine,
                     const float* rays_o, const float* rays_d, const float* z_vals0, const float* z_vals,
                     const NsosRandoms* rnd, uint64_t seed, const float* g_maps, float* grads_coarse,
                     float* grads_fine, int trunk_grads, void* workspace, size_t workspace_bytes,

@@ -9,11 +9,11 @@ size_t simt_render_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays);
 int simt_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, const float* rays_o, const float* rays_d,
                     const float* near, const float* far, const NsosRandoms* rnd, uint64_t seed, const NsosRenderOut& out,
                     void* workspace, size_t workspace_bytes, int64_t n_rays, cudaStream_t st);
-size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays);
+size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays, int trunk);
 int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, const float* rays_o, const float* rays_d,
                     const float* z_vals0, const float* z_vals, const NsosRandoms* rnd, uint64_t seed, const float* g_maps,
-                    float* grads_c, float* grads_f, int trunk, void* workspace, size_t workspace_bytes, int64_t n_rays,
-                    cudaStream_t st);
+                    float* grads_c, float* grads_f, int trunk, const void* packed_c, const void* packed_f, void* workspace,
+                    size_t workspace_bytes, int64_t n_rays, cudaStream_t st);
 int simt_invert_cdf(const float* bins, const float* cdf, const float* u, float* samples, int64_t* inds, int64_t n_rays, int M, int K,
                     cudaStream_t st);
 size_t simt_mlp_workspace_bytes(const NetGeom& g, int64_t P);
@@ -28,6 +28,10 @@ int tc_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, co
                   const float* rays_o, const float* rays_d, const float* near, const float* far, const NsosRandoms* rnd,
                   uint64_t seed, const NsosRenderOut& out, void* workspace, size_t workspace_bytes, int64_t n_rays,
                   cudaStream_t st);
+bool tc_net_supported(const NsosNetDesc& net);
+int tc_render_replay(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
+                     const float* z0, const float* z1, float* raw0, float* raw1, float* h0, float* s00, float* h1, float* s01,
+                     int64_t n_rays, cudaStream_t st);
 int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,
                 cudaStream_t st);
 

@@ -3,7 +3,9 @@
 //    for configurations the fused kernel does not cover, e.g. BASELINE config[0] D=4 W=64)
 //  * backward (recompute-in-backward, chunked) for training: replaces autograd through
 //    models/nerf_mlp.py:67-100 and models/renderer.py:21-85 (engines/trainer.py:201).
+#include <cstdlib>
 #include "render_device.cuh"
+#include "internal.h"
 
 namespace nsos {
 
@@ -432,23 +434,95 @@ size_t carve_bwd(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& gf,
 }
 }  // namespace
 
-size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays) {
+// Semantic-head-only backward with the trunk recomputed on tensor cores (tc_render_replay): per chunk the replay kernel
+// leaves h_last / s0 / raw per point, the GEMMs below only touch the 4 semantic_linear tensors.
+namespace {
+int64_t bwd_tc_chunk_rays(int64_t n_rays) { return n_rays < 4096 ? n_rays : 4096; }
+struct BwdTcWs {
+  float *enc, *encv, *dnorm, *raw[2], *g_raw, *h[2], *s0[2], *g_half;
+};
+size_t carve_bwd_tc(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& gf, int64_t R, char* base, BwdTcWs* ws) {
+  const bool fine = cfg.n_importance > 0;
+  const int Sc = cfg.n_samples, Sf = cfg.n_samples + cfg.n_importance;
+  const int64_t P0 = R * Sc, P1 = fine ? R * Sf : 0, Pm = std::max(P0, P1);
+  Carver c{base, 0, 0};
+  BwdTcWs w{};
+  w.enc = c.take<float>(Pm * kEncLd); w.encv = c.take<float>(R * kEncVLd); w.dnorm = c.take<float>(R);
+  w.raw[0] = c.take<float>(P0 * gc.C); w.raw[1] = c.take<float>(P1 * gf.C + 1);
+  w.g_raw = c.take<float>(Pm * std::max(gc.C, gf.C));
+  w.h[0] = c.take<float>(P0 * gc.W); w.s0[0] = c.take<float>(P0 * (gc.W / 2));
+  w.h[1] = c.take<float>(P1 * gf.W + 1); w.s0[1] = c.take<float>(P1 * (gf.W / 2) + 1);
+  w.g_half = c.take<float>(Pm * (std::max(gc.W, gf.W) / 2 + 1));
+  if (ws) *ws = w;
+  return align_up(c.off, 256);
+}
+bool bwd_uses_tc(const NsosRenderCfg& cfg, int trunk, const NetGeom& gc, const NetGeom& gf) {
+  if (trunk || !(cfg.mode == NSOS_MODE_TC_EXACT || cfg.mode == NSOS_MODE_TC_FAST)) return false;
+  if (getenv("NSOS_BWD_SIMT")) return false;   // parity tests: force the all-fp32 recompute
+  if (!gc.use_sem || !gf.use_sem || cfg.n_samples > 128) return false;
+  return tc_net_supported(cfg.coarse) && (cfg.n_importance == 0 || tc_net_supported(cfg.fine));
+}
+}  // namespace
+
+size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays, int trunk) {
   NetGeom gc, gf;
   if (!make_geom(cfg.coarse, gc)) return 0;
   if (cfg.n_importance > 0) { if (!make_geom(cfg.fine, gf)) return 0; } else gf = gc;
+  if (bwd_uses_tc(cfg, trunk, gc, gf)) return carve_bwd_tc(cfg, gc, gf, bwd_tc_chunk_rays(n_rays), nullptr, nullptr);
   return carve_bwd(cfg, gc, gf, bwd_chunk_rays(n_rays), nullptr, nullptr);
 }
 
 int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, const float* rays_o, const float* rays_d,
                     const float* z_vals0, const float* z_vals, const NsosRandoms* rnd, uint64_t seed, const float* g_maps,
-                    float* grads_c, float* grads_f, int trunk, void* workspace, size_t workspace_bytes, int64_t n_rays,
-                    cudaStream_t st) {
+                    float* grads_c, float* grads_f, int trunk, const void* packed_c, const void* packed_f, void* workspace,
+                    size_t workspace_bytes, int64_t n_rays, cudaStream_t st) {
   NetGeom gc, gf;
   NSOS_REQUIRE(make_geom(cfg.coarse, gc), NSOS_ERR_UNSUPPORTED, "invalid coarse net descriptor");
   const bool fine = cfg.n_importance > 0;
   if (fine) NSOS_REQUIRE(make_geom(cfg.fine, gf), NSOS_ERR_UNSUPPORTED, "invalid fine net descriptor"); else gf = gc;
   const int Sc = cfg.n_samples, K = cfg.n_importance, Sf = Sc + K;
   NSOS_REQUIRE(Sc >= 2 && Sf <= kMaxS, NSOS_ERR_UNSUPPORTED, "n_samples/n_importance out of range");
+  if (!trunk && !gc.use_sem && !gf.use_sem) return NSOS_OK;   // nothing trainable outside the trunk
+  if (bwd_uses_tc(cfg, trunk, gc, gf)) {
+    NSOS_REQUIRE(packed_c && (!fine || packed_f), NSOS_ERR_BAD_ARG, "nsos_render_bwd: tcgen05 modes need the packed weights");
+    const int64_t R = bwd_tc_chunk_rays(n_rays);
+    BwdTcWs w;
+    size_t need = carve_bwd_tc(cfg, gc, gf, R, (char*)workspace, &w);
+    NSOS_REQUIRE(workspace_bytes >= need, NSOS_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+    const int C6 = 6 + gc.sem_dim, ML = 2 * C6 + 1;
+    NsosRandoms rn{nullptr, nullptr, nullptr, nullptr};
+    if (rnd) rn = *rnd;
+    for (int64_t r0 = 0; r0 < n_rays; r0 += R) {
+      const int64_t n = std::min(R, n_rays - r0);
+      const float* ro = rays_o + r0 * 3; const float* rd = rays_d + r0 * 3;
+      const float* zc = (fine ? z_vals0 : z_vals) + r0 * Sc;
+      const float* zf = fine ? z_vals + r0 * Sf : nullptr;
+      int rc = tc_render_replay(cfg, packed_c, fine ? packed_f : packed_c, ro, rd, zc, zf, w.raw[0], w.raw[1], w.h[0], w.s0[0], w.h[1],
+                                w.s0[1], n, st);
+      if (rc) return rc;
+      k_encode_dirs<<<grid1(n), 256, 0, st>>>(rd, w.encv, w.dnorm, n, gc.Lv);
+      for (int pass = 0; pass < (fine ? 2 : 1); ++pass) {
+        const bool is_fine = fine && pass == 1;
+        const NetGeom& g = is_fine ? gf : gc;
+        const int S = is_fine ? Sf : Sc;
+        const float* z = is_fine ? zf : zc;
+        const float* noise = is_fine ? rn.noise1 : rn.noise0;
+        const int moff = (fine && !is_fine) ? C6 : 0;
+        const int64_t P = n * S;
+        k_encode_pts<<<grid1(P), 256, 0, st>>>(ro, rd, z, w.enc, P, S, g.Lp);
+        k_composite_bwd<<<grid1(n * 32, 128), 128, 0, st>>>(w.raw[pass], z, w.dnorm, noise ? noise + r0 * S : nullptr, cfg.raw_noise_std,
+                                                             seed, r0, is_fine ? RNG_NOISE1 : RNG_NOISE0, S, g.C, g.sem_dim,
+                                                             cfg.white_bkgd, g_maps + r0 * ML, ML, moff, w.g_raw, n);
+        NSOS_CHECK_CUDA(cudaGetLastError());
+        MlpBufs b{};
+        b.h[g.D - 1] = w.h[pass]; b.s0 = w.s0[pass];
+        BwdBufs bw{w.g_raw, {nullptr, nullptr}, w.g_half, nullptr};
+        rc = mlp_backward(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, w.enc, w.encv, S, P, b, bw, 0, st);
+        if (rc) return rc;
+      }
+    }
+    return NSOS_OK;
+  }
   const int64_t R = bwd_chunk_rays(n_rays);
   BwdWs w;
   size_t need = carve_bwd(cfg, gc, gf, R, (char*)workspace, &w);

@@ -204,6 +204,10 @@ struct TcParams {
   float perturb, noise_std;
   int white_bkgd, exact, fine, C, sem_dim, C6, ML, nslots;
   long long* trace;   // optional timeline buffer (NSOS_TRACE=1): clock64 stamps of CTA 0, see tools/trace_report.py
+  // replay (backward recompute on given samples): sample depths in, last trunk activation / semantic hidden layer out
+  const float* z_in[2];
+  float* dump_h[2];    // [n_rays*S, W]   relu(pts_linears[D-1])
+  float* dump_s0[2];   // [n_rays*S, W/2] relu(semantic_linear.0)
 };
 constexpr int kTraceTiles = 16, kTraceStamps = 6;   // [tile][stage][stamp]
 
@@ -394,7 +398,7 @@ __device__ __forceinline__ void encode_half(const float x[3], int L, int enc, bo
 // One 16-column chunk of an epilogue.  v = D read-out (already waited for).  x16 = 16*x = acc*inv16 + bias16
 // (+relu) feeds the fp32 head accumulators (head weights are pre-divided by 16) and/or becomes the next A operand.
 constexpr int kCW = 16;   // epilogue chunk width in columns
-template <int KIND, bool EXACT>
+template <int KIND, bool EXACT, bool DUMP>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
                                           const float* __restrict__ hw, int sem_dim, float* hacc, float* __restrict__ gout) {
   uint32_t hi[kCW / 2], lo[kCW / 2];
@@ -442,6 +446,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_
     } else if (KIND == EPI_RAW) {
       gout[c0 + j] = x0 * (1.f / kActScale); gout[c0 + j + 1] = x1 * (1.f / kActScale);
     }
+    if (DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM) && gout)
+      *reinterpret_cast<float2*>(gout + c0 + j) = make_float2(x0 * (1.f / kActScale), x1 * (1.f / kActScale));
     if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FEAT) {
       __half2 hh = __floats2half2_rn(x0, x1);
       hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
@@ -458,7 +464,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_
   }
 }
 
-template <int KIND, bool EXACT>
+template <int KIND, bool EXACT, bool DUMP>
 __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw, int sem_dim,
                                          float* hacc, float* gout) {
   // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
@@ -468,27 +474,27 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float
   tmem_wait_ld_fence16(va);
   for (int c = cb; c < ce; c += 2) {
     if (c + 1 < ce) tmem_ld16(tm_lane + kColD + (c + 1) * kCW, vb);
-    epi_chunk<KIND, EXACT>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, hacc, gout);
+    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, hacc, gout);
     if (c + 1 < ce) {
       tmem_wait_ld_fence16(vb);
       if (c + 2 < ce) tmem_ld16(tm_lane + kColD + (c + 2) * kCW, va);
-      epi_chunk<KIND, EXACT>(vb, tm_lane, (c + 1) * kCW, inv16, bias, hw, sem_dim, hacc, gout);
+      epi_chunk<KIND, EXACT, DUMP>(vb, tm_lane, (c + 1) * kCW, inv16, bias, hw, sem_dim, hacc, gout);
       if (c + 2 < ce) tmem_wait_ld_fence16(va);
     }
   }
 }
 
 // 16-column chunks [cb, ce) of a stage
-template <bool EXACT>
+template <bool EXACT, bool DUMP = false>
 __device__ __forceinline__ void epilogue(int kind, int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw,
                                          int sem_dim, float* hacc, float* gout) {
   switch (kind) {
-    case EPI_HIDDEN: epi_kind<EPI_HIDDEN, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    case EPI_HIDDEN_SIGMA: epi_kind<EPI_HIDDEN_SIGMA, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    case EPI_SEM: epi_kind<EPI_SEM, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    case EPI_FEAT: epi_kind<EPI_FEAT, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    case EPI_RGB: epi_kind<EPI_RGB, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    default: epi_kind<EPI_RAW, EXACT>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_HIDDEN: epi_kind<EPI_HIDDEN, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_HIDDEN_SIGMA: epi_kind<EPI_HIDDEN_SIGMA, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_SEM: epi_kind<EPI_SEM, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_FEAT: epi_kind<EPI_FEAT, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_RGB: epi_kind<EPI_RGB, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    default: epi_kind<EPI_RAW, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
   }
 }
 
@@ -513,7 +519,7 @@ __device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int wa
   tc_fence_after();
 }
 
-template <bool EXACT>
+template <bool EXACT, bool REPLAY>
 __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
@@ -578,7 +584,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
         float* rp = sm.rayp + t * kRayP;
         float d0 = P.rays_d[rr * 3], d1 = P.rays_d[rr * 3 + 1], d2 = P.rays_d[rr * 3 + 2];
         rp[0] = P.rays_o[rr * 3]; rp[1] = P.rays_o[rr * 3 + 1]; rp[2] = P.rays_o[rr * 3 + 2];
-        rp[3] = d0; rp[4] = d1; rp[5] = d2; rp[6] = P.near[rr]; rp[7] = P.far[rr];
+        rp[3] = d0; rp[4] = d1; rp[5] = d2;
+        rp[6] = REPLAY ? 0.f : P.near[rr]; rp[7] = REPLAY ? 1.f : P.far[rr];
         float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
         rp[8] = nrm; rp[9] = valid ? 1.f : 0.f;
         float vd[3] = {__fdiv_rn(d0, nrm), __fdiv_rn(d1, nrm), __fdiv_rn(d2, nrm)};
@@ -620,7 +627,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           const long long ray = pair * 2 + rl;
           {
             float z;
-            if (pass == 0) {
+            if (REPLAY) {
+              z = (rowvalid && rp[9] > 0.f) ? P.z_in[pass][ray * S + i] : 1.f;
+            } else if (pass == 0) {
               const bool pert = P.perturb > 0.f;
               float tr = 0.f;
               if (pert) tr = (P.rnd.t_rand && rp[9] > 0.f) ? P.rnd.t_rand[ray * P.Sc + i] : rng_uniform(P.seed, ray, RNG_T_RAND, i);
@@ -659,7 +668,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             tc_fence_after();
             if (tr) tr[st * kTraceStamps + 1] = clock64();                 // accumulator ready
             float* ha = (Sg.epi == EPI_HIDDEN_SIGMA) ? &hacc[0] : (Sg.epi == EPI_SEM) ? &hacc[4] : &hacc[1];
-            epilogue<EXACT>(Sg.epi, cb, ce, tm_lane, inv16, bias, hw, P.sem_dim, ha, nullptr);
+            float* gout = nullptr;
+            if (REPLAY && rowvalid && rp[9] > 0.f) {
+              const size_t pt = (size_t)ray * S + i;
+              if (Sg.epi == EPI_HIDDEN_SIGMA && P.dump_h[pass]) gout = P.dump_h[pass] + pt * pg.W;
+              if (Sg.epi == EPI_SEM && P.dump_s0[pass]) gout = P.dump_s0[pass] + pt * pg.H2;
+            }
+            epilogue<EXACT, REPLAY>(Sg.epi, cb, ce, tm_lane, inv16, bias, hw, P.sem_dim, ha, gout);
             if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
             if (st + 1 < pg.nst) {
               if (Sg.epi != EPI_SEM) tmem_wait_st();
@@ -690,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
         // The gamma tiles are idle between tiles (all MMAs of the tile have completed): their first bytes serve as
         // reduction scratch here.
         named_bar_sync(1, kWorkers);
-        {
+        if (!REPLAY) {
           const int gr = warp >> 2, gt = t & (kGroup - 1), gbar = 2 + gr;
           long long* gdbg = (P.trace && blockIdx.x == 0 && itp == 0 && t == 0) ? P.trace + (size_t)(kTraceTiles - 1) * 16 * kTraceStamps + pass * 16 : nullptr;
           if (gdbg) gdbg[8] = clock64();
@@ -857,10 +872,17 @@ int tc_pack_weights(const NsosNetDesc& net, const float* params, void* packed, i
 
 size_t tc_render_workspace_bytes(const NsosRenderCfg&, int64_t) { return sizeof(long long) * kTraceTiles * 16 * kTraceStamps + 256; }
 
-int tc_render_fwd(const NsosRenderCfg& cfg, const float* /*pc*/, const float* /*pf*/, const void* packed_c, const void* packed_f,
-                  const float* rays_o, const float* rays_d, const float* near, const float* far, const NsosRandoms* rnd,
-                  uint64_t seed, const NsosRenderOut& out, void* workspace, size_t workspace_bytes, int64_t n_rays,
-                  cudaStream_t st) {
+namespace {
+struct ReplayIO {
+  const float* z_in[2];
+  float* dump_h[2];
+  float* dump_s0[2];
+};
+
+// common launcher of k_render_tc: forward (replay == nullptr) or backward recompute on given sample depths
+int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
+              const float* near, const float* far, const NsosRandoms* rnd, uint64_t seed, const NsosRenderOut& out,
+              const ReplayIO* replay, void* workspace, size_t workspace_bytes, int64_t n_rays, cudaStream_t st) {
   NetGeom gc, gf;
   NSOS_REQUIRE(make_geom(cfg.coarse, gc), NSOS_ERR_UNSUPPORTED, "invalid coarse net descriptor");
   const bool fine = cfg.n_importance > 0;
@@ -882,7 +904,9 @@ int tc_render_fwd(const NsosRenderCfg& cfg, const float* /*pc*/, const float* /*
   P.seed = seed; P.out = out; P.n_rays = n_rays; P.Sc = Sc; P.K = K; P.Sf = fine ? Sf : Sc;
   P.perturb = cfg.perturb; P.noise_std = cfg.raw_noise_std; P.white_bkgd = cfg.white_bkgd; P.exact = exact; P.fine = fine;
   P.C = gc.C; P.sem_dim = gc.sem_dim; P.C6 = 6 + gc.sem_dim; P.ML = 2 * P.C6 + 1;
-  if (getenv("NSOS_TRACE") && workspace && workspace_bytes >= tc_render_workspace_bytes(cfg, n_rays)) {
+  if (replay)
+    for (int i = 0; i < 2; ++i) { P.z_in[i] = replay->z_in[i]; P.dump_h[i] = replay->dump_h[i]; P.dump_s0[i] = replay->dump_s0[i]; }
+  if (!replay && getenv("NSOS_TRACE") && workspace && workspace_bytes >= tc_render_workspace_bytes(cfg, n_rays)) {
     P.trace = reinterpret_cast<long long*>(workspace);
     NSOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(long long) * kTraceTiles * 16 * kTraceStamps, st));
   }
@@ -909,22 +933,48 @@ int tc_render_fwd(const NsosRenderCfg& cfg, const float* /*pc*/, const float* /*
   while (csize > 1 && n_pairs < csize) csize >>= 1;
   long long g = std::min<long long>((n_pairs + csize - 1) / csize * csize, (long long)(sms / csize) * csize);
   const int grid = (int)g;
-  NSOS_CHECK_CUDA(cudaMemsetAsync(out.maps, 0, sizeof(float) * n_rays * P.ML, st));
+  if (!replay) NSOS_CHECK_CUDA(cudaMemsetAsync(out.maps, 0, sizeof(float) * n_rays * P.ML, st));
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = need; lc.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   lc.attrs = attr; lc.numAttrs = 1;
-  if (exact) {
-    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    NSOS_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_render_tc<true>, P));
-  } else {
-    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    NSOS_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_render_tc<false>, P));
-  }
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&lc, kern, P);
+  };
+  if (replay) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, true>) : launch(k_render_tc<false, true>));
+  else NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, false>) : launch(k_render_tc<false, false>));
   NSOS_CHECK_CUDA(cudaGetLastError());
   return NSOS_OK;
+}
+}  // namespace
+
+int tc_render_fwd(const NsosRenderCfg& cfg, const float* /*pc*/, const float* /*pf*/, const void* packed_c, const void* packed_f,
+                  const float* rays_o, const float* rays_d, const float* near, const float* far, const NsosRandoms* rnd,
+                  uint64_t seed, const NsosRenderOut& out, void* workspace, size_t workspace_bytes, int64_t n_rays,
+                  cudaStream_t st) {
+  return tc_launch(cfg, packed_c, packed_f, rays_o, rays_d, near, far, rnd, seed, out, nullptr, workspace, workspace_bytes, n_rays, st);
+}
+
+bool tc_net_supported(const NsosNetDesc& net) {
+  NetGeom g;
+  return make_geom(net, g) && tc_supported(g, nullptr);
+}
+
+// Backward recompute: evaluates both nets at the SAVED sample depths (no sampling, no compositing) and writes, per point, the
+// raw outputs plus the last trunk activation and the semantic hidden layer -- everything the semantic-head gradients need.
+int tc_render_replay(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
+                     const float* z0, const float* z1, float* raw0, float* raw1, float* h0, float* s00, float* h1, float* s01,
+                     int64_t n_rays, cudaStream_t st) {
+  ReplayIO io{{z0, z1}, {h0, h1}, {s00, s01}};
+  NsosRenderOut out;
+  memset(&out, 0, sizeof(out));
+  const bool fine = cfg.n_importance > 0;
+  if (fine) { out.raw0 = raw0; out.raw = raw1; } else { out.raw = raw0; }
+  return tc_launch(cfg, packed_c, packed_f, rays_o, rays_d, nullptr, nullptr, nullptr, 0, out, &io, nullptr, 0, n_rays, st);
 }
 
 int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,

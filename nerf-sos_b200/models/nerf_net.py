@@ -109,9 +109,13 @@ class _RenderFn(torch.autograd.Function):
                 sem_ids |= {id(p) for p in m.semantic_linear.parameters()}
         trunk = int(any(r and id(p) not in sem_ids for p, r in zip(plist, ctx.req)))
         rs = _lib.Randoms(*[_lib.ptr(ctx.rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
-        wsz = L.nsos_render_bwd_workspace_bytes(cfg, N)
+        wsz = L.nsos_render_bwd_workspace_bytes(cfg, N, trunk)
         ws = net._workspace(wsz, dev)
-        _lib.check(L.nsos_render_bwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(z0),
+        # the packed images of the forward call (parameters are unchanged between forward and backward)
+        pk_c = net.nerf.packed(cfg.mode)
+        pk_f = net.nerf_fine.packed(cfg.mode) if fine else pk_c
+        _lib.check(L.nsos_render_bwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
+                                     _lib.ptr(rays_d), _lib.ptr(z0),
                                      _lib.ptr(z1), C.byref(rs), ctx.seed, _lib.ptr(g_maps.contiguous()), _lib.ptr(g_c), _lib.ptr(g_f),
                                      trunk, _lib.ptr(ws), ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_bwd")
         grads = []

@@ -123,3 +123,52 @@ if SEL == "--all":
     for name in STEPS:
         r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=600)
         print(r.stdout[-6000:]); print(r.stderr[-1500:] if r.returncode else "", flush=True)
+
+
+@step("trainstep timing 32768 rays (--fix_backbone recipe, B=8 patches 64x64)")
+def _():
+    """fwd / bwd / full train_one_step time at the shipped batch (8 patches x 64x64 rays)."""
+    import dist_gpu_worker as W
+    a = W.Args()
+    a.use_correlation = True
+    net = W.make_net(dev)
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=2e-3)
+    from nerfsos_b200.engines.lr import LRScheduler
+    sched = LRScheduler(opt, 2e-3, 0.1, 250000)
+    losses = [None, None, W.CorrelationLoss(a), W.GeoCorrelationLoss(a)]
+    B, Ps = 8, 64
+    g = load_golden("flower_eval_256")
+    base = torch.from_numpy(g["rays"])
+    rays = base.repeat(1, B * Ps * Ps // base.shape[1], 1).permute(1, 0, 2).reshape(B, Ps * Ps, 2, 3).contiguous()
+    rays[..., 1, :] += 0.02 * torch.randn(B, Ps * Ps, 3, generator=torch.Generator().manual_seed(1))
+    gt = torch.rand(B, Ps * Ps, 3, generator=torch.Generator().manual_seed(0))
+    a.patch_size = Ps
+    for variant in ("tc", "simt"):
+        if variant == "simt":
+            os.environ["NSOS_BWD_SIMT"] = "1"
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ts = []
+        for it in range(3):
+            torch.cuda.synchronize()
+            ev[0].record()
+            out = W.train_one_step((rays, gt), [net, W.FakeDino()], opt, sched, W.Loader(), it + 1, losses, dev, a)
+            ev[1].record()
+            torch.cuda.synchronize()
+            ts.append(ev[0].elapsed_time(ev[1]))
+        print(f"  backward={variant}: train_one_step ms = {[round(t, 1) for t in ts]}  loss={out['loss'].item():.4f}  "
+              f"=> {B * Ps * Ps / (min(ts) * 1e-3):.0f} rays/s fwd+bwd+losses+Adam", flush=True)
+        # forward / backward split of the render alone
+        r = rays.reshape(-1, 2, 3).permute(1, 0, 2).contiguous().to(dev)
+        net.train()
+        for it in range(2):
+            torch.cuda.synchronize(); ev[0].record()
+            o = net(r, (1.2, 12.0))
+            ev[1].record(); torch.cuda.synchronize()
+            tf = ev[0].elapsed_time(ev[1])
+            l = o["semantics"].sum() + o["semantics0"].sum()
+            torch.cuda.synchronize(); ev[0].record()
+            l.backward()
+            ev[1].record(); torch.cuda.synchronize()
+            tb = ev[0].elapsed_time(ev[1])
+        print(f"  backward={variant}: render fwd {tf:.1f} ms, render bwd {tb:.1f} ms", flush=True)
+    os.environ.pop("NSOS_BWD_SIMT", None)
