@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "lib", "libnerfsos.so")
-SOURCES = ["api.cu", "simt_gemm.cu", "simt_render.cu", "tc_render.cu", "corr_loss.cu"]
+SOURCES = ["api.cu", "simt_gemm.cu", "simt_render.cu", "tc_render.cu", "tc_wgrad.cu", "corr_loss.cu"]
 
 MODE_SIMT, MODE_TC_EXACT, MODE_TC_FAST = 0, 1, 2
 MODES = {"simt": MODE_SIMT, "exact": MODE_TC_EXACT, "fast": MODE_TC_FAST}

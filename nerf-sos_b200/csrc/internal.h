@@ -32,6 +32,10 @@ bool tc_net_supported(const NsosNetDesc& net);
 int tc_render_replay(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
                      const float* z0, const float* z1, float* raw0, float* raw1, float* h0, float* s00, float* h1, float* s01,
                      int64_t n_rays, cudaStream_t st);
+// tc_wgrad.cu (semantic-head weight gradients on tcgen05)
+bool tc_sem_wgrad_supported(const NetGeom& g);
+int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, const float* s0,
+                 const float* g_raw, int64_t P, cudaStream_t st);
 int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,
                 cudaStream_t st);
 

@@ -514,10 +514,14 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
                                                              seed, r0, is_fine ? RNG_NOISE1 : RNG_NOISE0, S, g.C, g.sem_dim,
                                                              cfg.white_bkgd, g_maps + r0 * ML, ML, moff, w.g_raw, n);
         NSOS_CHECK_CUDA(cudaGetLastError());
-        MlpBufs b{};
-        b.h[g.D - 1] = w.h[pass]; b.s0 = w.s0[pass];
-        BwdBufs bw{w.g_raw, {nullptr, nullptr}, w.g_half, nullptr};
-        rc = mlp_backward(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, w.enc, w.encv, S, P, b, bw, 0, st);
+        if (tc_sem_wgrad_supported(g) && !getenv("NSOS_WGRAD_SIMT")) {
+          rc = tc_sem_wgrad(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, w.h[pass], w.enc, kEncLd, w.s0[pass], w.g_raw, P, st);
+        } else {
+          MlpBufs b{};
+          b.h[g.D - 1] = w.h[pass]; b.s0 = w.s0[pass];
+          BwdBufs bw{w.g_raw, {nullptr, nullptr}, w.g_half, nullptr};
+          rc = mlp_backward(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, w.enc, w.encv, S, P, b, bw, 0, st);
+        }
         if (rc) return rc;
       }
     }

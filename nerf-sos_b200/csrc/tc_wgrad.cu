@@ -1,0 +1,294 @@
+// Kernel C: weight gradients of the semantic head on the tcgen05 tensor cores (the --fix_backbone training recipe,
+// run_nerf.py:307-318 -- the only parameters every shipped config trains are semantic_linear.{0,2} of both nets).
+//
+// Replaces, for one net and one chunk of P sample points, autograd through nerf_mlp.py:79-80
+//     s0  = relu(W0 . [h, gamma] + b0)            (semantic_linear.0, 319 -> 128)
+//     sem = W2 . s0 + b2                          (semantic_linear.2, 128 -> sem_dim)
+// given g_sem = d(loss)/d(sem) per point (from the compositing backward):
+//     g_s0 = (W2^T g_sem) * [s0 > 0]
+//     dW0 += g_s0^T . [h, gamma]      db0 += sum_p g_s0        dW2 += g_sem^T . s0       db2 += sum_p g_sem
+//
+// The contraction runs over POINTS, so both operands are transposed on the way into shared memory: per slab of 64
+// points the 8 worker warps read h / gamma / s0 / g_raw rows (one point per lane), split every value into bf16 hi + lo,
+// pair neighbouring points with one shuffle and store K-major SWIZZLE_128B tiles
+//     A  [128 units   x 64 pts] = g_s0^T      B  [320 feats x 64 pts] = [h(256), gamma(63), 1]^T
+//     A2 [128 units   x 64 pts] = s0^T        B2 [ 16       x 64 pts] = g_sem^T (rows >= sem_dim zero)
+// and one elected thread issues 3 x 4 x 3 tcgen05.mma (hi.hi + lo.hi + hi.lo; M=128, N=256/64/16, K=16) that accumulate
+// in TMEM for the whole life of the CTA:  D[:, 0:319] = dW0, D[:, 319] = db0 (the constant-one feature), D[:, 320:324] =
+// dW2^T.  At the end every CTA adds its partial sums to the flat gradient buffer with atomics.
+// bf16 hi+lo carries 16 mantissa bits per operand with fp32 range (gradients can be far below the fp16 range).
+#include <cuda_bf16.h>
+
+#include "internal.h"
+#include "tc_ptx.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace nsos {
+namespace {
+using namespace ptx;
+
+constexpr int kWgWorkers = 256, kWgThreads = 288, kWgMmaWarp = 8;
+constexpr int kSlabPts = 64;
+constexpr int kRowsA = 128, kRowsB = 320, kRowsB2 = 16;
+constexpr int kColD1 = 0, kColD1b = 256, kColD2 = 320;
+constexpr uint32_t kWgTmemCols = 512;
+
+struct WgParams {
+  const float *h, *enc, *s0, *g_raw, *w_s2;
+  float *gW0, *gb0, *gW2, *gb2;
+  long long P;
+  int C, enc_dim, enc_ld, sem_dim, sem_coord, ld0;
+};
+
+struct WgSmem {
+  uint8_t *a[2], *a2[2], *b[2], *b2[2];   // [plane]: 0 = hi, 1 = lo
+  float* w2;                              // [4][128]
+  uint64_t *ready, *done;
+  uint32_t* tmem_ptr;
+};
+__host__ __device__ inline size_t wg_carve(uint8_t* base, WgSmem* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; size_t o = off; off += bytes; return o; };
+  size_t oa[2], oa2[2], ob[2], ob2[2];
+  for (int p = 0; p < 2; ++p) oa[p] = take(kRowsA * 128, 1024);
+  for (int p = 0; p < 2; ++p) oa2[p] = take(kRowsA * 128, 1024);
+  for (int p = 0; p < 2; ++p) ob[p] = take(kRowsB * 128, 1024);
+  for (int p = 0; p < 2; ++p) ob2[p] = take(kRowsB2 * 128, 1024);
+  size_t ow = take(sizeof(float) * 4 * 128, 16), obar = take(16, 8), otp = take(16, 16);
+  if (s) {
+    for (int p = 0; p < 2; ++p) { s->a[p] = base + oa[p]; s->a2[p] = base + oa2[p]; s->b[p] = base + ob[p]; s->b2[p] = base + ob2[p]; }
+    s->w2 = (float*)(base + ow); s->ready = (uint64_t*)(base + obar); s->done = s->ready + 1; s->tmem_ptr = (uint32_t*)(base + otp);
+  }
+  return off;
+}
+
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // D=f32, A=B=bf16, K-major
+}
+
+// bf16 hi in the low half, bf16 lo (= residual) in the high half
+__device__ __forceinline__ uint32_t split_bf16(float x) {
+  __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+
+// Values xa (tile row ra) and xb (tile row ra+4) of THIS lane's point; lanes 2k / 2k+1 hold neighbouring points.
+// Even lanes store row ra, odd lanes row ra+4 (their swizzle images use disjoint bank halves): one 32-bit word
+// (2 points) per plane.
+__device__ __forceinline__ void put_pair(uint8_t* hi_tile, uint8_t* lo_tile, int ra, float xa, float xb, int lane, int wd) {
+  const uint32_t pa = split_bf16(xa), pb = split_bf16(xb);
+  const bool even = (lane & 1) == 0;
+  const uint32_t recv = __shfl_xor_sync(0xffffffffu, even ? pb : pa, 1);
+  const uint32_t first = even ? pa : recv, second = even ? recv : pb;     // first = even point, second = odd point
+  const int R = even ? ra : ra + 4;
+  const size_t off = (size_t)(R >> 3) * 1024 + (size_t)(R & 7) * 128 + (size_t)((((wd >> 2) ^ (R & 7)) << 4) + ((wd & 3) << 2));
+  *reinterpret_cast<uint32_t*>(hi_tile + off) = __byte_perm(first, second, 0x5410);
+  *reinterpret_cast<uint32_t*>(lo_tile + off) = __byte_perm(first, second, 0x7632);
+}
+
+__device__ __forceinline__ void put8(uint8_t* hi_tile, uint8_t* lo_tile, int r0, const float (&v)[8], int lane, int wd) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) put_pair(hi_tile, lo_tile, r0 + i, v[i], v[4 + i], lane, wd);
+}
+
+__device__ __forceinline__ void load8(const float* __restrict__ src, bool valid, float (&v)[8]) {
+  if (valid) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) k_sem_wgrad(const __grid_constant__ WgParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  WgSmem sm;
+  wg_carve(base, &sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+  const long long nslabs = (P.P + kSlabPts - 1) / kSlabPts;
+  const long long my_slabs = (nslabs - blockIdx.x + gridDim.x - 1) / gridDim.x;     // >= 1 (grid <= nslabs)
+  if (t == 0) {
+    mbar_init(smem_u32(sm.ready), kWgWorkers);
+    mbar_init(smem_u32(sm.done), 1);
+    fence_mbar_init();
+  }
+  if (warp == kWgMmaWarp) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
+  // B2 rows >= 8 are never written by the fill: zero the whole small tile once;  W2 -> smem
+  for (int i = t; i < kRowsB2 * 128 / 4; i += kWgThreads) {
+    reinterpret_cast<uint32_t*>(sm.b2[0])[i] = 0u;
+    reinterpret_cast<uint32_t*>(sm.b2[1])[i] = 0u;
+  }
+  for (int i = t; i < 4 * 128; i += kWgThreads) sm.w2[i] = (i / 128 < P.sem_dim) ? __ldg(&P.w_s2[i]) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *sm.tmem_ptr;
+
+  if (warp == kWgMmaWarp) {
+    const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, a2[2] = {smem_u32(sm.a2[0]), smem_u32(sm.a2[1])};
+    const uint32_t b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])}, b2[2] = {smem_u32(sm.b2[0]), smem_u32(sm.b2[1])};
+    const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64), id16 = make_idesc_bf16(16);
+    for (long long it = 0; it < my_slabs; ++it) {
+      mbar_wait(smem_u32(sm.ready), (uint32_t)(it & 1), 700);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;     // hi.hi, lo.hi, hi.lo
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (it > 0 || pass > 0 || ks > 0) ? 1u : 0u;
+            const uint64_t da = make_sw128_desc(a[pa] + ks * 32), db = make_sw128_desc(b[pb] + ks * 32);
+            umma_ss(tm + kColD1, da, db, id256, acc);
+            umma_ss(tm + kColD1b, da, make_sw128_desc(b[pb] + 256 * 128 + ks * 32), id64, acc);
+            umma_ss(tm + kColD2, make_sw128_desc(a2[pa] + ks * 32), make_sw128_desc(b2[pb] + ks * 32), id16, acc);
+          }
+        }
+        umma_commit(smem_u32(sm.done));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int pgp = warp & 1, q = warp >> 1;            // point group (32 points), feature quarter
+    const int pl = 32 * pgp + lane, wd = pl >> 1;
+    float gb2_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long it = 0; it < my_slabs; ++it) {
+      const long long slab = blockIdx.x + it * gridDim.x;
+      const long long p = slab * kSlabPts + pl;
+      const bool valid = p < P.P;
+      // issue the first global loads before waiting for the tensor pipe to release the tiles
+      float gs[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid)
+        for (int c = 0; c < 4; ++c) if (c < P.sem_dim) gs[c] = __ldg(&P.g_raw[p * P.C + 4 + c]);
+      float v[8];
+      const float* hrow = P.h + p * 256 + q * 64;
+      load8(hrow, valid, v);
+      if (it > 0) { mbar_wait(smem_u32(sm.done), (uint32_t)((it - 1) & 1), 710); tc_fence_after(); }
+      // ---- B rows 0..255: h
+#pragma unroll 2
+      for (int g8 = 0; g8 < 8; ++g8) {
+        float nx[8];
+        if (g8 + 1 < 8) load8(hrow + 8 * (g8 + 1), valid, nx);
+        put8(sm.b[0], sm.b[1], q * 64 + 8 * g8, v, lane, wd);
+        if (g8 + 1 < 8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = nx[i];
+        }
+      }
+      // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0)
+#pragma unroll
+      for (int g8 = 0; g8 < 2; ++g8) {
+        const int e0 = q * 16 + 8 * g8;
+        load8(P.enc + p * P.enc_ld + e0, valid && P.sem_coord, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (e0 + i >= P.enc_dim) v[i] = 0.f;
+          if (e0 + i == 63) v[i] = valid ? 1.f : 0.f;
+        }
+        put8(sm.b[0], sm.b[1], 256 + e0, v, lane, wd);
+      }
+      // ---- A2 = s0^T and A = g_s0^T, units q*32..+31
+#pragma unroll 2
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const int u0 = q * 32 + 8 * g8;
+        load8(P.s0 + p * 128 + u0, valid, v);
+        put8(sm.a2[0], sm.a2[1], u0, v, lane, wd);
+        float g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float d = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) d = fmaf(gs[c], sm.w2[c * 128 + u0 + i], d);     // zero rows beyond sem_dim
+          g[i] = v[i] > 0.f ? d : 0.f;
+        }
+        put8(sm.a[0], sm.a[1], u0, g, lane, wd);
+      }
+      // ---- B2 = g_sem^T (rows 0..7; rows >= sem_dim are zero)
+      if (q == 0) {
+        float g[8] = {gs[0], gs[1], gs[2], gs[3], 0.f, 0.f, 0.f, 0.f};
+        put8(sm.b2[0], sm.b2[1], 0, g, lane, wd);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gb2_acc[c] += gs[c];
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(smem_u32(sm.ready));
+    }
+    // ---- epilogue: TMEM partial sums -> global gradients (atomics; every CTA contributes)
+    mbar_wait(smem_u32(sm.done), (uint32_t)((my_slabs - 1) & 1), 720);
+    tc_fence_after();
+    const int q4 = warp & 3, hf = warp >> 2;
+    const int u = q4 * 32 + lane;
+    const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
+    const int nfeat = P.sem_coord ? 256 + P.enc_dim : 256;
+    for (int c = hf * 10; c < hf * 10 + 10; ++c) {
+      uint32_t r[16];
+      tmem_ld16(tm_lane + kColD1 + c * 16, r);
+      tmem_wait_ld_fence16(r);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int f = c * 16 + j;
+        const float x = __uint_as_float(r[j]);
+        if (f < nfeat) atomicAdd(&P.gW0[(size_t)u * P.ld0 + f], x);
+        else if (f == 319) atomicAdd(&P.gb0[u], x);
+      }
+    }
+    if (hf == 1) {
+      uint32_t r[16];
+      tmem_ld16(tm_lane + kColD2, r);
+      tmem_wait_ld_fence16(r);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < P.sem_dim) atomicAdd(&P.gW2[c * 128 + u], __uint_as_float(r[c]));
+    }
+    if (q == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float s = gb2_acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && c < P.sem_dim) atomicAdd(&P.gb2[c], s);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWgMmaWarp) tmem_dealloc(tm, kWgTmemCols);
+}
+
+}  // namespace
+
+bool tc_sem_wgrad_supported(const NetGeom& g) {
+  return g.use_viewdirs && g.use_sem && g.W == 256 && g.enc <= 63 && g.sem_dim >= 1 && g.sem_dim <= 4;
+}
+
+// h [P,256], enc [P,enc_ld] (gamma(x), only read with sem_with_coord), s0 [P,128] (post-ReLU), g_raw [P,C] (sem gradients in
+// columns 4..).  Accumulates into the flat gradient buffer `grads` (layout of nsos_param_layout).
+int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, const float* s0,
+                 const float* g_raw, int64_t P, cudaStream_t st) {
+  NSOS_REQUIRE(tc_sem_wgrad_supported(g), NSOS_ERR_UNSUPPORTED, "semantic-head wgrad kernel needs W=256, sem_dim<=4");
+  if (P <= 0) return NSOS_OK;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.h = h; p.enc = enc; p.s0 = s0; p.g_raw = g_raw; p.w_s2 = prm + g.w_s2;
+  p.gW0 = grads + g.w_s0; p.gb0 = grads + g.b_s0; p.gW2 = grads + g.w_s2; p.gb2 = grads + g.b_s2;
+  p.P = P; p.C = g.C; p.enc_dim = g.enc; p.enc_ld = enc_ld; p.sem_dim = g.sem_dim; p.sem_coord = g.sem_coord; p.ld0 = g.sem_in;
+  int dev = 0, sms = 0;
+  NSOS_CHECK_CUDA(cudaGetDevice(&dev));
+  NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long nslabs = (P + kSlabPts - 1) / kSlabPts;
+  const int grid = (int)std::min<long long>(nslabs, sms);
+  const size_t need = wg_carve(nullptr, nullptr) + 1024;
+  NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_sem_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  k_sem_wgrad<<<grid, kWgThreads, need, st>>>(p);
+  NSOS_CHECK_CUDA(cudaGetLastError());
+  return NSOS_OK;
+}
+
+}  // namespace nsos

@@ -178,9 +178,10 @@ def test_flower_semantic_head_gradients(mode):
         assert err <= tol * scale, (n, err, scale)
 
 
-def test_semantic_head_backward_tensor_core_replay_matches_fp32_recompute(monkeypatch):
-    """--fix_backbone backward at a size that crosses the 4096-ray chunk with an odd tail: the tcgen05 replay
-    (trunk recomputed on tensor cores at the saved sample depths) against the all-fp32 CUDA-core recompute."""
+def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypatch):
+    """--fix_backbone backward at a size that crosses the 4096-ray chunk with an odd tail.  Three implementations of the
+    same gradients: (tc) trunk replay + weight gradients on tcgen05, (wsimt) trunk replay on tcgen05 + fp32 CUDA-core
+    GEMMs, (simt) everything recomputed in fp32 on CUDA cores."""
     g = load_golden("flower_eval_256")
     n = 4096 + 37
     rays = torch.from_numpy(g["rays"]).to(DEV)
@@ -190,21 +191,32 @@ def test_semantic_head_backward_tensor_core_replay_matches_fp32_recompute(monkey
     gsem = torch.randn(n, 2, device=DEV, generator=gen)
     gsem0 = torch.randn(n, 2, device=DEV, generator=gen)
     grads = {}
-    for which in ("tc", "simt"):
-        if which == "simt":
-            monkeypatch.setenv("NSOS_BWD_SIMT", "1")
+    for which, env in (("tc", None), ("wsimt", "NSOS_WGRAD_SIMT"), ("simt", "NSOS_BWD_SIMT")):
+        if env:
+            monkeypatch.setenv(env, "1")
         net = flower_net("exact", perturb=1.0, raw_noise_std=0.5).train()
         for nme, p in net.named_parameters():
             p.requires_grad_("semantic_linear" in nme)
-        torch.manual_seed(11)                       # same Philox seed for both runs
+        torch.manual_seed(11)                       # same Philox seed for all runs
         out = net(rays, (1.2, 12.0))
         ((out["semantics"] * gsem).sum() + (out["semantics0"] * gsem0).sum()).backward()
         grads[which] = {nme: p.grad.clone() for nme, p in net.named_parameters() if p.grad is not None}
-    assert set(grads["tc"]) == set(grads["simt"]) and len(grads["tc"]) == 8
-    for nme, ref in grads["simt"].items():
+        if env:
+            monkeypatch.delenv(env)
+    assert len(grads["tc"]) == 8 and set(grads["tc"]) == set(grads["simt"]) == set(grads["wsimt"])
+    for nme, ref in grads["wsimt"].items():
+        # identical inputs (same replay), bf16 hi+lo tensor-core contraction vs fp32 FMA: 2e-5 of max
+        scale = ref.abs().max().item()
         err = (grads["tc"][nme] - ref).abs().max().item()
-        # a ReLU of semantic_linear.0 that sits at 0 +- 1 ulp flips its mask between the two recomputes: <= 1e-3 of max observed
-        assert err <= 2e-3 * ref.abs().max().item() + 1e-6, (nme, err, ref.abs().max().item())
+        assert err <= 2e-5 * scale + 1e-6, (nme, err, scale)
+    for nme, ref in grads["simt"].items():
+        # different trunk arithmetic: a ReLU of semantic_linear.0 sitting at 0 +- 1 ulp flips its mask and moves one row of
+        # the weight gradient by one point's contribution -> robust criterion plus a loose bound on the outliers
+        scale = ref.abs().max().item()
+        d = (grads["tc"][nme] - ref).abs()
+        assert d.median().item() <= 2e-5 * scale + 1e-6, (nme, d.median().item(), scale)
+        assert (d > 1e-3 * scale).float().mean().item() <= 0.02, (nme, scale)
+        assert d.max().item() <= 2e-2 * scale, (nme, d.max().item(), scale)
 
 
 def test_cfg1_full_gradients():
