@@ -93,6 +93,12 @@ typedef struct NsosRenderOut {
   float* z_vals;     /* [N, Sc+K] sorted             */
   float* z_samples;  /* [N, K] (unsorted, as drawn)  */
   int64_t* inds;     /* [N, K] searchsorted indices  */
+  /* Optional activations saved for nsos_render_bwd (tcgen05 modes, W=256; ignored by NSOS_MODE_SIMT_FP32):
+   * last trunk activation relu(pts_linears[D-1]) and semantic hidden layer relu(semantic_linear.0), per point. */
+  float* h_last0;    /* [N, Sc, W]                   */
+  float* s_hid0;     /* [N, Sc, W/2]                 */
+  float* h_last;     /* [N, Sc+K, W]                 */
+  float* s_hid;      /* [N, Sc+K, W/2]               */
 } NsosRenderOut;
 
 /* ---- introspection ------------------------------------------------------------------------- */
@@ -135,14 +141,16 @@ int nsos_render_fwd(const NsosRenderCfg* cfg, const float* params_coarse, const 
  * nsos_param_layout); trunk_grads=0 computes only semantic_linear.{0,2} (--fix_backbone,
  * run_nerf.py:307-318).  With trunk_grads=0 and a tcgen05 cfg->mode the trunk is recomputed on the tensor
  * cores from packed_* (the images nsos_render_fwd used; may be NULL in NSOS_MODE_SIMT_FP32) and only the
- * semantic-head GEMMs run in fp32 on CUDA cores; otherwise everything runs in fp32 on CUDA cores. */
+ * semantic-head weight gradients run on the tensor cores too (bf16 hi/lo, fp32 accumulate); otherwise everything
+ * runs in fp32 on CUDA cores.  `saved` (may be NULL) points at the NsosRenderOut of the forward call: when it holds
+ * raw0/raw and the h_last / s_hid arrays the trunk is not recomputed at all. */
 size_t nsos_render_bwd_workspace_bytes(const NsosRenderCfg* cfg, int64_t n_rays, int trunk_grads);
 int nsos_render_bwd(const NsosRenderCfg* cfg, const float* params_coarse, const float* params_fine,
                     const void* packed_coarse, const void* packed_fine,
                     const float* rays_o, const float* rays_d, const float* z_vals0, const float* z_vals,
                     const NsosRandoms* rnd, uint64_t seed, const float* g_maps, float* grads_coarse,
-                    float* grads_fine, int trunk_grads, void* workspace, size_t workspace_bytes,
-                    int64_t n_rays, void* stream);
+                    float* grads_fine, int trunk_grads, const NsosRenderOut* saved, void* workspace,
+                    size_t workspace_bytes, int64_t n_rays, void* stream);
 
 /* Stage-wise entry for the 'exact sample indices' contract: ImportanceSampler.sample_pdf
  * (sampler.py:117-132) on caller-supplied cdf.  bins/cdf [N,M], u [N,K] -> samples [N,K], inds [N,K]. */

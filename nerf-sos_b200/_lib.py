@@ -34,7 +34,7 @@ class Randoms(C.Structure):
 
 class RenderOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
-                                          "z_samples", "inds")]
+                                          "z_samples", "inds", "h_last0", "s_hid0", "h_last", "s_hid")]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -83,7 +83,7 @@ def lib() -> C.CDLL:
         "nsos_render_workspace_bytes": (sz, [P(RenderCfg), i64]),
         "nsos_render_fwd": (C.c_int, [P(RenderCfg), vp, vp, vp, vp, vp, vp, vp, vp, P(Randoms), u64, P(RenderOut), vp, sz, i64, vp]),
         "nsos_render_bwd_workspace_bytes": (sz, [P(RenderCfg), i64, C.c_int]),
-        "nsos_render_bwd": (C.c_int, [P(RenderCfg), vp, vp, vp, vp, vp, vp, vp, vp, P(Randoms), u64, vp, vp, vp, C.c_int, vp, sz, i64, vp]),
+        "nsos_render_bwd": (C.c_int, [P(RenderCfg), vp, vp, vp, vp, vp, vp, vp, vp, P(Randoms), u64, vp, vp, vp, C.c_int, P(RenderOut), vp, sz, i64, vp]),
         "nsos_invert_cdf": (C.c_int, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
         "nsos_mlp_workspace_bytes": (sz, [P(NetDesc), i64]),
         "nsos_mlp_query": (C.c_int, [P(NetDesc), vp, vp, vp, vp, vp, sz, i64, vp]),

@@ -97,15 +97,15 @@ size_t nsos_render_bwd_workspace_bytes(const NsosRenderCfg* cfg, int64_t n_rays,
 int nsos_render_bwd(const NsosRenderCfg* cfg, const float* params_coarse, const float* params_fine, const void* packed_coarse,
                     const void* packed_fine, const float* rays_o,
                     const float* rays_d, const float* z_vals0, const float* z_vals, const NsosRandoms* rnd, uint64_t seed,
-                    const float* g_maps, float* grads_coarse, float* grads_fine, int trunk_grads, void* workspace,
-                    size_t workspace_bytes, int64_t n_rays, void* stream) {
+                    const float* g_maps, float* grads_coarse, float* grads_fine, int trunk_grads, const NsosRenderOut* saved,
+                    void* workspace, size_t workspace_bytes, int64_t n_rays, void* stream) {
   NSOS_REQUIRE(cfg && params_coarse && rays_o && rays_d && z_vals && g_maps && grads_coarse, NSOS_ERR_BAD_ARG,
                "nsos_render_bwd: null argument");
   if (n_rays <= 0) return NSOS_OK;
   if (cfg->n_importance > 0) NSOS_REQUIRE(params_fine && grads_fine && z_vals0, NSOS_ERR_BAD_ARG, "nsos_render_bwd: fine-pass argument missing");
   else { params_fine = params_coarse; grads_fine = grads_coarse; }
   return simt_render_bwd(*cfg, params_coarse, params_fine, rays_o, rays_d, z_vals0, z_vals, rnd, seed, g_maps, grads_coarse,
-                         grads_fine, trunk_grads, packed_coarse, packed_fine, workspace, workspace_bytes, n_rays,
+                         grads_fine, trunk_grads, packed_coarse, packed_fine, saved, workspace, workspace_bytes, n_rays,
                          (cudaStream_t)stream);
 }
 

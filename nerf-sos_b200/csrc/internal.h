@@ -12,8 +12,8 @@ int simt_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
 size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays, int trunk);
 int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, const float* rays_o, const float* rays_d,
                     const float* z_vals0, const float* z_vals, const NsosRandoms* rnd, uint64_t seed, const float* g_maps,
-                    float* grads_c, float* grads_f, int trunk, const void* packed_c, const void* packed_f, void* workspace,
-                    size_t workspace_bytes, int64_t n_rays, cudaStream_t st);
+                    float* grads_c, float* grads_f, int trunk, const void* packed_c, const void* packed_f,
+                    const NsosRenderOut* saved, void* workspace, size_t workspace_bytes, int64_t n_rays, cudaStream_t st);
 int simt_invert_cdf(const float* bins, const float* cdf, const float* u, float* samples, int64_t* inds, int64_t n_rays, int M, int K,
                     cudaStream_t st);
 size_t simt_mlp_workspace_bytes(const NetGeom& g, int64_t P);

@@ -474,8 +474,8 @@ size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays,
 
 int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, const float* rays_o, const float* rays_d,
                     const float* z_vals0, const float* z_vals, const NsosRandoms* rnd, uint64_t seed, const float* g_maps,
-                    float* grads_c, float* grads_f, int trunk, const void* packed_c, const void* packed_f, void* workspace,
-                    size_t workspace_bytes, int64_t n_rays, cudaStream_t st) {
+                    float* grads_c, float* grads_f, int trunk, const void* packed_c, const void* packed_f,
+                    const NsosRenderOut* saved, void* workspace, size_t workspace_bytes, int64_t n_rays, cudaStream_t st) {
   NetGeom gc, gf;
   NSOS_REQUIRE(make_geom(cfg.coarse, gc), NSOS_ERR_UNSUPPORTED, "invalid coarse net descriptor");
   const bool fine = cfg.n_importance > 0;
@@ -484,7 +484,16 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
   NSOS_REQUIRE(Sc >= 2 && Sf <= kMaxS, NSOS_ERR_UNSUPPORTED, "n_samples/n_importance out of range");
   if (!trunk && !gc.use_sem && !gf.use_sem) return NSOS_OK;   // nothing trainable outside the trunk
   if (bwd_uses_tc(cfg, trunk, gc, gf)) {
-    NSOS_REQUIRE(packed_c && (!fine || packed_f), NSOS_ERR_BAD_ARG, "nsos_render_bwd: tcgen05 modes need the packed weights");
+    // activations saved by the forward call make the trunk replay unnecessary
+    const float* sv_raw[2] = {nullptr, nullptr}; const float* sv_h[2] = {nullptr, nullptr}; const float* sv_s[2] = {nullptr, nullptr};
+    if (saved) {
+      if (fine) { sv_raw[0] = saved->raw0; sv_h[0] = saved->h_last0; sv_s[0] = saved->s_hid0;
+                  sv_raw[1] = saved->raw; sv_h[1] = saved->h_last; sv_s[1] = saved->s_hid; }
+      else { sv_raw[0] = saved->raw; sv_h[0] = saved->h_last; sv_s[0] = saved->s_hid; }
+    }
+    const bool have_saved = sv_raw[0] && sv_h[0] && sv_s[0] && (!fine || (sv_raw[1] && sv_h[1] && sv_s[1]));
+    if (!have_saved)
+      NSOS_REQUIRE(packed_c && (!fine || packed_f), NSOS_ERR_BAD_ARG, "nsos_render_bwd: tcgen05 modes need the packed weights");
     const int64_t R = bwd_tc_chunk_rays(n_rays);
     BwdTcWs w;
     size_t need = carve_bwd_tc(cfg, gc, gf, R, (char*)workspace, &w);
@@ -497,8 +506,15 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
       const float* ro = rays_o + r0 * 3; const float* rd = rays_d + r0 * 3;
       const float* zc = (fine ? z_vals0 : z_vals) + r0 * Sc;
       const float* zf = fine ? z_vals + r0 * Sf : nullptr;
-      int rc = tc_render_replay(cfg, packed_c, fine ? packed_f : packed_c, ro, rd, zc, zf, w.raw[0], w.raw[1], w.h[0], w.s0[0], w.h[1],
-                                w.s0[1], n, st);
+      int rc = NSOS_OK;
+      const float* raw_p[2] = {w.raw[0], w.raw[1]}; const float* h_p[2] = {w.h[0], w.h[1]}; const float* s_p[2] = {w.s0[0], w.s0[1]};
+      if (have_saved) {
+        raw_p[0] = sv_raw[0] + r0 * Sc * gc.C; h_p[0] = sv_h[0] + r0 * Sc * gc.W; s_p[0] = sv_s[0] + r0 * Sc * (gc.W / 2);
+        if (fine) { raw_p[1] = sv_raw[1] + r0 * Sf * gf.C; h_p[1] = sv_h[1] + r0 * Sf * gf.W; s_p[1] = sv_s[1] + r0 * Sf * (gf.W / 2); }
+      } else {
+        rc = tc_render_replay(cfg, packed_c, fine ? packed_f : packed_c, ro, rd, zc, zf, w.raw[0], w.raw[1], w.h[0], w.s0[0], w.h[1],
+                              w.s0[1], n, st);
+      }
       if (rc) return rc;
       k_encode_dirs<<<grid1(n), 256, 0, st>>>(rd, w.encv, w.dnorm, n, gc.Lv);
       for (int pass = 0; pass < (fine ? 2 : 1); ++pass) {
@@ -510,15 +526,15 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
         const int moff = (fine && !is_fine) ? C6 : 0;
         const int64_t P = n * S;
         k_encode_pts<<<grid1(P), 256, 0, st>>>(ro, rd, z, w.enc, P, S, g.Lp);
-        k_composite_bwd<<<grid1(n * 32, 128), 128, 0, st>>>(w.raw[pass], z, w.dnorm, noise ? noise + r0 * S : nullptr, cfg.raw_noise_std,
+        k_composite_bwd<<<grid1(n * 32, 128), 128, 0, st>>>(raw_p[pass], z, w.dnorm, noise ? noise + r0 * S : nullptr, cfg.raw_noise_std,
                                                              seed, r0, is_fine ? RNG_NOISE1 : RNG_NOISE0, S, g.C, g.sem_dim,
                                                              cfg.white_bkgd, g_maps + r0 * ML, ML, moff, w.g_raw, n);
         NSOS_CHECK_CUDA(cudaGetLastError());
         if (tc_sem_wgrad_supported(g) && !getenv("NSOS_WGRAD_SIMT")) {
-          rc = tc_sem_wgrad(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, w.h[pass], w.enc, kEncLd, w.s0[pass], w.g_raw, P, st);
+          rc = tc_sem_wgrad(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, h_p[pass], w.enc, kEncLd, s_p[pass], w.g_raw, P, st);
         } else {
           MlpBufs b{};
-          b.h[g.D - 1] = w.h[pass]; b.s0 = w.s0[pass];
+          b.h[g.D - 1] = const_cast<float*>(h_p[pass]); b.s0 = const_cast<float*>(s_p[pass]);
           BwdBufs bw{w.g_raw, {nullptr, nullptr}, w.g_half, nullptr};
           rc = mlp_backward(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, w.enc, w.encv, S, P, b, bw, 0, st);
         }

@@ -519,8 +519,11 @@ __device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int wa
   tc_fence_after();
 }
 
-template <bool EXACT, bool REPLAY>
+// MODE 0: forward.  MODE 1: forward that also saves h_last / s_hid per point (training).  MODE 2: replay at given sample
+// depths (backward recompute: no sampling, no compositing) with the same saves.
+template <bool EXACT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant__ TcParams P) {
+  constexpr bool REPLAY = (MODE == 2), DUMP = (MODE >= 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   Smem sm;
@@ -669,12 +672,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             if (tr) tr[st * kTraceStamps + 1] = clock64();                 // accumulator ready
             float* ha = (Sg.epi == EPI_HIDDEN_SIGMA) ? &hacc[0] : (Sg.epi == EPI_SEM) ? &hacc[4] : &hacc[1];
             float* gout = nullptr;
-            if (REPLAY && rowvalid && rp[9] > 0.f) {
+            if (DUMP && rowvalid && rp[9] > 0.f) {
               const size_t pt = (size_t)ray * S + i;
               if (Sg.epi == EPI_HIDDEN_SIGMA && P.dump_h[pass]) gout = P.dump_h[pass] + pt * pg.W;
               if (Sg.epi == EPI_SEM && P.dump_s0[pass]) gout = P.dump_s0[pass] + pt * pg.H2;
             }
-            epilogue<EXACT, REPLAY>(Sg.epi, cb, ce, tm_lane, inv16, bias, hw, P.sem_dim, ha, gout);
+            epilogue<EXACT, DUMP>(Sg.epi, cb, ce, tm_lane, inv16, bias, hw, P.sem_dim, ha, gout);
             if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
             if (st + 1 < pg.nst) {
               if (Sg.epi != EPI_SEM) tmem_wait_st();
@@ -904,8 +907,14 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
   P.seed = seed; P.out = out; P.n_rays = n_rays; P.Sc = Sc; P.K = K; P.Sf = fine ? Sf : Sc;
   P.perturb = cfg.perturb; P.noise_std = cfg.raw_noise_std; P.white_bkgd = cfg.white_bkgd; P.exact = exact; P.fine = fine;
   P.C = gc.C; P.sem_dim = gc.sem_dim; P.C6 = 6 + gc.sem_dim; P.ML = 2 * P.C6 + 1;
-  if (replay)
+  if (replay) {
     for (int i = 0; i < 2; ++i) { P.z_in[i] = replay->z_in[i]; P.dump_h[i] = replay->dump_h[i]; P.dump_s0[i] = replay->dump_s0[i]; }
+  } else if (fine) {
+    P.dump_h[0] = out.h_last0; P.dump_s0[0] = out.s_hid0; P.dump_h[1] = out.h_last; P.dump_s0[1] = out.s_hid;
+  } else {
+    P.dump_h[0] = out.h_last; P.dump_s0[0] = out.s_hid;
+  }
+  const bool dump = !replay && (P.dump_h[0] || P.dump_h[1] || P.dump_s0[0] || P.dump_s0[1]);
   if (!replay && getenv("NSOS_TRACE") && workspace && workspace_bytes >= tc_render_workspace_bytes(cfg, n_rays)) {
     P.trace = reinterpret_cast<long long*>(workspace);
     NSOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(long long) * kTraceTiles * 16 * kTraceStamps, st));
@@ -945,8 +954,9 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
     if (e != cudaSuccess) return e;
     return cudaLaunchKernelEx(&lc, kern, P);
   };
-  if (replay) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, true>) : launch(k_render_tc<false, true>));
-  else NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, false>) : launch(k_render_tc<false, false>));
+  if (replay) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 2>) : launch(k_render_tc<false, 2>));
+  else if (dump) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 1>) : launch(k_render_tc<false, 1>));
+  else NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 0>) : launch(k_render_tc<false, 0>));
   NSOS_CHECK_CUDA(cudaGetLastError());
   return NSOS_OK;
 }

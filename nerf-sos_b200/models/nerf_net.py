@@ -26,6 +26,22 @@ from .nerf_mlp import NeRFMLP
 _MAP_KEYS = ("rgb", "disp", "acc", "depth")
 
 
+def _save_acts(net, params, cfg, n_points, grad_mode) -> bool:
+    """Save h_last / s_hid in the forward pass?  Only when exactly the semantic heads train (run_nerf.py:307-318), on a
+    tcgen05 mode, for the W=256 geometry the weight-gradient kernel covers, and within NSOS_SAVE_ACT_GB (default 24)."""
+    if cfg.mode == _lib.MODE_SIMT or not grad_mode or os.environ.get("NSOS_BWD_SIMT") or os.environ.get("NSOS_WGRAD_SIMT"):
+        return False
+    m = net.nerf.mlp
+    if not (m.use_semantics and m.W == 256 and m.sem_dim <= 4 and net.nerf_fine.mlp.W == 256):
+        return False
+    sem_ids = {id(p) for mm in (net.nerf.mlp, net.nerf_fine.mlp) if mm.use_semantics for p in mm.semantic_linear.parameters()}
+    req = [p for p in params if p.requires_grad]
+    if not req or any(id(p) not in sem_ids for p in req):
+        return False
+    cap = float(os.environ.get("NSOS_SAVE_ACT_GB", "24")) * 2 ** 30
+    return n_points * (m.W + m.W // 2) * 4 <= cap
+
+
 def _cfg(net: "NeRFNet", n_samples, n_importance, perturb, raw_noise_std, mode) -> _lib.RenderCfg:
     return _lib.RenderCfg(net.nerf.desc(), net.nerf_fine.desc(), int(n_samples), int(n_importance), float(perturb),
                           float(raw_noise_std), int(bool(net.white_bkgd)), int(mode))
@@ -51,7 +67,17 @@ class _RenderFn(torch.autograd.Function):
         out = dict(maps=maps, weights=torch.empty(N, S_last, **f32))
         if fine:
             out["weights0"] = torch.empty(N, Sc, **f32)
-        if want["raw"]:
+        # --fix_backbone training on the tcgen05 path: keep the two activations the semantic-head gradients need, so that
+        # the backward pass does not recompute the trunk (393 kB per ray at 64+192 samples; beyond the cap it replays)
+        acts = {}
+        if _save_acts(net, params, cfg, N * (Sc + (Sf if fine else 0)), want.get("grad", False)):
+            Wd = net.nerf.mlp.W
+            acts["h_last"] = torch.empty(N, S_last, Wd, **f32)
+            acts["s_hid"] = torch.empty(N, S_last, Wd // 2, **f32)
+            if fine:
+                acts["h_last0"] = torch.empty(N, Sc, Wd, **f32)
+                acts["s_hid0"] = torch.empty(N, Sc, Wd // 2, **f32)
+        if want["raw"] or acts:
             out["raw"] = torch.empty(N, S_last, Cr, **f32)
             if fine:
                 out["raw0"] = torch.empty(N, Sc, Cr, **f32)
@@ -64,7 +90,9 @@ class _RenderFn(torch.autograd.Function):
             out["z_samples"] = torch.empty(N, K, **f32)
             out["inds"] = torch.empty(N, K, dtype=torch.int64, device=dev)
         ro = _lib.RenderOut(*[_lib.ptr(out.get(k)) for k in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
-                                                             "z_samples", "inds")])
+                                                             "z_samples", "inds")],
+                            *[_lib.ptr(acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")])
+        ctx.acts = dict(acts, raw=out.get("raw"), raw0=out.get("raw0")) if acts else None
         rs = _lib.Randoms(*[_lib.ptr(rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
         flat_c, flat_f = net.nerf.flat_params(), net.nerf_fine.flat_params()
         pk_c = net.nerf.packed(cfg.mode, force=net.training)
@@ -114,10 +142,15 @@ class _RenderFn(torch.autograd.Function):
         # the packed images of the forward call (parameters are unchanged between forward and backward)
         pk_c = net.nerf.packed(cfg.mode)
         pk_f = net.nerf_fine.packed(cfg.mode) if fine else pk_c
+        saved = None
+        if ctx.acts and not trunk:
+            saved = C.byref(_lib.RenderOut(None, None, None, _lib.ptr(ctx.acts.get("raw0")), _lib.ptr(ctx.acts.get("raw")), None, None,
+                                           None, None, *[_lib.ptr(ctx.acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")]))
         _lib.check(L.nsos_render_bwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
                                      _lib.ptr(rays_d), _lib.ptr(z0),
                                      _lib.ptr(z1), C.byref(rs), ctx.seed, _lib.ptr(g_maps.contiguous()), _lib.ptr(g_c), _lib.ptr(g_f),
-                                     trunk, _lib.ptr(ws), ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_bwd")
+                                     trunk, saved, _lib.ptr(ws), ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_bwd")
+        ctx.acts = None
         grads = []
         offs = list(net.nerf._flat.offsets) + (list(net.nerf_fine._flat.offsets) if fine else [])
         for i, (shape, req) in enumerate(zip(ctx.shapes, ctx.req)):
@@ -198,7 +231,7 @@ class NeRFNet(nn.Module):
         near, far = f(near).reshape(N), f(far).reshape(N)
         rnd = {k: v.to(dev, torch.float32).contiguous() for k, v in (kwargs.get('randoms') or {}).items()}
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (perturb > 0 or raw_noise_std > 0) else 0
-        want = dict(raw=bool(retraw), z=bool(kwargs.get('retz', False)))
+        want = dict(raw=bool(retraw), z=bool(kwargs.get('retz', False)), grad=torch.is_grad_enabled())
         fine = n_importance > 0
         pc = list(self.nerf._flat.params)
         pf = list(self.nerf_fine._flat.params) if fine else []

@@ -180,8 +180,9 @@ def test_flower_semantic_head_gradients(mode):
 
 def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypatch):
     """--fix_backbone backward at a size that crosses the 4096-ray chunk with an odd tail.  Three implementations of the
-    same gradients: (tc) trunk replay + weight gradients on tcgen05, (wsimt) trunk replay on tcgen05 + fp32 CUDA-core
-    GEMMs, (simt) everything recomputed in fp32 on CUDA cores."""
+    same gradients: (tc) activations saved by the forward kernel + weight gradients on tcgen05, (replay) trunk replayed on
+    tcgen05 in backward + the same weight-gradient kernel, (wsimt) trunk replay on tcgen05 + fp32 CUDA-core GEMMs, (simt)
+    everything recomputed in fp32 on CUDA cores."""
     g = load_golden("flower_eval_256")
     n = 4096 + 37
     rays = torch.from_numpy(g["rays"]).to(DEV)
@@ -191,9 +192,10 @@ def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypat
     gsem = torch.randn(n, 2, device=DEV, generator=gen)
     gsem0 = torch.randn(n, 2, device=DEV, generator=gen)
     grads = {}
-    for which, env in (("tc", None), ("wsimt", "NSOS_WGRAD_SIMT"), ("simt", "NSOS_BWD_SIMT")):
+    for which, env, val in (("tc", None, ""), ("replay", "NSOS_SAVE_ACT_GB", "0"), ("wsimt", "NSOS_WGRAD_SIMT", "1"),
+                            ("simt", "NSOS_BWD_SIMT", "1")):
         if env:
-            monkeypatch.setenv(env, "1")
+            monkeypatch.setenv(env, val)
         net = flower_net("exact", perturb=1.0, raw_noise_std=0.5).train()
         for nme, p in net.named_parameters():
             p.requires_grad_("semantic_linear" in nme)
@@ -203,12 +205,13 @@ def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypat
         grads[which] = {nme: p.grad.clone() for nme, p in net.named_parameters() if p.grad is not None}
         if env:
             monkeypatch.delenv(env)
-    assert len(grads["tc"]) == 8 and set(grads["tc"]) == set(grads["simt"]) == set(grads["wsimt"])
+    assert len(grads["tc"]) == 8 and set(grads["tc"]) == set(grads["simt"]) == set(grads["wsimt"]) == set(grads["replay"])
     for nme, ref in grads["wsimt"].items():
-        # identical inputs (same replay), bf16 hi+lo tensor-core contraction vs fp32 FMA: 2e-5 of max
+        # identical inputs (same trunk activations), bf16 hi+lo tensor-core contraction vs fp32 FMA: 2e-5 of max
         scale = ref.abs().max().item()
-        err = (grads["tc"][nme] - ref).abs().max().item()
-        assert err <= 2e-5 * scale + 1e-6, (nme, err, scale)
+        for which in ("tc", "replay"):
+            err = (grads[which][nme] - ref).abs().max().item()
+            assert err <= 2e-5 * scale + 1e-6, (which, nme, err, scale)
     for nme, ref in grads["simt"].items():
         # different trunk arithmetic: a ReLU of semantic_linear.0 sitting at 0 +- 1 ulp flips its mask and moves one row of
         # the weight gradient by one point's contribution -> robust criterion plus a loose bound on the outliers
