@@ -172,3 +172,38 @@ def _():
             tb = ev[0].elapsed_time(ev[1])
         print(f"  backward={variant}: render fwd {tf:.1f} ms, render bwd {tb:.1f} ms", flush=True)
     os.environ.pop("NSOS_BWD_SIMT", None)
+
+
+@step("corrloss timing (kernel B: geometry + appearance correlation losses, B=8 patches 64x64)")
+def _():
+    """ms per forward+backward of the two loss modules at the shipped batch; pairs/s for the all-pairs geometry loss."""
+    from nerfsos_b200.utils import image as I
+
+    class A:
+        rand_neg = False; self_corr_w = 1; use_sim_matrix = True; patch_stride = 6
+        app_corr_params = [0.18, 1, 0.46, 1]; geo_corr_params = [0.5, 1, 3, 1]
+    g = torch.Generator().manual_seed(0)
+    B, Pp = 8, 64
+    code = torch.randn(B, 2, Pp, Pp, generator=g).to(dev).requires_grad_(True)
+    ray_o = (torch.rand(B, 3, 1, 1, generator=g) * 0.6 - 0.3).expand(B, 3, Pp, Pp).contiguous().to(dev)
+    ray_d = torch.randn(B, 3, Pp, Pp, generator=g).to(dev)
+    depth = (torch.rand(B, 1, Pp, Pp, generator=g) * 10 + 1.2).to(dev)
+    sim = I.get_similarity_matrix(torch.randn(B, 384, generator=g).to(dev))
+    feat = torch.randn(B, 384, 14, 14, generator=g).to(dev)
+    geo, app = I.GeoCorrelationLoss(A()), I.CorrelationLoss(A())
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for name, fn in (("geometry", lambda: geo(depth.clone(), code, [ray_o, ray_d, None], sim)),
+                     ("appearance", lambda: app(feat.permute(0, 2, 3, 1).reshape(B, 196, 384) if False else feat, code, sim))):
+        ts = []
+        for it in range(5):
+            code.grad = None
+            torch.cuda.synchronize(); ev[0].record()
+            l = fn()
+            l.backward()
+            ev[1].record(); torch.cuda.synchronize()
+            ts.append(ev[0].elapsed_time(ev[1]))
+        extra = ""
+        if name == "geometry":
+            pairs = 2 * B * (Pp * Pp) ** 2          # negative + self term, all pixel pairs
+            extra = f"  {pairs / (min(ts) * 1e-3) / 1e9:.1f} G pairs/s (fwd+bwd)"
+        print(f"  {name}: fwd+bwd ms = {[round(t, 3) for t in ts]}{extra}", flush=True)
