@@ -46,14 +46,14 @@ constexpr int kHalfMax = 128;          // W/2 max
 constexpr int kSemMax = 4;
 constexpr int kHeadFloats = 256 + 4 + kSemMax * kHalfMax + 4 + 3 * kHalfMax + 4;
 
-enum EpiKind { EPI_HIDDEN = 0, EPI_HIDDEN_SIGMA = 1, EPI_SEM = 2, EPI_FEAT = 3, EPI_RGB = 4, EPI_RAW = 5 };
+enum EpiKind { EPI_HIDDEN = 0, EPI_HIDDEN_SIGMA = 1, EPI_SEM = 2, EPI_RGB = 4, EPI_RAW = 5, EPI_SEM_RGB = 6 };
 constexpr int A_GAMMA = -1;
 
 // fp32 side data at the head of the packed image
 struct TcAux {
-  float inv_scale[16];          // per stage: 1 / (weight scale * kActScale)
-  uint32_t absmax_bits[16];     // per stage max |w| (float bits), scratch of the pack pass
-  float bias[16][256];          // per stage bias (zero padded)
+  float inv_scale[16][2];       // per stage and row group: 1 / (weight scale * kActScale)
+  uint32_t absmax_bits[16][2];  // per stage and row group max |w| (float bits), scratch of the pack pass
+  float bias[16][256];          // per stage bias, by accumulator column (zero padded)
   float heads[kHeadFloats];     // w_alpha[256] b_alpha[4] w_s2[4][128] b_s2[4] w_rgb[3][128] b_rgb[4]
   float w_vdir[kHalfMax][28];   // views_linears.0.weight[:, W:W+encv]
 };
@@ -62,23 +62,28 @@ constexpr int kHeadWAlpha = 0, kHeadBAlpha = 256, kHeadWS2 = 260, kHeadBS2 = 260
               kHeadWRgb = kHeadBS2 + 4, kHeadBRgb = kHeadWRgb + 3 * kHalfMax;
 
 struct TcStage {
-  int n;                 // MMA N (multiple of 16)
+  int n;                 // accumulator columns of the stage (multiple of 16)
   int nslab;             // K slabs of 64
   int epi;               // EpiKind
   int asrc[kMaxSlabs];   // A_GAMMA or TMEM K-slab index
+  int sn[kMaxSlabs];     // MMA N of the slab (<= n; the gamma slab of the merged head stage only feeds the semantic half)
 };
 struct TcProg {
   int nst, W, Lp, Lv, enc, encv, sem_dim, H2;
+  int ub_off;            // column of the last stage's bias row where the (fused) views bias starts
   TcStage st[kMaxStages];
 };
 
-// host-side plan used by the pack kernels
-struct PackSlab { int64_t w_off; int ld, col0, kvalid, nvalid, n, stage; int64_t dst_hi, dst_lo; };
+// host-side plan used by the pack kernels.  A stage's accumulator columns come from up to two ROW GROUPS (weight
+// matrices stacked along N): group 0 = columns [0, rows[0]), group 1 = the next rows[1].  src 0 = the flat parameter
+// buffer, src 1 = the fused views matrix W_v[:, :W] . W_feat computed into the image by k_fuse_views.
+struct PackGroup { int src; int64_t w_off; int ld, rows; int bsrc; int64_t b_off; };
+struct PackSlab { int stage, n; int col0[2], kvalid[2]; int64_t dst_hi, dst_lo; };
 struct PackPlan {
   int nslab, nst;
   PackSlab s[kMaxStages * kMaxSlabs];
-  int64_t st_w_off[kMaxStages]; int st_rows[kMaxStages], st_ld[kMaxStages];  // tensor extents for absmax
-  int64_t st_b_off[kMaxStages]; int st_nb[kMaxStages];                       // bias source
+  PackGroup grp[kMaxStages][2];
+  int64_t fused_off;     // byte offset of the fused fp32 block in the image: W_uf[H2][W], then b_uf[H2]
   int64_t total_bytes;
 };
 
@@ -93,71 +98,126 @@ bool tc_supported(const NetGeom& g, const char** why) {
   return true;
 }
 
+// Stage program.  Two algebraic fusions keep work off the tensor pipe (both exact up to fp32 rounding order):
+//  * feature_linear has no non-linearity (nerf_mlp.py:86-89), so views_linears.0([feature_linear(h), enc_dirs]) =
+//    (W_v[:, :W] W_f) h + (W_v[:, :W] b_f + b_v) + W_v[:, W:] enc_dirs: the W x W feature stage disappears, the product
+//    matrix is formed once at pack time (k_fuse_views, fp64 accumulation);
+//  * semantic_linear.0 and the fused views layer both read h_last, so they share ONE stage: accumulator columns
+//    [0, W/2) = semantic hidden layer, [W/2, W) = views hidden layer; the gamma slab (sem_with_coord) is issued with
+//    N = W/2 so that it only feeds the semantic half.
 void build_prog(const NetGeom& g, bool exact, TcProg& p, PackPlan& plan) {
   memset(&p, 0, sizeof(p)); memset(&plan, 0, sizeof(plan));
   p.W = g.W; p.Lp = g.Lp; p.Lv = g.Lv; p.enc = g.enc; p.encv = g.encv; p.sem_dim = g.sem_dim; p.H2 = g.W / 2;
-  const int ks = g.W / 64;
+  const int ks = g.W / 64, H2 = g.W / 2;
   int64_t off = (int64_t)kAuxBytes;
-  auto add_stage = [&](int n, int nvalid, int epi, int64_t w_off, int ld, int64_t b_off, int nb, int col_gamma_first,
-                       int col_h0, bool has_h, bool gamma_first, bool gamma_last, int col_gamma_last) {
+  auto add_slab = [&](int asrc, int n, int col0_0, int kv0, int col0_1, int kv1) {
     TcStage& s = p.st[p.nst];
-    s.n = n; s.epi = epi; s.nslab = 0;
-    auto add_slab = [&](int asrc, int col0, int kvalid) {
-      s.asrc[s.nslab++] = asrc;
-      PackSlab& ps = plan.s[plan.nslab++];
-      ps.w_off = w_off; ps.ld = ld; ps.col0 = col0; ps.kvalid = kvalid; ps.nvalid = nvalid; ps.n = n; ps.stage = p.nst;
-      ps.dst_hi = off; off += (int64_t)n * 128;
-      ps.dst_lo = -1;
-      if (exact) { ps.dst_lo = off; off += (int64_t)n * 128; }
-    };
-    if (gamma_first) add_slab(A_GAMMA, col_gamma_first, g.enc);
-    if (has_h) for (int j = 0; j < ks; ++j) add_slab(j, col_h0 + 64 * j, 64);
-    if (gamma_last) add_slab(A_GAMMA, col_gamma_last, g.enc);
-    plan.st_w_off[p.nst] = w_off; plan.st_rows[p.nst] = nvalid; plan.st_ld[p.nst] = ld;
-    plan.st_b_off[p.nst] = b_off; plan.st_nb[p.nst] = nb;
-    ++p.nst;
+    s.sn[s.nslab] = n;
+    s.asrc[s.nslab++] = asrc;
+    PackSlab& ps = plan.s[plan.nslab++];
+    ps.stage = p.nst; ps.n = n; ps.col0[0] = col0_0; ps.kvalid[0] = kv0; ps.col0[1] = col0_1; ps.kvalid[1] = kv1;
+    ps.dst_hi = off; off += (int64_t)n * 128;
+    ps.dst_lo = -1;
+    if (exact) { ps.dst_lo = off; off += (int64_t)n * 128; }
+  };
+  auto group = [&](int gi, int src, int64_t w_off, int ld, int rows, int bsrc, int64_t b_off) {
+    PackGroup& pgp = plan.grp[p.nst][gi];
+    pgp.src = src; pgp.w_off = w_off; pgp.ld = ld; pgp.rows = rows; pgp.bsrc = bsrc; pgp.b_off = b_off;
   };
   for (int i = 0; i < g.D; ++i) {
-    int epi = (i == g.D - 1) ? EPI_HIDDEN_SIGMA : EPI_HIDDEN;
-    if (i == 0) add_stage(g.W, g.W, epi, g.w_pts[i], g.enc, g.b_pts[i], g.W, 0, 0, false, true, false, 0);
-    else if (g.in_pts[i] == g.W) add_stage(g.W, g.W, epi, g.w_pts[i], g.W, g.b_pts[i], g.W, 0, 0, true, false, false, 0);
-    else add_stage(g.W, g.W, epi, g.w_pts[i], g.W + g.enc, g.b_pts[i], g.W, 0, g.enc, true, true, false, 0);  // [enc, h]
+    TcStage& s = p.st[p.nst];
+    s.n = g.W; s.epi = (i == g.D - 1) ? EPI_HIDDEN_SIGMA : EPI_HIDDEN;
+    group(0, 0, g.w_pts[i], g.in_pts[i], g.W, 0, g.b_pts[i]);
+    if (i == 0) add_slab(A_GAMMA, g.W, 0, g.enc, 0, 0);
+    else if (g.in_pts[i] == g.W) for (int j = 0; j < ks; ++j) add_slab(j, g.W, 64 * j, 64, 0, 0);
+    else {                                                           // [enc, h] (nerf_mlp.py:73-74)
+      add_slab(A_GAMMA, g.W, 0, g.enc, 0, 0);
+      for (int j = 0; j < ks; ++j) add_slab(j, g.W, g.enc + 64 * j, 64, 0, 0);
+    }
+    ++p.nst;
   }
-  if (g.use_sem)  // semantic_linear.0 on [h, enc]
-    add_stage(g.W / 2, g.W / 2, EPI_SEM, g.w_s0, g.sem_in, g.b_s0, g.W / 2, 0, 0, true, false, g.sem_coord != 0, g.W);
-  add_stage(g.W, g.W, EPI_FEAT, g.w_feat, g.W, g.b_feat, g.W, 0, 0, true, false, false, 0);
-  add_stage(g.W / 2, g.W / 2, EPI_RGB, g.w_views, g.W + g.encv, g.b_views, g.W / 2, 0, 0, true, false, false, 0);
+  {
+    TcStage& s = p.st[p.nst];
+    if (g.use_sem) {                                                 // semantic_linear.0 on [h, enc] | fused views on h
+      s.n = 2 * H2; s.epi = EPI_SEM_RGB; p.ub_off = H2;
+      group(0, 0, g.w_s0, g.sem_in, H2, 0, g.b_s0);
+      group(1, 1, 0, g.W, H2, 1, 0);
+      for (int j = 0; j < ks; ++j) add_slab(j, 2 * H2, 64 * j, 64, 64 * j, 64);
+      if (g.sem_coord) add_slab(A_GAMMA, H2, g.W, g.enc, 0, 0);
+    } else {
+      s.n = H2; s.epi = EPI_RGB; p.ub_off = 0;
+      group(0, 1, 0, g.W, H2, 1, 0);
+      for (int j = 0; j < ks; ++j) add_slab(j, H2, 64 * j, 64, 0, 0);
+    }
+    ++p.nst;
+  }
   plan.nst = p.nst;
-  plan.total_bytes = off;
+  plan.fused_off = off;
+  off += (int64_t)sizeof(float) * ((int64_t)H2 * g.W + H2);
+  plan.total_bytes = (off + 255) / 256 * 256;
 }
 
 // ---- pack kernels -----------------------------------------------------------------------------------
-__global__ void k_pack_absmax(const float* __restrict__ prm, TcAux* aux, const PackPlan plan) {
-  int st = blockIdx.y;
-  int64_t n = (int64_t)plan.st_rows[st] * plan.st_ld[st];
-  const float* w = prm + plan.st_w_off[st];
+// W_uf[j][k] = sum_m W_v[j][m] W_f[m][k],  b_uf[j] = b_v[j] + sum_m W_v[j][m] b_f[m]   (fp64 accumulation, fp32 result)
+__global__ void k_fuse_views(const float* __restrict__ prm, float* __restrict__ fused, const NetGeom g) {
+  const int j = blockIdx.x, H2 = g.W / 2;
+  const float* wv = prm + g.w_views + (int64_t)j * (g.W + g.encv);
+  for (int k = threadIdx.x; k <= g.W; k += blockDim.x) {
+    double acc = 0.0;
+    if (k < g.W) {
+      for (int m = 0; m < g.W; ++m) acc += (double)wv[m] * (double)prm[g.w_feat + (int64_t)m * g.W + k];
+      fused[(int64_t)j * g.W + k] = (float)acc;
+    } else {
+      for (int m = 0; m < g.W; ++m) acc += (double)wv[m] * (double)prm[g.b_feat + m];
+      fused[(int64_t)H2 * g.W + j] = (float)(acc + (double)prm[g.b_views + j]);
+    }
+  }
+}
+__device__ __forceinline__ const float* group_src(const PackGroup& pg, const float* prm, const float* fused) {
+  return (pg.src ? fused : prm) + pg.w_off;
+}
+__global__ void k_pack_absmax(const float* __restrict__ prm, uint8_t* __restrict__ img, const PackPlan plan) {
+  const int st = blockIdx.y, gi = blockIdx.z;
+  const PackGroup& pg = plan.grp[st][gi];
+  TcAux* aux = reinterpret_cast<TcAux*>(img);
+  const int64_t n = (int64_t)pg.rows * pg.ld;
+  const float* w = group_src(pg, prm, reinterpret_cast<const float*>(img + plan.fused_off));
   float m = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
 #pragma unroll
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(&aux->absmax_bits[st], __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && n > 0) atomicMax(&aux->absmax_bits[st][gi], __float_as_uint(m));
 }
-__device__ __forceinline__ float stage_scale(const TcAux* aux, int st) {
-  float amax = __uint_as_float(aux->absmax_bits[st]);
+__device__ __forceinline__ float stage_scale(const TcAux* aux, int st, int gi) {
+  float amax = __uint_as_float(aux->absmax_bits[st][gi]);
   if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
   int e;
   frexpf(amax, &e);                      // amax = m * 2^e, m in [0.5, 1)
   return ldexpf(1.f, 15 - e);            // amax*scale in [2^14, 2^15)
 }
-__global__ void k_pack_aux(const float* __restrict__ prm, TcAux* aux, const PackPlan plan, const NetGeom g) {
+__global__ void k_pack_aux(const float* __restrict__ prm, uint8_t* __restrict__ img, const PackPlan plan, const NetGeom g) {
+  TcAux* aux = reinterpret_cast<TcAux*>(img);
+  const float* fused = reinterpret_cast<const float*>(img + plan.fused_off);
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int nt = gridDim.x * blockDim.x;
-  for (int st = t; st < 16; st += nt) aux->inv_scale[st] = (st < plan.nst) ? 1.f / stage_scale(aux, st) : 0.f;   // acc -> 16*x
-  for (int i = t; i < 16 * 256; i += nt) {
-    int st = i / 256, c = i % 256;
-    aux->bias[st][c] = (st < plan.nst && c < plan.st_nb[st]) ? prm[plan.st_b_off[st] + c] * kActScale : 0.f;   // 16*b
+  for (int i = t; i < 32; i += nt) {
+    const int st = i >> 1, gi = i & 1;
+    float v = 0.f;
+    if (st < plan.nst) v = 1.f / stage_scale(aux, st, plan.grp[st][gi].rows > 0 ? gi : 0);   // acc -> 16*x
+    aux->inv_scale[st][gi] = v;
   }
   const int H = g.W / 2;
+  for (int i = t; i < 16 * 256; i += nt) {
+    int st = i / 256, c = i % 256;
+    float v = 0.f;
+    if (st < plan.nst) {
+      const int r0 = plan.grp[st][0].rows;
+      const int gi = (c < r0) ? 0 : 1, cc = c - (gi ? r0 : 0);
+      const PackGroup& pg = plan.grp[st][gi];
+      if (cc < pg.rows) v = (pg.bsrc ? fused[(int64_t)H * g.W + cc] : prm[pg.b_off + cc]) * kActScale;   // 16*b
+    }
+    aux->bias[st][c] = v;
+  }
   for (int i = t; i < kHeadFloats; i += nt) {
     float v = 0.f;
     const float hs = 1.f / kActScale;          // head weights act on 16*x
@@ -174,16 +234,21 @@ __global__ void k_pack_aux(const float* __restrict__ prm, TcAux* aux, const Pack
     aux->w_vdir[r][c] = (r < H && c < g.encv) ? prm[g.w_views + (int64_t)r * (g.W + g.encv) + g.W + c] : 0.f;
   }
 }
-__global__ void k_fix_scale(TcAux* aux) { aux->inv_scale[0] = 1.f / stage_scale(aux, 0); }
+__global__ void k_fix_scale(TcAux* aux) { aux->inv_scale[0][0] = aux->inv_scale[0][1] = 1.f / stage_scale(aux, 0, 0); }
 // one block per (slab, 64-row group): writes the hi (and lo) SWIZZLE_128B K-major image of the slab
 __global__ void k_pack_slabs(const float* __restrict__ prm, uint8_t* __restrict__ img, const PackPlan plan) {
   const PackSlab ps = plan.s[blockIdx.x];
   const TcAux* aux = reinterpret_cast<const TcAux*>(img);
-  const float scale = stage_scale(aux, ps.stage);
+  const float* fused = reinterpret_cast<const float*>(img + plan.fused_off);
+  const PackGroup g0 = plan.grp[ps.stage][0], g1 = plan.grp[ps.stage][1];
+  const float* src[2] = {group_src(g0, prm, fused), group_src(g1, prm, fused)};
+  const float scale[2] = {stage_scale(aux, ps.stage, 0), g1.rows > 0 ? stage_scale(aux, ps.stage, 1) : 1.f};
   for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < ps.n * 64; e += gridDim.y * blockDim.x) {
     int n = e >> 6, k = e & 63;
+    const int gi = (n < g0.rows) ? 0 : 1, r = n - (gi ? g0.rows : 0);
+    const PackGroup& pg = gi ? g1 : g0;
     float w = 0.f;
-    if (n < ps.nvalid && k < ps.kvalid) w = prm[ps.w_off + (int64_t)n * ps.ld + ps.col0 + k] * scale;
+    if (r < pg.rows && k < ps.kvalid[gi]) w = src[gi][(int64_t)r * pg.ld + ps.col0[gi] + k] * scale[gi];
     __half h = __float2half_rn(w);
     size_t byte = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
     *reinterpret_cast<__half*>(img + ps.dst_hi + byte) = h;
@@ -253,11 +318,12 @@ __device__ __forceinline__ void producer_tile(const TcProg& pg, const uint8_t* i
                                               uint32_t& chunk, uint32_t crank, uint32_t csize, uint32_t pidx) {
   const uint8_t* src = img + kAuxBytes;
   const uint16_t mask = (uint16_t)((1u << csize) - 1u);
+  const int nplanes = exact ? 2 : 1;
   for (int st = 0; st < pg.nst; ++st) {
-    const uint32_t bytes = (uint32_t)pg.st[st].n * 128u;
-    const uint32_t share = bytes / csize;
-    const int planes = pg.st[st].nslab * (exact ? 2 : 1);
+    const int planes = pg.st[st].nslab * nplanes;
     for (int c = 0; c < planes; ++c) {
+      const uint32_t bytes = (uint32_t)pg.st[st].sn[c / nplanes] * 128u;
+      const uint32_t share = bytes / csize;
       if (chunk % kNumProducers != pidx) { src += bytes; ++chunk; continue; }   // chunks alternate between the producer warps
       const uint32_t slot = chunk % nslots, par = (chunk / nslots) & 1u;
       mbar_wait(smem_u32(&sm.empty[slot]), par ^ 1u, 100 + (int)slot);     // released by every CTA of the cluster
@@ -301,7 +367,6 @@ __device__ __forceinline__ void mma_tile(const TcProg& pg, bool exact, const Sme
     ++it;
     tc_fence_after();
     if (trace) trace[st * kTraceStamps + 3] = clock64();        // a_ready observed by the MMA warp
-    const uint32_t idesc = make_idesc_f16(S.n);
     const int nchunks = S.nslab * nplanes;
     if (elect_one()) {
       // The whole stage is issued by the elected lane inside ONE block: no reconvergence (= no wait for the MMA
@@ -310,6 +375,7 @@ __device__ __forceinline__ void mma_tile(const TcProg& pg, bool exact, const Sme
       uint32_t accum = 0;
       for (int j = 0; j < S.nslab; ++j) {
         const int asrc = S.asrc[j];
+        const uint32_t idesc = make_idesc_f16(S.sn[j]);
         for (int plane = 0; plane < nplanes; ++plane) {
           // full[cur.slot] of THIS chunk was already waited for (inside the previous chunk, or before the first tile)
           const uint32_t b = ring + cur.slot * kSlotBytes;
@@ -425,7 +491,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_
   for (int j = 0; j < kCW; j += 2) {
     float x0 = fmaf(__uint_as_float(v[j]), inv16, bz[j]);
     float x1 = fmaf(__uint_as_float(v[j + 1]), inv16, bz[j + 1]);
-    if (KIND != EPI_FEAT && KIND != EPI_RAW) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+    if (KIND != EPI_RAW) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
     if (KIND == EPI_HIDDEN_SIGMA) {
       hacc[0] = fmaf(h0[j], x0, hacc[0]);
       hacc[0] = fmaf(h0[j + 1], x1, hacc[0]);
@@ -448,7 +514,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_
     }
     if (DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM) && gout)
       *reinterpret_cast<float2*>(gout + c0 + j) = make_float2(x0 * (1.f / kActScale), x1 * (1.f / kActScale));
-    if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FEAT) {
+    if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA) {
       __half2 hh = __floats2half2_rn(x0, x1);
       hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
       if (EXACT) {
@@ -458,7 +524,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_
       }
     }
   }
-  if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FEAT) {
+  if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA) {
     tmem_st8(tm_lane + kColAhi + (c0 >> 1), hi);
     if (EXACT) tmem_st8(tm_lane + kColAlo + (c0 >> 1), lo);
   }
@@ -492,7 +558,6 @@ __device__ __forceinline__ void epilogue(int kind, int cb, int ce, uint32_t tm_l
     case EPI_HIDDEN: epi_kind<EPI_HIDDEN, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
     case EPI_HIDDEN_SIGMA: epi_kind<EPI_HIDDEN_SIGMA, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
     case EPI_SEM: epi_kind<EPI_SEM, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    case EPI_FEAT: epi_kind<EPI_FEAT, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
     case EPI_RGB: epi_kind<EPI_RGB, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
     default: epi_kind<EPI_RAW, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
   }
@@ -604,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
         const TcProg& pg = P.prog[net];
         float acc = 0.f;
         if (j < pg.H2) {
-          acc = __ldg(&aux->bias[pg.nst - 1][j]);                     // 16 * b_views
+          acc = __ldg(&aux->bias[pg.nst - 1][pg.ub_off + j]);         // 16 * (b_views + W_v[:, :W] b_feat)
           float d = 0.f;
 #pragma unroll
           for (int c = 0; c < 28; ++c) d = fmaf(__ldg(&aux->w_vdir[j][c]), sm.encv[rl * 28 + c], d);   // zero padded beyond encv
@@ -660,27 +725,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             float* sb = sm.sbias + (it_bias & 1u) * 256;
             ++it_bias;
             sb[t] = __ldg(&aux->bias[st][t]);                            // kWorkers == 256 == bias row length
-            const float inv16 = __ldg(&aux->inv_scale[st]);
+            const bool merged = Sg.epi == EPI_SEM_RGB;                   // columns [0,H2) semantic hidden | [H2,2*H2) views hidden
+            const float inv16 = __ldg(&aux->inv_scale[st][merged ? hf : 0]);
             named_bar_sync(1, kWorkers);
-            const float* bias = (Sg.epi == EPI_RGB) ? (sm.dirbias + (pass * 2 + rl) * kHalfMax) : sb;
+            const bool rgb_part = Sg.epi == EPI_RGB || (merged && hf == 1);
+            const bool sem_part = merged && hf == 0;
+            const float* bias = rgb_part ? (sm.dirbias + (pass * 2 + rl) * kHalfMax) : sb;
             int cb, ce;
-            chunk_range(Sg.n, hf, cb, ce);
+            if (merged) { cb = 0; ce = pg.H2 / kCW; } else chunk_range(Sg.n, hf, cb, ce);
             if (tr) tr[st * kTraceStamps + 0] = clock64();                 // worker starts waiting for the accumulator
             mbar_wait(smem_u32(sm.acc_full), it_acc & 1u, 500 + st);
             ++it_acc;
             tc_fence_after();
             if (tr) tr[st * kTraceStamps + 1] = clock64();                 // accumulator ready
-            float* ha = (Sg.epi == EPI_HIDDEN_SIGMA) ? &hacc[0] : (Sg.epi == EPI_SEM) ? &hacc[4] : &hacc[1];
+            float* ha = (Sg.epi == EPI_HIDDEN_SIGMA) ? &hacc[0] : sem_part ? &hacc[4] : &hacc[1];
             float* gout = nullptr;
             if (DUMP && rowvalid && rp[9] > 0.f) {
               const size_t pt = (size_t)ray * S + i;
               if (Sg.epi == EPI_HIDDEN_SIGMA && P.dump_h[pass]) gout = P.dump_h[pass] + pt * pg.W;
-              if (Sg.epi == EPI_SEM && P.dump_s0[pass]) gout = P.dump_s0[pass] + pt * pg.H2;
+              if (sem_part && P.dump_s0[pass]) gout = P.dump_s0[pass] + pt * pg.H2;
             }
-            epilogue<EXACT, DUMP>(Sg.epi, cb, ce, tm_lane, inv16, bias, hw, P.sem_dim, ha, gout);
+            const int kind = merged ? (hf ? EPI_RGB : EPI_SEM) : Sg.epi;
+            epilogue<EXACT, DUMP>(kind, cb, ce, tm_lane + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout);
             if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
             if (st + 1 < pg.nst) {
-              if (Sg.epi != EPI_SEM) tmem_wait_st();
+              tmem_wait_st();
               tc_fence_before();
               mbar_arrive(smem_u32(sm.a_ready));
             }
@@ -828,7 +897,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
     float dummy[4];
     int cb, ce;
     chunk_range(P.N, hf, cb, ce);
-    epilogue<EXACT>(EPI_RAW, cb, ce, tm_lane, __ldg(&aux->inv_scale[0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)row * P.N);
+    epilogue<EXACT>(EPI_RAW, cb, ce, tm_lane, __ldg(&aux->inv_scale[0][0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)row * P.N);
   }
   tc_fence_before();
   __syncthreads();
@@ -837,10 +906,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
 
 int run_pack(const PackPlan& plan, const NetGeom* g, const float* params, void* packed, cudaStream_t st) {
   TcAux* aux = reinterpret_cast<TcAux*>(packed);
+  uint8_t* img = reinterpret_cast<uint8_t*>(packed);
   NSOS_CHECK_CUDA(cudaMemsetAsync(aux->absmax_bits, 0, sizeof(aux->absmax_bits), st));
-  k_pack_absmax<<<dim3(32, plan.nst), 256, 0, st>>>(params, aux, plan);
-  if (g) k_pack_aux<<<16, 256, 0, st>>>(params, aux, plan, *g);
-  k_pack_slabs<<<dim3(plan.nslab, 8), 256, 0, st>>>(params, reinterpret_cast<uint8_t*>(packed), plan);
+  if (g) k_fuse_views<<<g->W / 2, 128, 0, st>>>(params, reinterpret_cast<float*>(img + plan.fused_off), *g);
+  k_pack_absmax<<<dim3(32, plan.nst, 2), 256, 0, st>>>(params, img, plan);
+  if (g) k_pack_aux<<<16, 256, 0, st>>>(params, img, plan, *g);
+  k_pack_slabs<<<dim3(plan.nslab, 8), 256, 0, st>>>(params, img, plan);
   NSOS_CHECK_CUDA(cudaGetLastError());
   return NSOS_OK;
 }
@@ -1003,14 +1074,17 @@ int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in
   int64_t off = (int64_t)kAuxBytes;
   const int nsl = a_in_tmem ? K / 64 : 1;
   for (int j = 0; j < nsl; ++j) {
+    S.sn[S.nslab] = N;
     S.asrc[S.nslab++] = a_in_tmem ? j : A_GAMMA;
     PackSlab& ps = plan.s[plan.nslab++];
-    ps.w_off = 0; ps.ld = K; ps.col0 = 64 * j; ps.kvalid = a_in_tmem ? 64 : K; ps.nvalid = N; ps.n = N; ps.stage = 0;
+    ps.stage = 0; ps.n = N; ps.col0[0] = 64 * j; ps.kvalid[0] = a_in_tmem ? 64 : K; ps.col0[1] = 0; ps.kvalid[1] = 0;
     ps.dst_hi = off; off += (int64_t)N * 128;
     ps.dst_lo = -1;
     if (exact) { ps.dst_lo = off; off += (int64_t)N * 128; }
   }
-  plan.nst = 1; plan.st_w_off[0] = 0; plan.st_rows[0] = N; plan.st_ld[0] = K; plan.st_b_off[0] = 0; plan.st_nb[0] = 0;
+  plan.nst = 1;
+  plan.grp[0][0].src = 0; plan.grp[0][0].w_off = 0; plan.grp[0][0].ld = K; plan.grp[0][0].rows = N;
+  plan.fused_off = off;
   plan.total_bytes = off;
   NSOS_REQUIRE(scratch_bytes >= (size_t)off, NSOS_ERR_WORKSPACE, "selftest scratch too small: need %lld", (long long)off);
   NSOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, kAuxBytes, st));
