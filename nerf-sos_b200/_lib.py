@@ -8,6 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "lib", "libnerfsos.so")
+if os.environ.get("NSOS_LIB"):      # A/B testing of kernel variants: load another build of the same library
+    LIB_PATH = os.path.abspath(os.environ["NSOS_LIB"])
 SOURCES = ["api.cu", "simt_gemm.cu", "simt_render.cu", "tc_render.cu", "tc_wgrad.cu", "corr_loss.cu"]
 
 MODE_SIMT, MODE_TC_EXACT, MODE_TC_FAST = 0, 1, 2

@@ -35,6 +35,7 @@ __device__ __forceinline__ double group_sum(double v, int tid, int bar_id, doubl
 }
 
 // VolumetricRenderer.forward for one ray with 128 threads; thread t owns samples [t*ns, t*ns+ns), ns = ceil(S/128) <= 2.
+// maps_out may be nullptr (padding ray of an odd batch): the maps are then not written.
 __device__ inline void group_composite(const RayPass& p, int tid, int bar_id, const GroupScratch& gs, float* maps_out, float* weights_out) {
   const int ns = (p.S + kGroup - 1) / kGroup;
   const int i0 = tid * ns;
@@ -96,7 +97,7 @@ __device__ inline void group_composite(const RayPass& p, int tid, int bar_id, co
     }
   }
   group_bar(bar_id);
-  if (tid == 0) {
+  if (tid == 0 && maps_out) {
     float s[9];
     for (int k = 0; k < 5 + p.sem_dim; ++k) s[k] = gs.f[8 + k] + gs.f[8 + 9 + k] + gs.f[8 + 18 + k] + gs.f[8 + 27 + k];
     float dep = s[3], ac = s[4];

@@ -36,7 +36,17 @@ constexpr int kMaxSlots = 6;
 constexpr int kWorkers = 256;          // 8 row-worker warps: warp w -> TMEM lane quarter w%4, column half w/4
 constexpr int kMmaWarp = 8, kProducerWarp = 9;   // producer warps: kProducerWarp .. kProducerWarp + kNumProducers - 1
 constexpr int kNumProducers = 2;                // one thread can issue only ~1 bulk copy per 680 cycles (tools/bulk_rate.cu)
+#ifdef NSOS_AB_REGS
+// 12 warps at 168 registers; the 8 worker warps grow to 216, the other 4 (MMA issuer, producers, one idle) shrink to 72:
+// 8*32*216 + 4*32*72 = 12*32*168.
+constexpr int kThreads = 384;
+__device__ __forceinline__ void regs_worker() { asm volatile("setmaxnreg.inc.sync.aligned.u32 216;"); }
+__device__ __forceinline__ void regs_other() { asm volatile("setmaxnreg.dec.sync.aligned.u32 72;"); }
+#else
 constexpr int kThreads = 32 * (kProducerWarp + kNumProducers);
+__device__ __forceinline__ void regs_worker() {}
+__device__ __forceinline__ void regs_other() {}
+#endif
 constexpr float kActScale = 16.f;      // activations are stored as fp16(16*a): keeps the lo plane out of fp16 subnormals
 constexpr int kMaxStages = 13;
 constexpr int kMaxSlabs = 5;
@@ -450,7 +460,11 @@ __device__ __forceinline__ void encode_half(const float x[3], int L, int enc, bo
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         float s, c;
+#ifdef NSOS_AB_OLDSINCOS
         sincosf(__fmul_rn(x[a], f), &s, &c);
+#else
+        sincos_cw(__fmul_rn(x[a], f), &s, &c);
+#endif
         const int cs = 3 + 6 * k + a, cc = cs + 3;
         if (cs >= lo && cs < hi) e[cs - lo] = s;
         if (cc >= lo && cc < hi) e[cc - lo] = c;
@@ -463,24 +477,30 @@ __device__ __forceinline__ void encode_half(const float x[3], int L, int enc, bo
 
 // One 16-column chunk of an epilogue.  v = D read-out (already waited for).  x16 = 16*x = acc*inv16 + bias16
 // (+relu) feeds the fp32 head accumulators (head weights are pre-divided by 16) and/or becomes the next A operand.
-constexpr int kCW = 16;   // epilogue chunk width in columns
+#ifdef NSOS_AB_X32
+constexpr int kCW = 32;   // epilogue chunk width in columns (one tcgen05.ld)
+#else
+constexpr int kCW = 16;
+#endif
+constexpr int kSW = 16;   // arithmetic sub-block of a chunk
 template <int KIND, bool EXACT, bool DUMP>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
-                                          const float* __restrict__ hw, int sem_dim, float* hacc, float* __restrict__ gout) {
-  uint32_t hi[kCW / 2], lo[kCW / 2];
-  // bias and head weights of this chunk as 16-byte shared loads (c0 is a multiple of 16 floats; all bases 16 B aligned)
-  float bz[kCW], h0[kCW], h1[kCW], h2[kCW];
+__device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
+                                        const float* __restrict__ hw, int sem_dim, float (&hacc)[4], float (&hodd)[4],
+                                        float* __restrict__ gout) {
+  uint32_t hi[kSW / 2], lo[kSW / 2];
+  // bias and head weights of this sub-block as 16-byte shared loads (c0 is a multiple of 16 floats; all bases 16 B aligned)
+  float bz[kSW], h0[kSW], h1[kSW], h2[kSW];
   {
     const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
-    for (int q = 0; q < kCW / 4; ++q) { float4 t4 = b4[q]; bz[4 * q] = t4.x; bz[4 * q + 1] = t4.y; bz[4 * q + 2] = t4.z; bz[4 * q + 3] = t4.w; }
+    for (int q = 0; q < kSW / 4; ++q) { float4 t4 = b4[q]; bz[4 * q] = t4.x; bz[4 * q + 1] = t4.y; bz[4 * q + 2] = t4.z; bz[4 * q + 3] = t4.w; }
     if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_RGB) {
       const int o0 = (KIND == EPI_HIDDEN_SIGMA) ? kHeadWAlpha : (KIND == EPI_SEM) ? kHeadWS2 : kHeadWRgb;
       const float4* w0 = reinterpret_cast<const float4*>(hw + o0 + c0);
       const float4* w1 = reinterpret_cast<const float4*>(hw + o0 + kHalfMax + c0);
       const float4* w2 = reinterpret_cast<const float4*>(hw + o0 + 2 * kHalfMax + c0);
 #pragma unroll
-      for (int q = 0; q < kCW / 4; ++q) {
+      for (int q = 0; q < kSW / 4; ++q) {
         float4 t4 = w0[q]; h0[4 * q] = t4.x; h0[4 * q + 1] = t4.y; h0[4 * q + 2] = t4.z; h0[4 * q + 3] = t4.w;
         if (KIND != EPI_HIDDEN_SIGMA) { t4 = w1[q]; h1[4 * q] = t4.x; h1[4 * q + 1] = t4.y; h1[4 * q + 2] = t4.z; h1[4 * q + 3] = t4.w; }
         if (KIND == EPI_RGB) { t4 = w2[q]; h2[4 * q] = t4.x; h2[4 * q + 1] = t4.y; h2[4 * q + 2] = t4.z; h2[4 * q + 3] = t4.w; }
@@ -488,29 +508,35 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_
     }
   }
 #pragma unroll
-  for (int j = 0; j < kCW; j += 2) {
+  for (int j = 0; j < kSW; j += 2) {
     float x0 = fmaf(__uint_as_float(v[j]), inv16, bz[j]);
     float x1 = fmaf(__uint_as_float(v[j + 1]), inv16, bz[j + 1]);
     if (KIND != EPI_RAW) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+    // head partial sums: two independent FMA chains (even / odd columns) per output, all in registers
     if (KIND == EPI_HIDDEN_SIGMA) {
       hacc[0] = fmaf(h0[j], x0, hacc[0]);
-      hacc[0] = fmaf(h0[j + 1], x1, hacc[0]);
+      hodd[0] = fmaf(h0[j + 1], x1, hodd[0]);
     } else if (KIND == EPI_SEM) {
-      // sem_dim <= 2 uses the vector-loaded rows; wider heads fall back to scalar shared loads
-      hacc[0] = fmaf(h0[j], x0, hacc[0]); hacc[0] = fmaf(h0[j + 1], x1, hacc[0]);
-      if (sem_dim > 1) { hacc[1] = fmaf(h1[j], x0, hacc[1]); hacc[1] = fmaf(h1[j + 1], x1, hacc[1]); }
+      hacc[0] = fmaf(h0[j], x0, hacc[0]); hodd[0] = fmaf(h0[j + 1], x1, hodd[0]);
+      if (sem_dim > 1) { hacc[1] = fmaf(h1[j], x0, hacc[1]); hodd[1] = fmaf(h1[j + 1], x1, hodd[1]); }
+    } else if (KIND == EPI_RGB) {
+      hacc[0] = fmaf(h0[j], x0, hacc[0]); hodd[0] = fmaf(h0[j + 1], x1, hodd[0]);
+      hacc[1] = fmaf(h1[j], x0, hacc[1]); hodd[1] = fmaf(h1[j + 1], x1, hodd[1]);
+      hacc[2] = fmaf(h2[j], x0, hacc[2]); hodd[2] = fmaf(h2[j + 1], x1, hodd[2]);
+    } else if (KIND == EPI_RAW) {
+      gout[c0 + j] = x0 * (1.f / kActScale); gout[c0 + j + 1] = x1 * (1.f / kActScale);
+    }
+#ifdef NSOS_AB_SEMLOOP
+    if (KIND == EPI_SEM) {
+#else
+    if (KIND == EPI_SEM && sem_dim > 2) {       // wide heads: warp-uniform branch, scalar shared loads
+#endif
 #pragma unroll
       for (int s = 2; s < kSemMax; ++s)
         if (s < sem_dim) {
           hacc[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j], x0, hacc[s]);
-          hacc[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j + 1], x1, hacc[s]);
+          hodd[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j + 1], x1, hodd[s]);
         }
-    } else if (KIND == EPI_RGB) {
-      hacc[0] = fmaf(h0[j], x0, hacc[0]); hacc[0] = fmaf(h0[j + 1], x1, hacc[0]);
-      hacc[1] = fmaf(h1[j], x0, hacc[1]); hacc[1] = fmaf(h1[j + 1], x1, hacc[1]);
-      hacc[2] = fmaf(h2[j], x0, hacc[2]); hacc[2] = fmaf(h2[j + 1], x1, hacc[2]);
-    } else if (KIND == EPI_RAW) {
-      gout[c0 + j] = x0 * (1.f / kActScale); gout[c0 + j + 1] = x1 * (1.f / kActScale);
     }
     if (DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM) && gout)
       *reinterpret_cast<float2*>(gout + c0 + j) = make_float2(x0 * (1.f / kActScale), x1 * (1.f / kActScale));
@@ -531,22 +557,43 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_
 }
 
 template <int KIND, bool EXACT, bool DUMP>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
+                                          const float* __restrict__ hw, int sem_dim, float (&hacc)[4], float (&hodd)[4],
+                                          float* __restrict__ gout) {
+#pragma unroll
+  for (int sb = 0; sb < kCW / kSW; ++sb)
+    epi_sub<KIND, EXACT, DUMP>(&v[kSW * sb], tm_lane, c0 + kSW * sb, inv16, bias, hw, sem_dim, hacc, hodd, gout);
+}
+__device__ __forceinline__ void tmem_ldc(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+__device__ __forceinline__ void tmem_ldc(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[16]) { tmem_wait_ld_fence16(r); }
+__device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[32]) { tmem_wait_ld_fence(r); }
+
+template <int KIND, bool EXACT, bool DUMP>
 __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw, int sem_dim,
                                          float* hacc, float* gout) {
   // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
   uint32_t va[kCW], vb[kCW];
   if (cb >= ce) return;
-  tmem_ld16(tm_lane + kColD + cb * kCW, va);
-  tmem_wait_ld_fence16(va);
+  float* const hout = hacc;
+  float he[4] = {0.f, 0.f, 0.f, 0.f}, ho[4] = {0.f, 0.f, 0.f, 0.f};
+  tmem_ldc(tm_lane + kColD + cb * kCW, va);
+  tmem_wait_ldc(va);
   for (int c = cb; c < ce; c += 2) {
-    if (c + 1 < ce) tmem_ld16(tm_lane + kColD + (c + 1) * kCW, vb);
-    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, hacc, gout);
+    if (c + 1 < ce) tmem_ldc(tm_lane + kColD + (c + 1) * kCW, vb);
+    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, he, ho, gout);
     if (c + 1 < ce) {
-      tmem_wait_ld_fence16(vb);
-      if (c + 2 < ce) tmem_ld16(tm_lane + kColD + (c + 2) * kCW, va);
-      epi_chunk<KIND, EXACT, DUMP>(vb, tm_lane, (c + 1) * kCW, inv16, bias, hw, sem_dim, hacc, gout);
-      if (c + 2 < ce) tmem_wait_ld_fence16(va);
+      tmem_wait_ldc(vb);
+      if (c + 2 < ce) tmem_ldc(tm_lane + kColD + (c + 2) * kCW, va);
+      epi_chunk<KIND, EXACT, DUMP>(vb, tm_lane, (c + 1) * kCW, inv16, bias, hw, sem_dim, he, ho, gout);
+      if (c + 2 < ce) tmem_wait_ldc(va);
     }
+  }
+  if (KIND == EPI_HIDDEN_SIGMA) hout[0] += he[0] + ho[0];
+  if (KIND == EPI_RGB) { hout[0] += he[0] + ho[0]; hout[1] += he[1] + ho[1]; hout[2] += he[2] + ho[2]; }
+  if (KIND == EPI_SEM) {
+#pragma unroll
+    for (int k = 0; k < kSemMax; ++k) if (k < sem_dim) hout[k] += he[k] + ho[k];
   }
 }
 
@@ -603,7 +650,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
   const long long iters = (n_pairs + gridDim.x - 1) / gridDim.x;
   const int npass = P.fine ? 2 : 1;
 
-  if (warp >= kProducerWarp) {
+  if (warp >= kProducerWarp + kNumProducers) {
+    regs_other();                                                // spare warp (register redistribution build only)
+  } else if (warp >= kProducerWarp) {
+    regs_other();
     uint32_t chunk = 0;
     for (long long itp = 0; itp < iters; ++itp)
       for (int pass = 0; pass < npass; ++pass) {
@@ -612,6 +662,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           producer_tile(P.prog[pass], P.packed[pass], EXACT, sm, P.nslots, chunk, crank, csize, warp - kProducerWarp);
       }
   } else if (warp == kMmaWarp) {
+    regs_other();
     uint32_t it = 0;
     RingPos pos{0u, 0u};
     int ntile_seen = 0;
@@ -630,6 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
       }
   } else {
     // ================= row workers: 8 warps; warp w owns TMEM lanes 32*(w%4).. and column half w/4 =================
+    regs_worker();
     const int q4 = warp & 3, hf = warp >> 2;
     const int row = q4 * 32 + lane;
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
@@ -644,7 +696,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
       const bool pair_valid = pair_raw < n_pairs;
       const long long pair = pair_valid ? pair_raw : 0;
       named_bar_sync(1, kWorkers);
-      // ---- per-pair ray setup: o, d, near, far, |d|, gamma_v(d/|d|)
+      long long* pdbg = (P.trace && blockIdx.x == 0 && itp == 1 && t == 0) ? P.trace + (size_t)(kTraceTiles - 1) * 16 * kTraceStamps + 40 : nullptr;
+      if (pdbg) pdbg[0] = clock64();
+      // ---- per-pair ray setup: o, d, near, far, |d|, then gamma_v(d/|d|) with one (ray, octave, axis) per thread
       if (t < 2) {
         long long r = pair * 2 + t;
         bool valid = pair_valid && r < P.n_rays;
@@ -656,28 +710,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
         rp[6] = REPLAY ? 0.f : P.near[rr]; rp[7] = REPLAY ? 1.f : P.far[rr];
         float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
         rp[8] = nrm; rp[9] = valid ? 1.f : 0.f;
-        float vd[3] = {__fdiv_rn(d0, nrm), __fdiv_rn(d1, nrm), __fdiv_rn(d2, nrm)};
-        float e[3 + 6 * 4 + 1];
-        encode3(vd, P.prog[0].Lv, e);
-        for (int c = 0; c < 28; ++c) sm.encv[t * 28 + c] = (c < P.prog[0].encv) ? e[c] : 0.f;
+        rp[10] = __fdiv_rn(d0, nrm); rp[11] = __fdiv_rn(d1, nrm); rp[12] = __fdiv_rn(d2, nrm);   // nerf_net.py:165
       }
       named_bar_sync(1, kWorkers);
-      // view-direction half of views_linears.0 folded into a per-ray bias (fp32, x16): dirbias[net][ray][j]
-      for (int idx = t; idx < npass * 2 * kHalfMax; idx += kWorkers) {
-        int net = idx / (2 * kHalfMax), rl = (idx / kHalfMax) & 1, j = idx % kHalfMax;
-        const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[net]);
-        const TcProg& pg = P.prog[net];
-        float acc = 0.f;
-        if (j < pg.H2) {
-          acc = __ldg(&aux->bias[pg.nst - 1][pg.ub_off + j]);         // 16 * (b_views + W_v[:, :W] b_feat)
-          float d = 0.f;
-#pragma unroll
-          for (int c = 0; c < 28; ++c) d = fmaf(__ldg(&aux->w_vdir[j][c]), sm.encv[rl * 28 + c], d);   // zero padded beyond encv
-          acc = fmaf(d, kActScale, acc);
+      if (t < 64) {
+        // thread = (ray, octave slot, axis): slot 0 copies v, slot k+1 writes sin/cos(2^k v) (embedder.py:34-48); columns >= encv are zero
+        const int rl = t >> 5, k = (t & 31) / 3, a = (t & 31) % 3;
+        if ((t & 31) < 15) {
+          const float v = sm.rayp[rl * kRayP + 10 + a];
+          float* ev = sm.encv + rl * 28;
+          if (k == 0) ev[a] = v;
+          else if (k - 1 < P.prog[0].Lv) {
+            float sn, cs;
+            sincos_cw(__fmul_rn(v, (float)(1 << (k - 1))), &sn, &cs);
+            ev[3 + 6 * (k - 1) + a] = sn; ev[6 + 6 * (k - 1) + a] = cs;
+          } else { ev[3 + 6 * (k - 1) + a] = 0.f; ev[6 + 6 * (k - 1) + a] = 0.f; }
+          if (t == 32 * rl) ev[27] = 0.f;
         }
-        sm.dirbias[idx] = acc;
       }
       named_bar_sync(1, kWorkers);
+      if (pdbg) pdbg[1] = clock64();
+      // view-direction half of views_linears.0 folded into a per-ray bias (fp32, x16): dirbias[net][ray][j].
+      // One (net, j) per thread: the weight row is read once (7 x 16 B) and used for both rays of the pair.
+      {
+        const int net = t >> 7, j = t & (kHalfMax - 1);
+        if (net < npass) {
+          const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[net]);
+          const TcProg& pg = P.prog[net];
+          float acc0 = 0.f, acc1 = 0.f;
+          if (j < pg.H2) {
+            const float b = __ldg(&aux->bias[pg.nst - 1][pg.ub_off + j]);   // 16 * (b_views + W_v[:, :W] b_feat)
+            const float4* wr = reinterpret_cast<const float4*>(&aux->w_vdir[j][0]);
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 7; ++c4) {
+              const float4 w = __ldg(wr + c4);
+              const float4 e0 = *reinterpret_cast<const float4*>(sm.encv + 4 * c4), e1 = *reinterpret_cast<const float4*>(sm.encv + 28 + 4 * c4);
+              d0 = fmaf(w.x, e0.x, d0); d0 = fmaf(w.y, e0.y, d0); d0 = fmaf(w.z, e0.z, d0); d0 = fmaf(w.w, e0.w, d0);
+              d1 = fmaf(w.x, e1.x, d1); d1 = fmaf(w.y, e1.y, d1); d1 = fmaf(w.z, e1.z, d1); d1 = fmaf(w.w, e1.w, d1);
+            }
+            acc0 = fmaf(d0, kActScale, b); acc1 = fmaf(d1, kActScale, b);
+          }
+          sm.dirbias[(net * 2 + 0) * kHalfMax + j] = acc0;
+          sm.dirbias[(net * 2 + 1) * kHalfMax + j] = acc1;
+        }
+      }
+      named_bar_sync(1, kWorkers);
+      if (pdbg) pdbg[2] = clock64();
 
 #pragma unroll 1
       for (int pass = 0; pass < npass; ++pass) {
@@ -688,6 +767,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
 #pragma unroll 1
         for (int tile = 0; tile < ntiles; ++tile) {
           // ---- tile setup: sample position, point, gamma(x) -> swizzled smem A tile (each half-warp-group writes 32 columns)
+          long long* tr = nullptr;
+          if (P.trace && blockIdx.x == 0 && t == 0 && ntile_seen < kTraceTiles - 1) tr = P.trace + (size_t)ntile_seen * 16 * kTraceStamps;
+          ++ntile_seen;
+          if (tr) tr[15 * kTraceStamps + 0] = clock64();                   // tile setup starts
           const int q = tile * 128 + row;
           const bool rowvalid = q < 2 * S;
           const int rl = rowvalid ? q / S : 0, i = rowvalid ? q % S : 0;
@@ -714,9 +797,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(smem_u32(sm.a_ready));
-          long long* tr = nullptr;
-          if (P.trace && blockIdx.x == 0 && t == 0 && ntile_seen < kTraceTiles - 1) tr = P.trace + (size_t)ntile_seen * 16 * kTraceStamps;
-          ++ntile_seen;
+          if (tr) tr[15 * kTraceStamps + 1] = clock64();                   // gamma tile written, a_ready signalled
 
           float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0] sigma, [1..3] rgb, [4..7] sem (partial over my columns)
 #pragma unroll 1
@@ -747,6 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             }
             const int kind = merged ? (hf ? EPI_RGB : EPI_SEM) : Sg.epi;
             epilogue<EXACT, DUMP>(kind, cb, ce, tm_lane + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout);
+            if (Sg.epi == EPI_HIDDEN_SIGMA && hf == 1) sm.hpart[row * 8] = hacc[0];   // sigma share of the upper column half
             if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
             if (st + 1 < pg.nst) {
               tmem_wait_st();
@@ -754,24 +836,44 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               mbar_arrive(smem_u32(sm.a_ready));
             }
           }
-          // ---- combine the two column halves and emit the raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
-          if (hf == 1) {
+          // ---- emit the raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
+          float* graw = (pass == 0 && P.fine) ? P.out.raw0 : P.out.raw;
+          float* gr_row = (graw && rp[9] > 0.f) ? graw + ((size_t)ray * S + i) * P.C : nullptr;
+#ifdef NSOS_AB_OLDTAIL
+          if (false) {
+#else
+          if (pg.st[pg.nst - 1].epi == EPI_SEM_RGB) {
+#endif
+            // merged head stage: worker half 1 owns the rgb sums, half 0 the semantic sums; the sigma share of half 1 was
+            // exchanged after the last trunk layer (at least one named barrier ago), so no barrier is needed here and the
+            // next tile's setup starts at once
+            if (rowvalid) {
+              float* rw = sm.rawbuf + (size_t)q * P.C;
+              if (hf == 0) {
+                rw[3] = hacc[0] + sm.hpart[row * 8] + hw[kHeadBAlpha];
+                for (int s = 0; s < P.sem_dim; ++s) rw[4 + s] = hacc[4 + s] + hw[kHeadBS2 + s];
+                if (gr_row) for (int c = 3; c < P.C; ++c) gr_row[c] = rw[c];
+              } else {
+                rw[0] = hacc[1] + hw[kHeadBRgb]; rw[1] = hacc[2] + hw[kHeadBRgb + 1]; rw[2] = hacc[3] + hw[kHeadBRgb + 2];
+                if (gr_row) { gr_row[0] = rw[0]; gr_row[1] = rw[1]; gr_row[2] = rw[2]; }
+              }
+            }
+          } else {
+            if (hf == 1) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sm.hpart[row * 8 + c] = hacc[c];
-          }
-          named_bar_sync(1, kWorkers);
-          if (hf == 0 && rowvalid) {
-            const float* hp = sm.hpart + row * 8;
-            float* rw = sm.rawbuf + (size_t)q * P.C;
-            rw[0] = hacc[1] + hp[1] + hw[kHeadBRgb]; rw[1] = hacc[2] + hp[2] + hw[kHeadBRgb + 1]; rw[2] = hacc[3] + hp[3] + hw[kHeadBRgb + 2];
-            rw[3] = hacc[0] + hp[0] + hw[kHeadBAlpha];
-            for (int s = 0; s < P.sem_dim; ++s) rw[4 + s] = hacc[4 + s] + hp[4 + s] + hw[kHeadBS2 + s];
-            float* graw = (pass == 0 && P.fine) ? P.out.raw0 : P.out.raw;
-            if (graw && rp[9] > 0.f) {
-              float* g = graw + ((size_t)ray * S + i) * P.C;
-              for (int c = 0; c < P.C; ++c) g[c] = rw[c];
+              for (int c = 0; c < 8; ++c) sm.hpart[row * 8 + c] = hacc[c];
+            }
+            named_bar_sync(1, kWorkers);
+            if (hf == 0 && rowvalid) {
+              const float* hp = sm.hpart + row * 8;
+              float* rw = sm.rawbuf + (size_t)q * P.C;
+              rw[0] = hacc[1] + hp[1] + hw[kHeadBRgb]; rw[1] = hacc[2] + hp[2] + hw[kHeadBRgb + 1]; rw[2] = hacc[3] + hp[3] + hw[kHeadBRgb + 2];
+              rw[3] = hacc[0] + hp[0] + hw[kHeadBAlpha];
+              for (int s = 0; s < P.sem_dim; ++s) rw[4 + s] = hacc[4 + s] + hp[4 + s] + hw[kHeadBS2 + s];
+              if (gr_row) for (int c = 0; c < P.C; ++c) gr_row[c] = rw[c];
             }
           }
+          if (tr) tr[15 * kTraceStamps + 2] = clock64();                   // raw outputs of the tile emitted
         }
         // ---- compositing (+ resampling after the coarse pass): 4 warps (128 threads) per ray of the pair.
         // The gamma tiles are idle between tiles (all MMAs of the tile have completed): their first bytes serve as
@@ -795,12 +897,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           rpx.noise = (nz && valid) ? nz + ray * S : nullptr;
           rpx.noise_std = P.noise_std; rpx.seed = P.seed; rpx.ray = ray; rpx.rng_stream = pass ? RNG_NOISE1 : RNG_NOISE0;
           rpx.dnorm = rp[8]; rpx.S = S; rpx.C = P.C; rpx.sem_dim = P.sem_dim; rpx.white_bkgd = P.white_bkgd;
-          float scratch_maps[6 + kSemMax];
           float* maps = valid ? P.out.maps + (size_t)ray * P.ML + (coarse_of_two ? P.C6 : 0) : nullptr;
           float* wsm = sm.w0 + gr * P.Sc;     // coarse weights stay in smem for the resampling
           float* gw = coarse_of_two ? P.out.weights0 : P.out.weights;
           float* wout = (pass == 0) ? wsm : ((gw && valid) ? gw + ray * S : nullptr);
-          group_composite(rpx, gt, gbar, gsc, maps ? maps : scratch_maps, wout);
+          group_composite(rpx, gt, gbar, gsc, maps, wout);      // maps == nullptr: dummy ray, nothing is written
           if (gdbg) gdbg[9] = clock64();
           if (pass == 0) {
             if (gw && valid) for (int k = gt; k < S; k += kGroup) gw[ray * S + k] = wsm[k];
@@ -849,7 +950,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
   init_pipeline(sm, P.nslots, warp, 1);
   const uint32_t tm = *sm.tmem_ptr;
-  if (warp >= kProducerWarp) {
+  if (warp >= kProducerWarp + kNumProducers) {
+  } else if (warp >= kProducerWarp) {
     uint32_t chunk = 0;
     producer_tile(P.prog, P.packed, EXACT, sm, P.nslots, chunk, 0, 1, warp - kProducerWarp);
   } else if (warp == kMmaWarp) {
@@ -866,11 +968,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
       // each worker half writes its half of the K columns (16-column chunks) of the A planes
       int cb, ce;
       chunk_range(P.K, hf, cb, ce);
-      for (int c = cb; c < ce; ++c) {
-        const int c0 = c * kCW;
-        uint32_t hi[kCW / 2], lo[kCW / 2];
+      for (int c = cb * (kCW / kSW); c < ce * (kCW / kSW); ++c) {
+        const int c0 = c * kSW;
+        uint32_t hi[kSW / 2], lo[kSW / 2];
 #pragma unroll
-        for (int j = 0; j < kCW; j += 2) {
+        for (int j = 0; j < kSW; j += 2) {
           float a0 = P.a[(size_t)row * P.K + c0 + j] * kActScale, a1 = P.a[(size_t)row * P.K + c0 + j + 1] * kActScale;
           __half2 hh = __floats2half2_rn(a0, a1);
           float2 hf2 = __half22float2(hh);

@@ -21,7 +21,7 @@ print("mma_lead = a_ready seen by MMA warp -> accumulator ready (MMA execution i
 for tile in range(8):
     t = tr[tile]
     if t[0, 1] == 0: break
-    nst = int((t[:, 1] > 0).sum())
+    nst = int((t[:10, 1] > 0).sum())
     base = t[0, 0]
     rows = []
     for st in range(nst):
@@ -29,13 +29,17 @@ for tile in range(8):
         rows.append((st, acc - w0, epi - acc, acc - ar, iss - ar))
     tot = t[nst - 1, 2] - t[0, 0]
     print(f"tile {tile}: {nst} stages, total {tot} cycles;  sum acc_wait {sum(r[1] for r in rows)}  sum epi {sum(r[2] for r in rows)}  sum mma_exec {sum(r[3] for r in rows)}")
-    if tile in (1, 2):
+    if tile in (1, 2, 3, 4):
         for r in rows: print(f"    stage {r[0]:2d}: acc_wait {r[1]:6d}  epi {r[2]:6d}  mma_exec {r[3]:6d}  issue {r[4]:6d}")
+    print(f"    setup (z, point, gamma -> smem) {t[15, 1] - t[15, 0]};  first acc wait starts {t[0, 0] - t[15, 1]} after a_ready;  tail (head combine, raw) {t[15, 2] - t[nst - 1, 2]}")
+    if tile + 1 < 16 and tr[tile + 1][15, 0] > 0:
+        print(f"    end of tile -> next tile's setup start (composite / resample / pair setup): {tr[tile + 1][15, 0] - t[15, 2]}")
     if tile + 1 < 16 and tr[tile + 1][0, 0] > 0:
         print(f"    gap to next tile's first wait (setup/composite): {tr[tile + 1][0, 0] - t[nst - 1, 2]}")
 
 
 g = tr[15].reshape(-1)
+print(f"pair setup (2nd pair of CTA 0): rays+dir encoding {g[41]-g[40]}  dir bias {g[42]-g[41]}")
 for ps, name in ((0, "coarse"), (1, "fine")):
     d = g[ps * 16: ps * 16 + 16]
     if d[8] == 0: continue
