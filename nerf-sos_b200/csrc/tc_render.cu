@@ -56,7 +56,7 @@ constexpr int kHalfMax = 128;          // W/2 max
 constexpr int kSemMax = 4;
 constexpr int kHeadFloats = 256 + 4 + kSemMax * kHalfMax + 4 + 3 * kHalfMax + 4;
 
-enum EpiKind { EPI_HIDDEN = 0, EPI_HIDDEN_SIGMA = 1, EPI_SEM = 2, EPI_RGB = 4, EPI_RAW = 5, EPI_SEM_RGB = 6 };
+enum EpiKind { EPI_HIDDEN = 0, EPI_HIDDEN_SIGMA = 1, EPI_SEM = 2, EPI_SEM_WIDE = 3, EPI_RGB = 4, EPI_RAW = 5, EPI_SEM_RGB = 6 };
 constexpr int A_GAMMA = -1;
 
 // fp32 side data at the head of the packed image
@@ -494,8 +494,9 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
     const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
     for (int q = 0; q < kSW / 4; ++q) { float4 t4 = b4[q]; bz[4 * q] = t4.x; bz[4 * q + 1] = t4.y; bz[4 * q + 2] = t4.z; bz[4 * q + 3] = t4.w; }
-    if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_RGB) {
-      const int o0 = (KIND == EPI_HIDDEN_SIGMA) ? kHeadWAlpha : (KIND == EPI_SEM) ? kHeadWS2 : kHeadWRgb;
+    constexpr bool SEM = (KIND == EPI_SEM || KIND == EPI_SEM_WIDE);
+    if (KIND == EPI_HIDDEN_SIGMA || SEM || KIND == EPI_RGB) {
+      const int o0 = (KIND == EPI_HIDDEN_SIGMA) ? kHeadWAlpha : SEM ? kHeadWS2 : kHeadWRgb;
       const float4* w0 = reinterpret_cast<const float4*>(hw + o0 + c0);
       const float4* w1 = reinterpret_cast<const float4*>(hw + o0 + kHalfMax + c0);
       const float4* w2 = reinterpret_cast<const float4*>(hw + o0 + 2 * kHalfMax + c0);
@@ -516,7 +517,7 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
     if (KIND == EPI_HIDDEN_SIGMA) {
       hacc[0] = fmaf(h0[j], x0, hacc[0]);
       hodd[0] = fmaf(h0[j + 1], x1, hodd[0]);
-    } else if (KIND == EPI_SEM) {
+    } else if (KIND == EPI_SEM || KIND == EPI_SEM_WIDE) {
       hacc[0] = fmaf(h0[j], x0, hacc[0]); hodd[0] = fmaf(h0[j + 1], x1, hodd[0]);
       if (sem_dim > 1) { hacc[1] = fmaf(h1[j], x0, hacc[1]); hodd[1] = fmaf(h1[j + 1], x1, hodd[1]); }
     } else if (KIND == EPI_RGB) {
@@ -526,11 +527,8 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
     } else if (KIND == EPI_RAW) {
       gout[c0 + j] = x0 * (1.f / kActScale); gout[c0 + j + 1] = x1 * (1.f / kActScale);
     }
-#ifdef NSOS_AB_SEMLOOP
-    if (KIND == EPI_SEM) {
-#else
-    if (KIND == EPI_SEM && sem_dim > 2) {       // wide heads: warp-uniform branch, scalar shared loads
-#endif
+    if (KIND == EPI_SEM_WIDE) {                 // sem_dim 3..4: own kind, so that the common case carries no branches
+
 #pragma unroll
       for (int s = 2; s < kSemMax; ++s)
         if (s < sem_dim) {
@@ -538,7 +536,7 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
           hodd[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j + 1], x1, hodd[s]);
         }
     }
-    if (DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM) && gout)
+    if (DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_SEM_WIDE) && gout)
       *reinterpret_cast<float2*>(gout + c0 + j) = make_float2(x0 * (1.f / kActScale), x1 * (1.f / kActScale));
     if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA) {
       __half2 hh = __floats2half2_rn(x0, x1);
@@ -579,6 +577,19 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float
   float he[4] = {0.f, 0.f, 0.f, 0.f}, ho[4] = {0.f, 0.f, 0.f, 0.f};
   tmem_ldc(tm_lane + kColD + cb * kCW, va);
   tmem_wait_ldc(va);
+#ifdef NSOS_AB_ONEBODY
+  // one copy of the chunk body (instruction-cache footprint): the prefetched chunk is moved into va with register copies
+#pragma unroll 1
+  for (int c = cb; c < ce; ++c) {
+    if (c + 1 < ce) tmem_ldc(tm_lane + kColD + (c + 1) * kCW, vb);
+    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, he, ho, gout);
+    if (c + 1 < ce) {
+      tmem_wait_ldc(vb);
+#pragma unroll
+      for (int k = 0; k < kCW; ++k) va[k] = vb[k];
+    }
+  }
+#else
   for (int c = cb; c < ce; c += 2) {
     if (c + 1 < ce) tmem_ldc(tm_lane + kColD + (c + 1) * kCW, vb);
     epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, he, ho, gout);
@@ -589,9 +600,11 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float
       if (c + 2 < ce) tmem_wait_ldc(va);
     }
   }
+#endif
   if (KIND == EPI_HIDDEN_SIGMA) hout[0] += he[0] + ho[0];
   if (KIND == EPI_RGB) { hout[0] += he[0] + ho[0]; hout[1] += he[1] + ho[1]; hout[2] += he[2] + ho[2]; }
-  if (KIND == EPI_SEM) {
+  if (KIND == EPI_SEM) { hout[0] += he[0] + ho[0]; if (sem_dim > 1) hout[1] += he[1] + ho[1]; }
+  if (KIND == EPI_SEM_WIDE) {
 #pragma unroll
     for (int k = 0; k < kSemMax; ++k) if (k < sem_dim) hout[k] += he[k] + ho[k];
   }
@@ -604,7 +617,10 @@ __device__ __forceinline__ void epilogue(int kind, int cb, int ce, uint32_t tm_l
   switch (kind) {
     case EPI_HIDDEN: epi_kind<EPI_HIDDEN, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
     case EPI_HIDDEN_SIGMA: epi_kind<EPI_HIDDEN_SIGMA, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    case EPI_SEM: epi_kind<EPI_SEM, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_SEM:
+      if (sem_dim <= 2) epi_kind<EPI_SEM, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout);
+      else epi_kind<EPI_SEM_WIDE, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout);
+      break;
     case EPI_RGB: epi_kind<EPI_RGB, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
     default: epi_kind<EPI_RAW, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
   }

@@ -275,7 +275,7 @@ def test_edge_shapes_and_bounds(mode):
 
 
 @pytest.mark.parametrize("mode", ["simt", "exact"])
-@pytest.mark.parametrize("variant", ["white_bkgd", "no_coord", "no_sem", "imp64"])
+@pytest.mark.parametrize("variant", ["white_bkgd", "no_coord", "no_sem", "imp64", "sem4"])
 def test_config_variants_vs_oracle(mode, variant):
     """Seeded random-init nets in configurations the shipped checkpoints do not cover."""
     from oracle import nerf_oracle as O
@@ -291,6 +291,8 @@ def test_config_variants_vs_oracle(mode, variant):
         kw["use_semantics"] = False; okw["use_semantics"] = False
     elif variant == "imp64":
         kw["N_importance"] = 64; okw["n_importance"] = 64
+    elif variant == "sem4":                                          # wide semantic head (own epilogue kind on the tcgen05 path)
+        kw["sem_dim"] = 4
     torch.manual_seed(5)
     net = NeRFNet(**kw)
     # make the field non-trivial: scale the density head so that alpha is not ~0 everywhere
