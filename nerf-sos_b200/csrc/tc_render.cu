@@ -508,6 +508,7 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
       }
     }
   }
+  float dq0 = 0.f, dq1 = 0.f;
 #pragma unroll
   for (int j = 0; j < kSW; j += 2) {
     float x0 = fmaf(__uint_as_float(v[j]), inv16, bz[j]);
@@ -536,8 +537,11 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
           hodd[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j + 1], x1, hodd[s]);
         }
     }
-    if (DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_SEM_WIDE) && gout)
-      *reinterpret_cast<float2*>(gout + c0 + j) = make_float2(x0 * (1.f / kActScale), x1 * (1.f / kActScale));
+    if (DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_SEM_WIDE) && gout) {
+      // saved activations: 16-byte stores (rows are W resp. W/2 floats, c0 + j a multiple of 4 on the odd pair)
+      if (j & 2) *reinterpret_cast<float4*>(gout + c0 + j - 2) = make_float4(dq0, dq1, x0 * (1.f / kActScale), x1 * (1.f / kActScale));
+      else { dq0 = x0 * (1.f / kActScale); dq1 = x1 * (1.f / kActScale); }
+    }
     if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA) {
       __half2 hh = __floats2half2_rn(x0, x1);
       hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
