@@ -140,18 +140,6 @@ class _TrainArgs:       # the fields train_one_step / the loss modules read (con
     app_corr_params = [0.18, 1, 0.46, 1]; geo_corr_params = [0.5, 1, 3, 1]
 
 
-class _FeatureStub:
-    """Deterministic stand-in for the DINO ViT-S/16 feature provider (models/extractor.py:204-213; no weights offline):
-    same interface and output shapes, a fixed random projection of the pooled patch."""
-    def get_vit_attn_feat(self, x):
-        import torch
-        B = x.shape[0]
-        p = torch.nn.functional.adaptive_avg_pool2d(x, 14).reshape(B, 3, 196).permute(0, 2, 1)
-        proj = torch.randn(3, 384, generator=torch.Generator().manual_seed(0)).to(x.device)
-        feat = p @ proj
-        return {"attn": feat[..., :1].permute(0, 2, 1), "cls_": feat.mean(1), "feat": feat}
-
-
 class _Loader:
     class dataset:
         @staticmethod
@@ -193,6 +181,8 @@ def run_train(args):
     opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=5e-4)
     sched = LRScheduler(opt, 5e-4, 0.1, 250000)
     losses = [None, None, CorrelationLoss(a), GeoCorrelationLoss(a)]
+    from nerfsos_b200.models.extractor import VitExtractor
+    dino = VitExtractor("dino_vits16", device=dev)                   # seeded random-init ViT-S/16: no DINO checkpoint offline
     rays_host = torch.from_numpy(llff_rays(n_rays, 200 + rank)).permute(1, 0, 2).reshape(B, Ps * Ps, 2, 3).contiguous().pin_memory()
     gt_host = torch.rand(B, Ps * Ps, 3, generator=torch.Generator().manual_seed(rank)).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -202,8 +192,8 @@ def run_train(args):
         # host -> device copy of the batch (what the DataLoader hands over), forward, losses, backward, all-reduce, Adam,
         # and the .item() reads of the logged scalars: the whole train_one_step, end to end
         it[0] += 1
-        out = train_one_step((rays_host, gt_host), [net, _FeatureStub()], opt, sched, _Loader(), it[0], losses, dev, a)
-        return float(out["loss"])
+        out = train_one_step((rays_host, gt_host), [net, dino], opt, sched, _Loader(), it[0], losses, dev, a)
+        return float(out["loss"].detach()) if hasattr(out["loss"], "detach") else float(out["loss"])
 
     def barrier():
         if dist is not None:
@@ -253,7 +243,7 @@ def run_train(args):
             "config": {"workload": "stage-2 training step: 8 patches x 64x64 rays per GPU, (64+128) samples, D=8 W=256 + seg head, "
                                    "--fix_backbone, appearance + geometry correlation losses, Adam (BASELINE configs[2])",
                        "rays_per_gpu": n_rays, "mode": args.mode, "weights": "shipped flower stage-2 checkpoint (fixture)",
-                       "features": "deterministic stand-in for the DINO provider (no weights offline)",
+                       "features": "DINO ViT-S/16 provider (nerfsos_b200.models.extractor) with seeded random-init weights (no checkpoint offline)",
                        "l2": "256 MB buffer written between timed steps (L2 flush, untimed)", "parallelism": f"patch-sharded x{world}"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "note": "whole step (render forward, both losses, backward, optimiser) against the tensor peak"},
