@@ -166,46 +166,52 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_sem_wgrad(const __grid_consta
       float gs[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid)
         for (int c = 0; c < 4; ++c) if (c < P.sem_dim) gs[c] = __ldg(&P.g_raw[p * P.C + 4 + c]);
-      float v[8];
+      // This thread's share of the slab is 64 h values, 16 gamma values and 32 s0 values of one point.  All of h is
+      // requested through a rolling window of 8 independent 16-byte loads per thread (32 KB in flight per SM, plus gamma / s0): the kernel streams 15 GB per
+      // training step and one or two loads in flight per thread left it at 23 % of the HBM roofline
+      // (profiles/r01_ncu_full_k_sem_wgrad_summary.txt).  The loads also overlap the tensor pipe working on the previous slab.
+      float hv[4][8];                                   // rolling window: 4 groups of 8 values (8 x 16 B in flight per thread)
       const float* hrow = P.h + p * 256 + q * 64;
-      load8(hrow, valid, v);
-      if (it > 0) { mbar_wait(smem_u32(sm.done), (uint32_t)((it - 1) & 1), 710); tc_fence_after(); }
-      // ---- B rows 0..255: h
-#pragma unroll 2
-      for (int g8 = 0; g8 < 8; ++g8) {
-        float nx[8];
-        if (g8 + 1 < 8) load8(hrow + 8 * (g8 + 1), valid, nx);
-        put8(sm.b[0], sm.b[1], q * 64 + 8 * g8, v, lane, wd);
-        if (g8 + 1 < 8) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = nx[i];
+      for (int g8 = 0; g8 < 4; ++g8) load8(hrow + 8 * g8, valid, hv[g8]);
+      if (it > 0) { mbar_wait(smem_u32(sm.done), (uint32_t)((it - 1) & 1), 710); tc_fence_after(); }
+      float ev[2][8], sv[4][8];
+      // ---- B rows 0..255: h (gamma and s0 are requested while h is being converted)
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {
+        put8(sm.b[0], sm.b[1], q * 64 + 8 * g8, hv[g8 & 3], lane, wd);
+        if (g8 + 4 < 8) load8(hrow + 8 * (g8 + 4), valid, hv[g8 & 3]);
+        // the window drains from g8 = 4 on: its registers take the gamma and s0 requests
+        if (g8 == 4) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) load8(P.enc + p * P.enc_ld + q * 16 + 8 * k, valid && P.sem_coord, ev[k]);
         }
+        if (g8 == 5) { load8(P.s0 + p * 128 + q * 32, valid, sv[0]); load8(P.s0 + p * 128 + q * 32 + 8, valid, sv[1]); }
+        if (g8 == 6) { load8(P.s0 + p * 128 + q * 32 + 16, valid, sv[2]); load8(P.s0 + p * 128 + q * 32 + 24, valid, sv[3]); }
       }
       // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0)
 #pragma unroll
       for (int g8 = 0; g8 < 2; ++g8) {
         const int e0 = q * 16 + 8 * g8;
-        load8(P.enc + p * P.enc_ld + e0, valid && P.sem_coord, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (e0 + i >= P.enc_dim) v[i] = 0.f;
-          if (e0 + i == 63) v[i] = valid ? 1.f : 0.f;
+          if (e0 + i >= P.enc_dim) ev[g8][i] = 0.f;
+          if (e0 + i == 63) ev[g8][i] = valid ? 1.f : 0.f;
         }
-        put8(sm.b[0], sm.b[1], 256 + e0, v, lane, wd);
+        put8(sm.b[0], sm.b[1], 256 + e0, ev[g8], lane, wd);
       }
       // ---- A2 = s0^T and A = g_s0^T, units q*32..+31
-#pragma unroll 2
+#pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
         const int u0 = q * 32 + 8 * g8;
-        load8(P.s0 + p * 128 + u0, valid, v);
-        put8(sm.a2[0], sm.a2[1], u0, v, lane, wd);
+        put8(sm.a2[0], sm.a2[1], u0, sv[g8], lane, wd);
         float g[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float d = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) d = fmaf(gs[c], sm.w2[c * 128 + u0 + i], d);     // zero rows beyond sem_dim
-          g[i] = v[i] > 0.f ? d : 0.f;
+          g[i] = sv[g8][i] > 0.f ? d : 0.f;
         }
         put8(sm.a[0], sm.a[1], u0, g, lane, wd);
       }
