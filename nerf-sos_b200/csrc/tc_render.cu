@@ -1,7 +1,7 @@
 // Kernel A on the 5th-gen tensor cores: fused hierarchical render for sm_100a.
 //
 // One persistent CTA per SM walks ray PAIRS.  Per pair: coarse tile(s) -> composite + inverse-CDF
-// resampling + sort (warp per ray, in shared memory) -> fine tiles -> composite -> one write of the
+// resampling + sort (4 warps per ray, in shared memory) -> fine tiles -> composite -> one write of the
 // per-ray maps.  A tile is 128 sample points = the 128 TMEM lanes; the whole MLP of a tile runs without
 // leaving the SM:
 //   * activations live in TENSOR MEMORY as the MMA A operand (fp16 hi plane cols 256..383, lo plane cols
@@ -13,10 +13,15 @@
 //     NSOS_MODE_TC_FAST issues the hi.hi product only;
 //   * the positional encoding gamma(x) is written by the row threads straight into a swizzled smem tile
 //     and used as an SMEM A operand (layer 0, the skip layer, the semantic head);
+//   * nine stages per tile for D=8: the trunk, then ONE head stage whose accumulator holds the semantic hidden layer
+//     (cols 0..W/2) and the views hidden layer (cols W/2..W); feature_linear is folded into views_linears.0 at pack
+//     time (see build_prog);
 //   * the N<=3 heads (sigma, rgb, semantic logits) and the per-ray view-direction half of views_linears
 //     are evaluated in fp32 on CUDA cores inside the epilogues, directly on the TMEM read-out.
-// Warp roles: warps 0-3 = row workers (setup, epilogues, compositing), warp 4 = MMA issuer (one lane),
-// warp 5 = bulk-copy producer (one lane).
+// Warp roles: warps 0-7 = row workers (setup, epilogues, compositing; warp w owns TMEM lane quarter w%4 and column
+// half w/4), warp 8 = MMA issuer (one elected lane), warps 9-10 = bulk-copy producers (one elected lane each).
+// What bounds it (DESIGN.md sections 3 and 6): the MMA phases run at the tensor pipe's floor (129 cycles per
+// M128 x N256 x K16), the epilogues at the TMEM read port's (64 B/clk: 2048 cycles per 256-column accumulator).
 //
 // Reference semantics: models/nerf_net.py:71-130 and the modules it calls (see include/nerfsos.h).
 #include <algorithm>
@@ -460,11 +465,7 @@ __device__ __forceinline__ void encode_half(const float x[3], int L, int enc, bo
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         float s, c;
-#ifdef NSOS_AB_OLDSINCOS
-        sincosf(__fmul_rn(x[a], f), &s, &c);
-#else
         sincos_cw(__fmul_rn(x[a], f), &s, &c);
-#endif
         const int cs = 3 + 6 * k + a, cc = cs + 3;
         if (cs >= lo && cs < hi) e[cs - lo] = s;
         if (cc >= lo && cc < hi) e[cc - lo] = c;
@@ -581,19 +582,6 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float
   float he[4] = {0.f, 0.f, 0.f, 0.f}, ho[4] = {0.f, 0.f, 0.f, 0.f};
   tmem_ldc(tm_lane + kColD + cb * kCW, va);
   tmem_wait_ldc(va);
-#ifdef NSOS_AB_ONEBODY
-  // one copy of the chunk body (instruction-cache footprint): the prefetched chunk is moved into va with register copies
-#pragma unroll 1
-  for (int c = cb; c < ce; ++c) {
-    if (c + 1 < ce) tmem_ldc(tm_lane + kColD + (c + 1) * kCW, vb);
-    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, he, ho, gout);
-    if (c + 1 < ce) {
-      tmem_wait_ldc(vb);
-#pragma unroll
-      for (int k = 0; k < kCW; ++k) va[k] = vb[k];
-    }
-  }
-#else
   for (int c = cb; c < ce; c += 2) {
     if (c + 1 < ce) tmem_ldc(tm_lane + kColD + (c + 1) * kCW, vb);
     epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, he, ho, gout);
@@ -604,7 +592,6 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float
       if (c + 2 < ce) tmem_wait_ldc(va);
     }
   }
-#endif
   if (KIND == EPI_HIDDEN_SIGMA) hout[0] += he[0] + ho[0];
   if (KIND == EPI_RGB) { hout[0] += he[0] + ho[0]; hout[1] += he[1] + ho[1]; hout[2] += he[2] + ho[2]; }
   if (KIND == EPI_SEM) { hout[0] += he[0] + ho[0]; if (sem_dim > 1) hout[1] += he[1] + ho[1]; }
@@ -859,11 +846,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           // ---- emit the raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
           float* graw = (pass == 0 && P.fine) ? P.out.raw0 : P.out.raw;
           float* gr_row = (graw && rp[9] > 0.f) ? graw + ((size_t)ray * S + i) * P.C : nullptr;
-#ifdef NSOS_AB_OLDTAIL
-          if (false) {
-#else
           if (pg.st[pg.nst - 1].epi == EPI_SEM_RGB) {
-#endif
             // merged head stage: worker half 1 owns the rgb sums, half 0 the semantic sums; the sigma share of half 1 was
             // exchanged after the last trunk layer (at least one named barrier ago), so no barrier is needed here and the
             // next tile's setup starts at once
