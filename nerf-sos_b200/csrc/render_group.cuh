@@ -36,7 +36,8 @@ __device__ __forceinline__ double group_sum(double v, int tid, int bar_id, doubl
 
 // VolumetricRenderer.forward for one ray with 128 threads; thread t owns samples [t*ns, t*ns+ns), ns = ceil(S/128) <= 2.
 // maps_out may be nullptr (padding ray of an odd batch): the maps are then not written.
-__device__ inline void group_composite(const RayPass& p, int tid, int bar_id, const GroupScratch& gs, float* maps_out, float* weights_out) {
+__device__ inline void group_composite(const RayPass& p, int tid, int bar_id, const GroupScratch& gs, float* maps_out, float* weights_out,
+                                       long long* dbg = nullptr) {   // dbg: optional clock64 stamps (thread 0 of the CTA)
   const int ns = (p.S + kGroup - 1) / kGroup;
   const int i0 = tid * ns;
   const int lane = tid & 31, w = tid >> 5;
@@ -55,6 +56,7 @@ __device__ inline void group_composite(const RayPass& p, int tid, int bar_id, co
       prod = __fmul_rn(prod, __fadd_rn(__fsub_rn(1.f, al), 1e-10f));         // :57
     }
   }
+  if (dbg) dbg[0] = clock64();                      // alpha computed
   // exclusive multiplicative scan over the 128 threads
   float incl = prod;
 #pragma unroll
@@ -68,6 +70,7 @@ __device__ inline void group_composite(const RayPass& p, int tid, int bar_id, co
   group_bar(bar_id);
   for (int k = 0; k < w; ++k) T = __fmul_rn(gs.f[k], T);
   group_bar(bar_id);
+  if (dbg) dbg[1] = clock64();                      // transmittance scan done
   float acc[9];   // rgb0 rgb1 rgb2 depth acc sem0..3
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = 0.f;
@@ -89,24 +92,35 @@ __device__ inline void group_composite(const RayPass& p, int tid, int bar_id, co
       T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, a[j]), 1e-10f));
     }
   }
+  if (dbg) dbg[2] = clock64();                      // per-sample products done
+  // nine independent butterfly reductions, interleaved (channels >= 5 + sem_dim are zero)
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    if (k < 5 + p.sem_dim) {
-      float v = warp_sum(acc[k]);
-      if (lane == 0) gs.f[8 + w * 9 + k] = v;
-    }
+  for (int o = 16; o; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if (lane < 9) {
+    float v = acc[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) v = (lane == k) ? acc[k] : v;
+    gs.f[8 + w * 9 + lane] = v;
   }
   group_bar(bar_id);
-  if (tid == 0 && maps_out) {
-    float s[9];
-    for (int k = 0; k < 5 + p.sem_dim; ++k) s[k] = gs.f[8 + k] + gs.f[8 + 9 + k] + gs.f[8 + 18 + k] + gs.f[8 + 27 + k];
-    float dep = s[3], ac = s[4];
-    if (ac <= 1e-10f) dep = 1e10f;                                            // :72
-    float disp = 1.f / fmaxf(1e-10f, dep / ac);                               // :74
-    float bg = p.white_bkgd ? (1.f - ac) : 0.f;                               // :77-81
-    maps_out[0] = s[0] + bg; maps_out[1] = s[1] + bg; maps_out[2] = s[2] + bg;
-    maps_out[3] = disp; maps_out[4] = ac; maps_out[5] = dep;
-    for (int c = 0; c < p.sem_dim; ++c) maps_out[6 + c] = s[5 + c] + bg;
+  if (dbg) dbg[3] = clock64();                      // warp sums done
+  // threads 0..8 each finish one channel (4 warp partials) and write one map entry; depth and acc also feed disp
+  if (tid < 9 && maps_out) {
+    const float* f = gs.f + 8;
+    const float mine = f[tid] + f[9 + tid] + f[18 + tid] + f[27 + tid];
+    const float ac = f[4] + f[9 + 4] + f[18 + 4] + f[27 + 4];
+    const float bg = p.white_bkgd ? (1.f - ac) : 0.f;                           // renderer.py:77-81
+    if (tid < 3) maps_out[tid] = mine + bg;                                     // rgb
+    else if (tid == 3) {
+      float dep = mine;
+      if (ac <= 1e-10f) dep = 1e10f;                                            // :72
+      maps_out[5] = dep;
+      maps_out[3] = 1.f / fmaxf(1e-10f, dep / ac);                              // :74 disp
+    } else if (tid == 4) maps_out[4] = ac;
+    else if (tid - 5 < p.sem_dim) maps_out[6 + tid - 5] = mine + bg;            // semantic logits (:65-66)
   }
   group_bar(bar_id);
 }
@@ -115,6 +129,7 @@ __device__ inline void group_composite(const RayPass& p, int tid, int bar_id, co
 __device__ inline void group_importance(const ImportanceIO& io, int tid, int bar_id, const GroupScratch& gs) {
   const int M = io.Sc - 1, Mw = io.Sc - 2;
   const int lane = tid & 31, w = tid >> 5;
+  if (io.dbg) io.dbg[0] = clock64();
   if (tid < M) io.bins[tid] = __fmul_rn(0.5f, __fadd_rn(io.z0[tid + 1], io.z0[tid]));   // sampler.py:157
   if (tid < io.Sc) io.zall[tid] = io.z0[tid];
   if (w == 0) {
@@ -142,6 +157,7 @@ __device__ inline void group_importance(const ImportanceIO& io, int tid, int bar
     for (int k = 0; k < 4; ++k) { int i = lane * per + k; if (k < per && i < Mw) io.cdf[i + 1] = (float)(off + loc[k]); }
   }
   group_bar(bar_id);
+  if (io.dbg) io.dbg[1] = clock64();                // cdf done
   double s1 = 0.0;
   for (int j = tid; j < io.K; j += kGroup) {
     float u = io.det ? lin01(j, io.K) : (io.u ? io.u[j] : rng_uniform(io.seed, io.ray, RNG_U, j));   // :98-103
@@ -152,12 +168,14 @@ __device__ inline void group_importance(const ImportanceIO& io, int tid, int bar
     if (io.inds) io.inds[j] = ind;
     s1 += (double)zs;
   }
+  if (io.dbg) io.dbg[2] = clock64();                // inverse cdf done
   // z_std = population std of the K new samples (nerf_net.py:124)
   const double mean = group_sum(s1, tid, bar_id, gs.d) / (double)io.K;      // (also publishes zall)
   double s2 = 0.0;
   for (int j = tid; j < io.K; j += kGroup) { double d = (double)io.zall[io.Sc + j] - mean; s2 += d * d; }
   s2 = group_sum(s2, tid, bar_id, gs.d);
   if (tid == 0 && io.z_std) *io.z_std = (float)sqrt(s2 / (double)io.K);
+  if (io.dbg) io.dbg[3] = clock64();                // z_std done
   // sort(cat([z, z_samples])) (:161) by stable rank.
   const int n = io.Sc + io.K;
   if (io.det) {

@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           float* wsm = sm.w0 + gr * P.Sc;     // coarse weights stay in smem for the resampling
           float* gw = coarse_of_two ? P.out.weights0 : P.out.weights;
           float* wout = (pass == 0) ? wsm : ((gw && valid) ? gw + ray * S : nullptr);
-          group_composite(rpx, gt, gbar, gsc, maps, wout);      // maps == nullptr: dummy ray, nothing is written
+          group_composite(rpx, gt, gbar, gsc, maps, wout, gdbg ? gdbg + 11 : nullptr);      // maps == nullptr: dummy ray, nothing is written
           if (gdbg) gdbg[9] = clock64();
           if (pass == 0) {
             if (gw && valid) for (int k = gt; k < S; k += kGroup) gw[ray * S + k] = wsm[k];
@@ -919,6 +919,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               io.inds = (P.out.inds && valid) ? P.out.inds + ray * P.K : nullptr;
               io.z_std = valid ? P.out.maps + (size_t)ray * P.ML + 2 * P.C6 : nullptr;
               io.Sc = P.Sc; io.K = P.K; io.det = !(P.perturb > 0.f); io.seed = P.seed; io.ray = ray;
+              io.dbg = (gdbg && pass == 0) ? gdbg + 32 + 24 : nullptr;      // trace slots 56..59 of the last trace tile
               group_importance(io, gt, gbar, gsc);
               if (P.out.z_vals && valid) for (int k = gt; k < P.Sf; k += kGroup) P.out.z_vals[ray * P.Sf + k] = io.zsorted[k];
             }

@@ -43,4 +43,7 @@ print(f"pair setup (2nd pair of CTA 0): rays+dir encoding {g[41]-g[40]}  dir bia
 for ps, name in ((0, "coarse"), (1, "fine")):
     d = g[ps * 16: ps * 16 + 16]
     if d[8] == 0: continue
-    print(f"post-{name} phase (thread 0): composite {d[9]-d[8]}  total {d[10]-d[8]}")
+    print(f"post-{name} phase (thread 0): composite {d[9]-d[8]}  total {d[10]-d[8]};  composite split: alpha {d[11]-d[8]}  scan {d[12]-d[11]}  products {d[13]-d[12]}  sums {d[14]-d[13]}  write {d[9]-d[14]}")
+r = g[56:60]
+if r[0] > 0:
+    print(f"resample split: bins+cdf {r[1]-r[0]}  inverse cdf {r[2]-r[1]}  z_std {r[3]-r[2]}  merge+write {g[10]-r[3]}")
