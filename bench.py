@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 N_RAYS = 4096
 N_SAMPLES, N_IMPORTANCE = 64, 128
 FLOP_PER_RAY = 256 * 1268992            # (64 + 192) points x 2 x 634,496 MAC
+ISSUED_FRAC = 552320 / 634496           # MACs kernel A issues per point / MACs the reference evaluates
 H, W, FOCAL = 756, 1008, 815.0
 NEAR, FAR = 1.2, 12.0
 
@@ -40,6 +41,17 @@ def llff_rays(n, seed):
     rng = np.random.default_rng(seed)
     t = rng.uniform(-0.3, 0.3, 3).astype(np.float32)
     pix = rng.choice(H * W, size=n, replace=False)
+    j, i = (pix // W).astype(np.float32), (pix % W).astype(np.float32)
+    d = np.stack([(i - W / 2) / FOCAL, -(j - H / 2) / FOCAL, -np.ones_like(i)], -1).astype(np.float32)
+    o = np.broadcast_to(t, d.shape).astype(np.float32)
+    return np.stack([o, d], 0)
+
+
+def llff_image_rays(seed):
+    """All H*W rays of one synthetic LLFF view in raster order (BASELINE configs[3]: full-image render)."""
+    rng = np.random.default_rng(seed)
+    t = rng.uniform(-0.3, 0.3, 3).astype(np.float32)
+    pix = np.arange(H * W)
     j, i = (pix // W).astype(np.float32), (pix % W).astype(np.float32)
     d = np.stack([(i - W / 2) / FOCAL, -(j - H / 2) / FOCAL, -np.ones_like(i)], -1).astype(np.float32)
     o = np.broadcast_to(t, d.shape).astype(np.float32)
@@ -237,7 +249,7 @@ def run_train(args):
         line = {
             "metric": "rays/sec fwd+bwd (training step, 64c+128f samples, D=8 W=256)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if image else "weak", "vs_baseline": None,
             "dtype": {"exact": "f16x2-split forward, bf16x2-split weight gradients (fp32 accumulate)", "fast": "f16 forward", "simt": "f32"}[args.mode],
             "data": "synthetic",
             "config": {"workload": "stage-2 training step: 8 patches x 64x64 rays per GPU, (64+128) samples, D=8 W=256 + seg head, "
@@ -250,7 +262,8 @@ def run_train(args):
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": int((rays_host.numel() + gt_host.numel()) * 4),
                     "d2h_bytes_per_step": 4 * 8,
                     "note": "the timed step IS the public train_one_step call with pinned host batches and host reads of the logged scalars"},
-            "gpu_launches": None, "clocks": clk, "final_loss": loss,
+            "gpu_launches": 99 * args.steps,       # own kernels per step, counted in profiles/r01_launches_bench_train_v3_summary.csv
+            "clocks": clk, "final_loss": loss,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -265,9 +278,10 @@ def main():
     ap.add_argument("--mode", default="exact", choices=["exact", "fast", "simt"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="eval", choices=["eval", "train"],
+    ap.add_argument("--workload", default="eval", choices=["eval", "train", "image"],
                     help="eval = BASELINE configs[1] (headline, default); train = one --fix_backbone training step "
-                         "(8 patches of 64x64 rays per GPU, correlation losses, Adam; BASELINE configs[2])")
+                         "(8 patches of 64x64 rays per GPU, correlation losses, Adam; BASELINE configs[2]); image = one "
+                         "1008x756 view, its rays sharded over the GPUs (strong scaling; BASELINE configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -296,9 +310,19 @@ def main():
                   mode=args.mode)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights().items()}, strict=True)
     net = net.to(dev).eval()
-    rays_host = torch.from_numpy(llff_rays(N_RAYS, 100 + rank)).pin_memory()
+    image = args.workload == "image"
+    if image:                                                            # contiguous 1/world slice of the raster-ordered view
+        full = llff_image_rays(100)
+        per = (full.shape[1] + world - 1) // world
+        rays_np = full[:, rank * per:(rank + 1) * per]
+        n_total = full.shape[1]
+    else:
+        rays_np = llff_rays(N_RAYS, 100 + rank)
+        n_total = world * N_RAYS
+    n_local = rays_np.shape[1]
+    rays_host = torch.from_numpy(np.ascontiguousarray(rays_np)).pin_memory()
     rays = rays_host.to(dev)
-    maps_host = torch.empty(N_RAYS, 17, dtype=torch.float32).pin_memory()
+    maps_host = torch.empty(n_local, 17, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)         # > 126 MB L2
 
     def step_resident():
@@ -356,7 +380,7 @@ def main():
     total_ms, e2e_s = tt.tolist()
     if rank == 0:
         ms_step = total_ms / args.steps
-        value = world * N_RAYS * args.steps / (total_ms * 1e-3)
+        value = n_total * args.steps / (total_ms * 1e-3)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -364,7 +388,7 @@ def main():
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-        achieved = N_RAYS * FLOP_PER_RAY / (ms_step * 1e-3) / 1e12        # per GPU, algorithmic FLOPs of the reference
+        achieved = n_local * FLOP_PER_RAY / (ms_step * 1e-3) / 1e12       # per GPU (rank 0's shard), algorithmic FLOPs of the reference
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(args.mode)
@@ -374,25 +398,28 @@ def main():
         line = {
             "metric": "rays/sec (64c+128f samples, D=8 W=256)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if image else "weak", "vs_baseline": None,
             "dtype": {"exact": "f16x2-split (fp32-equivalent, fp32 accumulate)", "fast": "f16 (fp32 accumulate)", "simt": "f32"}[args.mode],
             "data": "synthetic",
-            "config": {"workload": "flower_full 4096 rays x (64+128) samples, D=8 W=256 + seg head, eval forward (BASELINE configs[1])",
-                       "rays_per_gpu": N_RAYS, "mode": args.mode, "weights": "shipped flower stage-2 checkpoint (fixture)",
+            "config": {"workload": ("synthetic LLFF 1008x756 full-image render (762048 rays sharded over the GPUs), (64+128) samples, D=8 W=256 "
+                                    "+ seg head, eval forward (BASELINE configs[3])") if image else
+                                   "flower_full 4096 rays x (64+128) samples, D=8 W=256 + seg head, eval forward (BASELINE configs[1])",
+                       "rays_per_gpu": n_local, "mode": args.mode, "weights": "shipped flower stage-2 checkpoint (fixture)",
                        "l2": "256 MB buffer written between timed steps (L2 flush, untimed)", "parallelism": f"ray-sharded x{world}"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "note": f"algorithmic FLOPs (324.86 MFLOP/ray as the reference evaluates them); mode '{args.mode}' issues "
-                                 f"{passes} fp16 MMA pass(es) per product, so tensor-pipe work is {passes}x: "
-                                 f"{achieved * passes:.1f} TFLOP/s issued = {achieved * passes / peak:.3f} of peak"},
-            "e2e": {"value": world * N_RAYS * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": int(rays_host.numel() * 4),
+                                 f"{passes} fp16 MMA pass(es) over 552,320 of the reference's 634,496 MACs per point (feature_linear is "
+                                 f"folded into views_linears.0 at pack time): {achieved * passes * ISSUED_FRAC:.1f} TFLOP/s issued = "
+                                 f"{achieved * passes * ISSUED_FRAC / peak:.3f} of peak"},
+            "e2e": {"value": n_total * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": int(rays_host.numel() * 4),
                     "d2h_bytes_per_step": int(maps_host.numel() * 4)},
             "gpu_launches": args.steps * 1,
             "clocks": clk,
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores = cpu_port_rate(N_RAYS, repeats=2)
+            v, cores = cpu_port_rate(N_RAYS, repeats=2)                  # bounded sample: the 4096-ray batch
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": "the same 4096-ray batch, best of 2, PyTorch-CPU port of the reference path (oracle/torch_port.py)"}
         print(json.dumps(line))
