@@ -26,6 +26,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]             # stdout carries exactly one JSON line (NCCL prints its version banner there when set)
 
 N_RAYS = 4096
 N_SAMPLES, N_IMPORTANCE = 64, 128
@@ -249,7 +251,7 @@ def run_train(args):
         line = {
             "metric": "rays/sec fwd+bwd (training step, 64c+128f samples, D=8 W=256)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if image else "weak", "vs_baseline": None,
+            "scaling": "weak", "vs_baseline": None,
             "dtype": {"exact": "f16x2-split forward, bf16x2-split weight gradients (fp32 accumulate)", "fast": "f16 forward", "simt": "f32"}[args.mode],
             "data": "synthetic",
             "config": {"workload": "stage-2 training step: 8 patches x 64x64 rays per GPU, (64+128) samples, D=8 W=256 + seg head, "
