@@ -1119,7 +1119,9 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
   while (csize > 1 && n_pairs < csize) csize >>= 1;
   long long g = std::min<long long>((n_pairs + csize - 1) / csize * csize, (long long)(sms / csize) * csize);
   const int grid = (int)g;
-  if (!replay) NSOS_CHECK_CUDA(cudaMemsetAsync(out.maps, 0, sizeof(float) * n_rays * P.ML, st));
+  // with a fine pass every entry of a ray's row is written by the kernel (fine block, coarse block, z_std); coarse-only
+  // renders leave the second block and z_std untouched, so the row is cleared first
+  if (!replay && !fine) NSOS_CHECK_CUDA(cudaMemsetAsync(out.maps, 0, sizeof(float) * n_rays * P.ML, st));
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = need; lc.stream = st;
   cudaLaunchAttribute attr[1];

@@ -193,6 +193,16 @@ class NeRFNet(nn.Module):
         self._ws = None
 
     # ---- helpers -----------------------------------------------------------------------------------
+    def _const_bound(self, value, like):
+        key = (value, like.shape[0], like.device)
+        cache = self.__dict__.setdefault("_bound_cache", {})
+        t = cache.get(key)
+        if t is None:
+            if len(cache) >= 8:
+                cache.clear()
+            t = cache[key] = torch.full((like.shape[0], 1), value, dtype=torch.float32, device=like.device)
+        return t
+
     def _workspace(self, nbytes, device):
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
             self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
@@ -281,10 +291,10 @@ class NeRFNet(nn.Module):
         rays_o = torch.reshape(rays_o, [-1, rays_o.shape[-1]]).float()
         rays_d = torch.reshape(rays_d, [-1, rays_d.shape[-1]]).float()
         near, far = bound_batch
-        if isinstance(near, (int, float)):
-            near = near * torch.ones_like(rays_d[..., :1], dtype=torch.float)
+        if isinstance(near, (int, float)):                                   # :167-170; the [N,1] constants are cached: two fills
+            near = self._const_bound(float(near), rays_d)                    # and two multiplies per call otherwise
         if isinstance(far, (int, float)):
-            far = far * torch.ones_like(rays_d[..., :1], dtype=torch.float)
+            far = self._const_bound(float(far), rays_d)
         if rays_o.shape[0] == 0:
             raise ValueError("empty ray batch")                              # the reference fails in torch.cat here too
         # one fused launch instead of the serial ray_chunk loop (:177-188)
