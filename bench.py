@@ -420,6 +420,18 @@ def main():
             "clocks": clk,
             "wall_s_timed_region": t_wall,
         }
+        # parity beside the speed (BASELINE metric: "rays/sec ...; PSNR vs ref"): the same net and mode on the 256 rays whose
+        # outputs the unmodified reference produced (tests/golden/flower_eval_256.npz, generated by oracle/make_golden.py)
+        try:
+            gz = np.load(os.path.join(ROOT, "tests", "golden", "flower_eval_256.npz"))
+            with torch.no_grad():
+                got = net(torch.from_numpy(gz["rays"]).to(dev), (NEAR, FAR))["rgb"].float().cpu().numpy()
+            ref = gz["out/rgb"]
+            mse = float(((got - ref) ** 2).mean())
+            line["parity"] = {"psnr_db_vs_reference": float(-10.0 * np.log10(max(mse, 1e-20))), "max_abs_rgb_err": float(np.abs(got - ref).max()),
+                              "rays": int(ref.shape[0]), "source": "tests/golden/flower_eval_256.npz (reference-generated fixture)"}
+        except Exception as e:                                           # never lose the timing line over the side check
+            line["parity"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             v, cores = cpu_port_rate(N_RAYS, repeats=2)                  # bounded sample: the 4096-ray batch
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
