@@ -136,3 +136,30 @@ def test_torch_port_matches_reference(flower_sd):
     out = TP.render_eval(sd, rays[0], rays[1], 1.2, 12.0)
     for k in ("rgb", "rgb0", "acc", "semantics", "semantics0", "depth", "weights0", "z_std"):
         close(out[k].numpy(), g["out"][k][:96], rtol=1e-5, atol=2e-5)
+
+
+def test_feature_views_fusion_is_exact_to_fp32_rounding(flower_sd):
+    """Kernel A folds feature_linear into views_linears.0 at pack time (csrc/tc_render.cu: build_prog / k_fuse_views):
+    (W_v[:, :W] W_f) h + (W_v[:, :W] b_f + b_v) + W_v[:, W:] enc_dirs.  On the shipped fine net and realistic trunk
+    activations the fused pre-activation equals the reference order (nerf_mlp.py:86-89, oracle) to fp32 rounding noise."""
+    sd = {k: np.asarray(v) for k, v in flower_sd.items()}
+    pre = "nerf_fine.mlp."
+    Wf, bf = sd[pre + "feature_linear.weight"], sd[pre + "feature_linear.bias"]
+    Wv, bv = sd[pre + "views_linears.0.weight"], sd[pre + "views_linears.0.bias"]
+    W = Wf.shape[0]
+    rng = np.random.default_rng(0)
+    h = np.maximum(rng.normal(0.3, 1.0, (4096, W)), 0).astype(np.float32)           # post-ReLU trunk output
+    ev = rng.uniform(-1, 1, (4096, Wv.shape[1] - W)).astype(np.float32)              # encoded view directions
+    # reference order in fp32
+    feat = (h @ Wf.T + bf).astype(np.float32)
+    ref = (np.concatenate([feat, ev], -1) @ Wv.T + bv).astype(np.float32)
+    # fused: product matrix in fp64, rounded to fp32 once (what k_fuse_views stores), then fp32 arithmetic
+    Wuf = (Wv[:, :W].astype(np.float64) @ Wf.astype(np.float64)).astype(np.float32)
+    buf = (Wv[:, :W].astype(np.float64) @ bf.astype(np.float64) + bv).astype(np.float32)
+    fused = (h @ Wuf.T + buf + ev @ Wv[:, W:].T).astype(np.float32)
+    exact = (h.astype(np.float64) @ (Wv[:, :W].astype(np.float64) @ Wf.astype(np.float64)).T
+             + Wv[:, :W].astype(np.float64) @ bf.astype(np.float64) + bv + ev.astype(np.float64) @ Wv[:, W:].astype(np.float64).T)
+    scale = np.abs(exact).max()
+    e_ref, e_fused = np.abs(ref - exact).max() / scale, np.abs(fused - exact).max() / scale
+    assert e_fused < 2e-6 and e_fused < 4 * e_ref + 1e-7, (e_ref, e_fused)
+    assert np.abs(fused - ref).max() / scale < 4e-6
