@@ -123,22 +123,30 @@ class NeRFMLP(nn.Module):
 
     # ---- descriptors / buffers -------------------------------------------------------------------
     def desc(self) -> _lib.NetDesc:
-        m = self.mlp
-        return _lib.NetDesc(m.D, m.W, 4 if m.skips else -1, self.multires, self.multires_views, int(m.use_viewdirs),
-                            int(m.use_semantics), m.sem_dim if m.use_semantics else 0, int(m.sem_with_coord))
+        d = self.__dict__.get("_desc")
+        if d is None:                                    # the geometry is fixed at construction: build the struct once
+            m = self.mlp
+            d = self.__dict__["_desc"] = _lib.NetDesc(m.D, m.W, 4 if m.skips else -1, self.multires, self.multires_views,
+                                                      int(m.use_viewdirs), int(m.use_semantics),
+                                                      m.sem_dim if m.use_semantics else 0, int(m.sem_with_coord))
+        return d
 
     def flat_params(self) -> torch.Tensor:
         flat = self._flat.ensure()
-        n = _lib.lib().nsos_param_count(self.desc())
-        if n != flat.numel():
-            raise _lib.NsosError(f"parameter layout mismatch: library expects {n} floats, module holds {flat.numel()}")
+        if self.__dict__.get("_count_ok") != flat.numel():
+            n = _lib.lib().nsos_param_count(self.desc())
+            if n != flat.numel():
+                raise _lib.NsosError(f"parameter layout mismatch: library expects {n} floats, module holds {flat.numel()}")
+            self.__dict__["_count_ok"] = n
         return flat
 
-    def packed(self, mode: int, force: bool = False):
-        """fp16 hi/lo swizzled weight image for the tcgen05 kernel; re-packed when the parameters changed."""
+    def packed(self, mode: int, force: bool = False, flat: torch.Tensor = None):
+        """fp16 hi/lo swizzled weight image for the tcgen05 kernel; re-packed when the parameters changed.
+        `flat`: the result of a flat_params() call made earlier in the same forward (skips re-validating the views)."""
         if mode == _lib.MODE_SIMT:
             return None
-        flat = self.flat_params()
+        if flat is None:
+            flat = self.flat_params()
         ver = self._flat.version()
         hit = self._packed.get(mode)
         if hit is not None and hit[0] == ver and not force:

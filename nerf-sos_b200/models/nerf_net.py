@@ -94,9 +94,9 @@ class _RenderFn(torch.autograd.Function):
                             *[_lib.ptr(acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")])
         ctx.acts = dict(acts, raw=out.get("raw"), raw0=out.get("raw0")) if acts else None
         rs = _lib.Randoms(*[_lib.ptr(rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
-        flat_c, flat_f = net.nerf.flat_params(), net.nerf_fine.flat_params()
-        pk_c = net.nerf.packed(cfg.mode, force=net.training)
-        pk_f = net.nerf_fine.packed(cfg.mode, force=net.training) if fine else pk_c
+        flat_c, flat_f = want.get("flat") or (net.nerf.flat_params(), net.nerf_fine.flat_params())
+        pk_c = net.nerf.packed(cfg.mode, force=net.training, flat=flat_c)
+        pk_f = net.nerf_fine.packed(cfg.mode, force=net.training, flat=flat_f) if fine else pk_c
         wsz = L.nsos_render_workspace_bytes(cfg, N)
         ws = net._workspace(wsz, dev)
         _lib.check(L.nsos_render_fwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
@@ -245,8 +245,7 @@ class NeRFNet(nn.Module):
         fine = n_importance > 0
         pc = list(self.nerf._flat.params)
         pf = list(self.nerf_fine._flat.params) if fine else []
-        self.nerf.flat_params()
-        self.nerf_fine.flat_params()
+        want["flat"] = (self.nerf.flat_params(), self.nerf_fine.flat_params())    # validated once per call, reused below
         tensors = _RenderFn.apply(self, cfg, rays_o, rays_d, near, far, rnd, seed, want, len(pc), *(pc + pf))
         out = dict(zip(want["names"], tensors))
         maps = out.pop("maps")
