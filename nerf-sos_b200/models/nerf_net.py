@@ -52,7 +52,8 @@ class _RenderFn(torch.autograd.Function):
     coarse net then the fine net (flat-buffer order) so autograd routes gradients to the nn.Parameters."""
 
     @staticmethod
-    def forward(ctx, net, cfg, rays_o, rays_d, near, far, rnd, seed, want, n_coarse_params, *params):
+    def launch(net, cfg, rays_o, rays_d, near, far, rnd, seed, want, params):
+        """Allocate the outputs and launch kernel A; returns (out dict, saved activations or {})."""
         L = _lib.lib()
         dev = rays_o.device
         N = rays_o.shape[0]
@@ -81,7 +82,7 @@ class _RenderFn(torch.autograd.Function):
             out["raw"] = torch.empty(N, S_last, Cr, **f32)
             if fine:
                 out["raw0"] = torch.empty(N, Sc, Cr, **f32)
-        need_z = want["z"] or any(p.requires_grad for p in params)
+        need_z = want["z"] or (want.get("grad", False) and any(p.requires_grad for p in params))   # the backward needs the depths
         if need_z:
             out["z_vals"] = torch.empty(N, S_last, **f32)
             if fine:
@@ -92,7 +93,6 @@ class _RenderFn(torch.autograd.Function):
         ro = _lib.RenderOut(*[_lib.ptr(out.get(k)) for k in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
                                                              "z_samples", "inds")],
                             *[_lib.ptr(acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")])
-        ctx.acts = dict(acts, raw=out.get("raw"), raw0=out.get("raw0")) if acts else None
         rs = _lib.Randoms(*[_lib.ptr(rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
         flat_c, flat_f = want.get("flat") or (net.nerf.flat_params(), net.nerf_fine.flat_params())
         pk_c = net.nerf.packed(cfg.mode, force=net.training, flat=flat_c)
@@ -102,6 +102,12 @@ class _RenderFn(torch.autograd.Function):
         _lib.check(L.nsos_render_fwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
                                      _lib.ptr(rays_d), _lib.ptr(near), _lib.ptr(far), C.byref(rs), seed, C.byref(ro), _lib.ptr(ws),
                                      ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_fwd")
+        return out, acts
+
+    @staticmethod
+    def forward(ctx, net, cfg, rays_o, rays_d, near, far, rnd, seed, want, n_coarse_params, *params):
+        out, acts = _RenderFn.launch(net, cfg, rays_o, rays_d, near, far, rnd, seed, want, params)
+        ctx.acts = dict(acts, raw=out.get("raw"), raw0=out.get("raw0")) if acts else None
         ctx.net, ctx.cfg, ctx.rnd, ctx.seed, ctx.n_coarse = net, cfg, rnd, seed, n_coarse_params
         ctx.shapes = [p.shape for p in params]
         ctx.req = [p.requires_grad for p in params]
@@ -246,8 +252,11 @@ class NeRFNet(nn.Module):
         pc = list(self.nerf._flat.params)
         pf = list(self.nerf_fine._flat.params) if fine else []
         want["flat"] = (self.nerf.flat_params(), self.nerf_fine.flat_params())    # validated once per call, reused below
-        tensors = _RenderFn.apply(self, cfg, rays_o, rays_d, near, far, rnd, seed, want, len(pc), *(pc + pf))
-        out = dict(zip(want["names"], tensors))
+        if want["grad"] and any(p.requires_grad for p in pc + pf):
+            tensors = _RenderFn.apply(self, cfg, rays_o, rays_d, near, far, rnd, seed, want, len(pc), *(pc + pf))
+            out = dict(zip(want["names"], tensors))
+        else:                                            # nothing to differentiate: skip the autograd node
+            out, _ = _RenderFn.launch(self, cfg, rays_o, rays_d, near, far, rnd, seed, want, pc + pf)
         maps = out.pop("maps")
         sem = self.nerf.mlp.sem_dim if self.nerf.mlp.use_semantics else 0
         C6 = 6 + sem
