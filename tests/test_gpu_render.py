@@ -275,7 +275,7 @@ def test_edge_shapes_and_bounds(mode):
 
 
 @pytest.mark.parametrize("mode", ["simt", "exact"])
-@pytest.mark.parametrize("variant", ["white_bkgd", "no_coord", "no_sem", "imp64", "sem4"])
+@pytest.mark.parametrize("variant", ["white_bkgd", "no_coord", "no_sem", "imp64", "sem4", "sc128"])
 def test_config_variants_vs_oracle(mode, variant):
     """Seeded random-init nets in configurations the shipped checkpoints do not cover."""
     from oracle import nerf_oracle as O
@@ -291,6 +291,9 @@ def test_config_variants_vs_oracle(mode, variant):
         kw["use_semantics"] = False; okw["use_semantics"] = False
     elif variant == "imp64":
         kw["N_importance"] = 64; okw["n_importance"] = 64
+    elif variant == "sc128":                                         # largest supported sampling: 128 coarse (two coarse tiles per ray
+        kw["N_samples"] = 128; kw["N_importance"] = 128                 # pair) + 128 importance = 256 fine samples (four fine tiles)
+        okw["n_samples"] = 128; okw["n_importance"] = 128
     elif variant == "sem4":                                          # wide semantic head (own epilogue kind on the tcgen05 path)
         kw["sem_dim"] = 4
     torch.manual_seed(5)
