@@ -142,3 +142,45 @@ def test_sincos_cw_constants_accuracy():
         assert np.abs(S - ts).max() < 8e-8 and np.abs(C - tc).max() < 8e-8, k
         big = np.abs(ts) > 0.1
         assert (np.abs(S - ts)[big] / np.spacing(np.abs(ts[big]).astype(f32))).max() < 1.6, k
+
+
+def test_bench_has_no_undefined_names():
+    """bench.py's GPU branches cannot run here; at least every name they load must be bound somewhere in the function,
+    the module or builtins (a copy-paste slip in the train line once only showed up on the 8-GPU box)."""
+    import ast
+    import builtins
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    module_names = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
+    module_names |= {n.name for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
+    for n in ast.walk(tree):
+        if isinstance(n, (ast.Import, ast.ImportFrom)):
+            module_names |= {(a.asname or a.name).split(".")[0] for a in n.names}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        bound = {a.arg for a in fn.args.args + fn.args.kwonlyargs} | module_names
+        for n in ast.walk(fn):
+            if isinstance(n, ast.ExceptHandler) and n.name:
+                bound.add(n.name)
+            if isinstance(n, (ast.Lambda, ast.FunctionDef)):
+                bound |= {a.arg for a in n.args.args}
+            if isinstance(n, ast.comprehension):
+                bound |= {t.id for t in ast.walk(n.target) if isinstance(t, ast.Name)}
+        loads = {n.id for n in ast.walk(fn) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+        missing = sorted(x for x in loads if x not in bound and not hasattr(builtins, x))
+        assert not missing, (fn.name, missing)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) runs without a GPU and prints exactly one JSON line
+    with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "rays/s" and j["value"] > 0 and j["higher_is_better"] is True
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["e2e"]["h2d_bytes_per_step"] == 0
+    assert {"metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"} <= set(j)
