@@ -43,3 +43,40 @@ def test_oracle_matches_reference_on_fresh_rays(flower_sd):
         np.testing.assert_allclose(mine[k], ref[k].numpy(), rtol=1e-4, atol=1e-5, err_msg=k)
     same = np.abs(mine["rgb"] - ref["rgb"].numpy()).max(-1) < 1e-4               # fine pass: identical unless an index flipped
     assert same.mean() >= 0.9
+
+
+class _LossArgs:      # what CorrelationLoss / GeoCorrelationLoss read from args (image.py:276-283, 385-393)
+    rand_neg = False; self_corr_w = 1.0; use_sim_matrix = True; patch_stride = 6
+    app_corr_params = [0.25, 0.8, 0.4, 1.3]; geo_corr_params = [0.25, 1, 1, 1]      # CO3D values / off-fixture weights
+
+
+def test_oracle_losses_match_reference_on_fresh_inputs():
+    """Other batch size, patch size and loss parameters than the losses_b4_p16 fixture."""
+    from utils import image as ref_image
+    g = torch.Generator().manual_seed(77)
+    B, Pp = 3, 8
+    feat = torch.randn(B, 384, 14, 14, generator=g)
+    cls_ = torch.randn(B, 384, generator=g)
+    sim = ref_image.get_similarity_matrix(cls_)
+    code = torch.randn(B, 2, Pp, Pp, generator=g)
+    rand = []
+    _rand = torch.rand
+
+    def rec(*a, **k):
+        r = _rand(*a, **k); rand.append(r.clone()); return r
+    torch.rand = rec
+    try:
+        la = float(ref_image.CorrelationLoss(_LossArgs())(feat, code, sim))
+    finally:
+        torch.rand = _rand
+    c1, c2 = rand[0].numpy() * 2 - 1, rand[1].numpy() * 2 - 1
+    mine = O.correlation_loss(feat.numpy(), code.numpy(), sim.numpy(), c1, c2, tuple(_LossArgs.app_corr_params))
+    assert abs(mine - la) <= 1e-5 * max(1.0, abs(la)), (mine, la)
+
+    ray_o = torch.rand(B, 3, Pp, Pp, generator=g) * 0.2
+    ray_d = torch.cat([torch.rand(B, 2, Pp, Pp, generator=g) - 0.5, -torch.ones(B, 1, Pp, Pp)], 1)
+    depth = torch.rand(B, 1, Pp, Pp, generator=g) * 17.0 + 1.0                      # some beyond max_depth = 15
+    lg = float(ref_image.GeoCorrelationLoss(_LossArgs())(depth.clone(), code, [ray_o, ray_d, None], sim))
+    mine_g, _ = O.geo_correlation_loss(depth.numpy(), code.numpy(), ray_o.numpy(), ray_d.numpy(), sim.numpy(),
+                                       tuple(_LossArgs.geo_corr_params))
+    assert abs(mine_g - lg) <= 1e-4 * max(1.0, abs(lg)), (mine_g, lg)
