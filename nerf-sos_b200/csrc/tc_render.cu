@@ -297,7 +297,7 @@ struct Smem {
   uint64_t *full, *empty, *acc_full, *a_ready;
   uint32_t* tmem_ptr;
 };
-constexpr int kRayP = 16;  // per ray: o[3] d[3] near far dnorm valid
+constexpr int kRayP = 16;  // per ray: o[3] d[3] near far |d| valid v[3] = d/|d| (+3 pad)
 
 __host__ __device__ inline size_t carve_smem(uint8_t* base, int nslots, int Sc, int Sf, int C, Smem* s) {
   size_t off = 0;
