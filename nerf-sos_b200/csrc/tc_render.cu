@@ -283,7 +283,6 @@ struct TcParams {
   int Sc, K, Sf;
   float perturb, noise_std;
   int white_bkgd, exact, fine, C, sem_dim, C6, ML, nslots;
-  float hwc[2][kHeadFloats];   // EXPERIMENT: head weights in the constant bank (uniform operands)
   long long* trace;   // optional timeline buffer (NSOS_TRACE=1): clock64 stamps of CTA 0, see tools/trace_report.py
   // replay (backward recompute on given samples): sample depths in, last trunk activation / semantic hidden layer out
   const float* z_in[2];
@@ -770,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
       for (int pass = 0; pass < npass; ++pass) {
         const TcProg& pg = P.prog[pass];
         const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[pass]);
-        const float* hw = P.hwc[pass];        // EXPERIMENT: constant bank instead of sm.heads + pass * kHeadFloats
+        const float* hw = sm.heads + pass * kHeadFloats;
         const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
 #pragma unroll 1
         for (int tile = 0; tile < ntiles; ++tile) {
