@@ -99,6 +99,10 @@ typedef struct NsosRenderOut {
   float* s_hid0;     /* [N, Sc, W/2]                 */
   float* h_last;     /* [N, Sc+K, W]                 */
   float* s_hid;      /* [N, Sc+K, W/2]               */
+  /* Optional sticky status word (caller zero-initialises, reads and clears it; never reset by the library).
+   * bit 0: NSOS_MODE_TC_EXACT/FAST only -- a hidden activation exceeded the fp16 range of the activation planes
+   *        (|a| > 4094): the affected maps are non-finite.  Re-render those nets with NSOS_MODE_SIMT_FP32. */
+  uint32_t* status;
 } NsosRenderOut;
 
 /* ---- introspection ------------------------------------------------------------------------- */

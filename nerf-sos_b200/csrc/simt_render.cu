@@ -357,6 +357,8 @@ int simt_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
   if (fine) NSOS_REQUIRE(make_geom(cfg.fine, gf), NSOS_ERR_UNSUPPORTED, "invalid fine net descriptor"); else gf = gc;
   const int Sc = cfg.n_samples, K = cfg.n_importance, Sf = Sc + K;
   NSOS_REQUIRE(Sc >= 2 && Sc <= kMaxS && Sf <= kMaxS, NSOS_ERR_UNSUPPORTED, "n_samples/n_importance out of range (<=%d total)", kMaxS);
+  NSOS_REQUIRE(gc.enc <= kEncLd && gc.encv <= kEncVLd && gf.enc <= kEncLd && gf.encv <= kEncVLd, NSOS_ERR_UNSUPPORTED,
+               "positional encodings wider than %d / %d columns are not implemented (multires <= 10, multires_views <= 4)", kEncLd, kEncVLd);
   NSOS_REQUIRE(!fine || gc.C == gf.C, NSOS_ERR_UNSUPPORTED, "coarse and fine nets must have the same output channels");
   const int64_t R = fwd_chunk_rays(n_rays);
   FwdWs w;
@@ -482,6 +484,8 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
   if (fine) NSOS_REQUIRE(make_geom(cfg.fine, gf), NSOS_ERR_UNSUPPORTED, "invalid fine net descriptor"); else gf = gc;
   const int Sc = cfg.n_samples, K = cfg.n_importance, Sf = Sc + K;
   NSOS_REQUIRE(Sc >= 2 && Sf <= kMaxS, NSOS_ERR_UNSUPPORTED, "n_samples/n_importance out of range");
+  NSOS_REQUIRE(gc.enc <= kEncLd && gc.encv <= kEncVLd && gf.enc <= kEncLd && gf.encv <= kEncVLd, NSOS_ERR_UNSUPPORTED,
+               "positional encodings wider than %d / %d columns are not implemented (multires <= 10, multires_views <= 4)", kEncLd, kEncVLd);
   if (!trunk && !gc.use_sem && !gf.use_sem) return NSOS_OK;   // nothing trainable outside the trunk
   if (bwd_uses_tc(cfg, trunk, gc, gf)) {
     // activations saved by the forward call make the trunk replay unnecessary
@@ -601,6 +605,8 @@ size_t simt_mlp_workspace_bytes(const NetGeom& g, int64_t P) {
 
 int simt_mlp_query(const NetGeom& g, const float* prm, const float* pts, const float* viewdirs, float* raw, void* workspace,
                    size_t workspace_bytes, int64_t P, cudaStream_t st) {
+  NSOS_REQUIRE(g.enc <= kEncLd && g.encv <= kEncVLd, NSOS_ERR_UNSUPPORTED,
+               "positional encodings wider than %d / %d columns are not implemented (multires <= 10, multires_views <= 4)", kEncLd, kEncVLd);
   NSOS_REQUIRE(workspace_bytes >= simt_mlp_workspace_bytes(g, P), NSOS_ERR_WORKSPACE, "workspace too small");
   Carver c{(char*)workspace, 0, 0};
   float* enc = c.take<float>(P * kEncLd); float* encv = c.take<float>(P * kEncVLd);

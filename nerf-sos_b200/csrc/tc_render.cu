@@ -487,7 +487,7 @@ constexpr int kSW = 16;   // arithmetic sub-block of a chunk
 template <int KIND, bool EXACT, bool DUMP>
 __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
                                         const float* __restrict__ hw, int sem_dim, float (&hacc)[4], float (&hodd)[4],
-                                        float* __restrict__ gout) {
+                                        float* __restrict__ gout, float& vmax) {
   uint32_t hi[kSW / 2], lo[kSW / 2];
   // bias and head weights of this sub-block as 16-byte shared loads (c0 is a multiple of 16 floats; all bases 16 B aligned)
   float bz[kSW], h0[kSW], h1[kSW], h2[kSW];
@@ -544,6 +544,7 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
       else { dq0 = x0 * (1.f / kActScale); dq1 = x1 * (1.f / kActScale); }
     }
     if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA) {
+      vmax = fmaxf(vmax, fmaxf(x0, x1));          // range guard: 16*a must stay below the fp16 maximum (checked once per tile)
       __half2 hh = __floats2half2_rn(x0, x1);
       hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
       if (EXACT) {
@@ -562,10 +563,10 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
 template <int KIND, bool EXACT, bool DUMP>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
                                           const float* __restrict__ hw, int sem_dim, float (&hacc)[4], float (&hodd)[4],
-                                          float* __restrict__ gout) {
+                                          float* __restrict__ gout, float& vmax) {
 #pragma unroll
   for (int sb = 0; sb < kCW / kSW; ++sb)
-    epi_sub<KIND, EXACT, DUMP>(&v[kSW * sb], tm_lane, c0 + kSW * sb, inv16, bias, hw, sem_dim, hacc, hodd, gout);
+    epi_sub<KIND, EXACT, DUMP>(&v[kSW * sb], tm_lane, c0 + kSW * sb, inv16, bias, hw, sem_dim, hacc, hodd, gout, vmax);
 }
 __device__ __forceinline__ void tmem_ldc(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 __device__ __forceinline__ void tmem_ldc(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
@@ -574,7 +575,7 @@ __device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[32]) { tmem_wait_ld_
 
 template <int KIND, bool EXACT, bool DUMP>
 __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw, int sem_dim,
-                                         float* hacc, float* gout) {
+                                         float* hacc, float* gout, float& vmax) {
   // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
   uint32_t va[kCW], vb[kCW];
   if (cb >= ce) return;
@@ -584,11 +585,11 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float
   tmem_wait_ldc(va);
   for (int c = cb; c < ce; c += 2) {
     if (c + 1 < ce) tmem_ldc(tm_lane + kColD + (c + 1) * kCW, vb);
-    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, he, ho, gout);
+    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, he, ho, gout, vmax);
     if (c + 1 < ce) {
       tmem_wait_ldc(vb);
       if (c + 2 < ce) tmem_ldc(tm_lane + kColD + (c + 2) * kCW, va);
-      epi_chunk<KIND, EXACT, DUMP>(vb, tm_lane, (c + 1) * kCW, inv16, bias, hw, sem_dim, he, ho, gout);
+      epi_chunk<KIND, EXACT, DUMP>(vb, tm_lane, (c + 1) * kCW, inv16, bias, hw, sem_dim, he, ho, gout, vmax);
       if (c + 2 < ce) tmem_wait_ldc(va);
     }
   }
@@ -604,16 +605,16 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float
 // 16-column chunks [cb, ce) of a stage
 template <bool EXACT, bool DUMP = false>
 __device__ __forceinline__ void epilogue(int kind, int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw,
-                                         int sem_dim, float* hacc, float* gout) {
+                                         int sem_dim, float* hacc, float* gout, float& vmax) {
   switch (kind) {
-    case EPI_HIDDEN: epi_kind<EPI_HIDDEN, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    case EPI_HIDDEN_SIGMA: epi_kind<EPI_HIDDEN_SIGMA, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_HIDDEN: epi_kind<EPI_HIDDEN, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax); break;
+    case EPI_HIDDEN_SIGMA: epi_kind<EPI_HIDDEN_SIGMA, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax); break;
     case EPI_SEM:
-      if (sem_dim <= 2) epi_kind<EPI_SEM, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout);
-      else epi_kind<EPI_SEM_WIDE, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout);
+      if (sem_dim <= 2) epi_kind<EPI_SEM, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax);
+      else epi_kind<EPI_SEM_WIDE, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax);
       break;
-    case EPI_RGB: epi_kind<EPI_RGB, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
-    default: epi_kind<EPI_RAW, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout); break;
+    case EPI_RGB: epi_kind<EPI_RGB, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax); break;
+    default: epi_kind<EPI_RAW, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax); break;
   }
 }
 
@@ -807,6 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           if (tr) tr[15 * kTraceStamps + 1] = clock64();                   // gamma tile written, a_ready signalled
 
           float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0] sigma, [1..3] rgb, [4..7] sem (partial over my columns)
+          float vmax = 0.f;
 #pragma unroll 1
           for (int st = 0; st < pg.nst; ++st) {
             const TcStage& Sg = pg.st[st];
@@ -834,7 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               if (sem_part && P.dump_s0[pass]) gout = P.dump_s0[pass] + pt * pg.H2;
             }
             const int kind = merged ? (hf ? EPI_RGB : EPI_SEM) : Sg.epi;
-            epilogue<EXACT, DUMP>(kind, cb, ce, tm_lane + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout);
+            epilogue<EXACT, DUMP>(kind, cb, ce, tm_lane + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout, vmax);
             if (Sg.epi == EPI_HIDDEN_SIGMA && hf == 1) sm.hpart[row * 8] = hacc[0];   // sigma share of the upper column half
             if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
             if (st + 1 < pg.nst) {
@@ -843,6 +845,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               mbar_arrive(smem_u32(sm.a_ready));
             }
           }
+          // fp16(16*a) saturates at |a| > 4094: inf/NaN then reach the maps; the sticky status bit names the cause
+          if (!(vmax <= 65504.f) && P.out.status && rowvalid && rp[9] > 0.f) atomicOr(P.out.status, 1u);
           // ---- emit the raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
           float* graw = (pass == 0 && P.fine) ? P.out.raw0 : P.out.raw;
           float* gr_row = (graw && rp[9] > 0.f) ? graw + ((size_t)ray * S + i) * P.C : nullptr;
@@ -1003,7 +1007,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
     float dummy[4];
     int cb, ce;
     chunk_range(P.N, hf, cb, ce);
-    epilogue<EXACT>(EPI_RAW, cb, ce, tm_lane, __ldg(&aux->inv_scale[0][0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)row * P.N);
+    float vm = 0.f;
+    epilogue<EXACT>(EPI_RAW, cb, ce, tm_lane, __ldg(&aux->inv_scale[0][0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)row * P.N, vm);
   }
   tc_fence_before();
   __syncthreads();

@@ -158,7 +158,8 @@ class NeRFMLP(nn.Module):
             raise _lib.NsosError("this net geometry is not covered by the tcgen05 path (use mode='simt')")
         buf = hit[1] if hit is not None and hit[1].numel() == nbytes and hit[1].device == flat.device else \
             torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
-        _lib.check(L.nsos_pack_weights(d, _lib.ptr(flat), _lib.ptr(buf), mode, _lib.cur_stream(flat.device)), "nsos_pack_weights")
+        with torch.cuda.device(flat.device):        # the library launches on the calling thread's current device
+            _lib.check(L.nsos_pack_weights(d, _lib.ptr(flat), _lib.ptr(buf), mode, _lib.cur_stream(flat.device)), "nsos_pack_weights")
         self._packed[mode] = (ver, buf)
         return buf
 
@@ -182,7 +183,8 @@ class NeRFMLP(nn.Module):
         ws = torch.empty(L.nsos_mlp_workspace_bytes(d, min(n, step)), dtype=torch.uint8, device=flat.device)
         for i in range(0, n, step):
             m = min(step, n - i)
-            _lib.check(L.nsos_mlp_query(d, _lib.ptr(flat), _lib.ptr(pts[i:i + m]), _lib.ptr(vd[i:i + m]) if vd is not None else None,
-                                        _lib.ptr(out[i:i + m]), _lib.ptr(ws), ws.numel(), m, _lib.cur_stream(flat.device)),
-                       "nsos_mlp_query")
+            with torch.cuda.device(flat.device):
+                _lib.check(L.nsos_mlp_query(d, _lib.ptr(flat), _lib.ptr(pts[i:i + m]), _lib.ptr(vd[i:i + m]) if vd is not None else None,
+                                            _lib.ptr(out[i:i + m]), _lib.ptr(ws), ws.numel(), m, _lib.cur_stream(flat.device)),
+                           "nsos_mlp_query")
         return out.reshape(*sh[:-1], C)

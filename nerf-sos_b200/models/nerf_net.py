@@ -92,16 +92,17 @@ class _RenderFn(torch.autograd.Function):
             out["inds"] = torch.empty(N, K, dtype=torch.int64, device=dev)
         ro = _lib.RenderOut(*[_lib.ptr(out.get(k)) for k in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
                                                              "z_samples", "inds")],
-                            *[_lib.ptr(acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")])
+                            *[_lib.ptr(acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")], _lib.ptr(net._status(dev)))
         rs = _lib.Randoms(*[_lib.ptr(rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
         flat_c, flat_f = want.get("flat") or (net.nerf.flat_params(), net.nerf_fine.flat_params())
         pk_c = net.nerf.packed(cfg.mode, force=net.training, flat=flat_c)
         pk_f = net.nerf_fine.packed(cfg.mode, force=net.training, flat=flat_f) if fine else pk_c
         wsz = L.nsos_render_workspace_bytes(cfg, N)
         ws = net._workspace(wsz, dev)
-        _lib.check(L.nsos_render_fwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
-                                     _lib.ptr(rays_d), _lib.ptr(near), _lib.ptr(far), C.byref(rs), seed, C.byref(ro), _lib.ptr(ws),
-                                     ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_fwd")
+        with torch.cuda.device(dev):        # the library launches on the calling thread's current device
+            _lib.check(L.nsos_render_fwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
+                                         _lib.ptr(rays_d), _lib.ptr(near), _lib.ptr(far), C.byref(rs), seed, C.byref(ro), _lib.ptr(ws),
+                                         ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_fwd")
         return out, acts
 
     @staticmethod
@@ -151,11 +152,12 @@ class _RenderFn(torch.autograd.Function):
         saved = None
         if ctx.acts and not trunk:
             saved = C.byref(_lib.RenderOut(None, None, None, _lib.ptr(ctx.acts.get("raw0")), _lib.ptr(ctx.acts.get("raw")), None, None,
-                                           None, None, *[_lib.ptr(ctx.acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")]))
-        _lib.check(L.nsos_render_bwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
-                                     _lib.ptr(rays_d), _lib.ptr(z0),
-                                     _lib.ptr(z1), C.byref(rs), ctx.seed, _lib.ptr(g_maps.contiguous()), _lib.ptr(g_c), _lib.ptr(g_f),
-                                     trunk, saved, _lib.ptr(ws), ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_bwd")
+                                           None, None, *[_lib.ptr(ctx.acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")], None))
+        with torch.cuda.device(dev):
+            _lib.check(L.nsos_render_bwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
+                                         _lib.ptr(rays_d), _lib.ptr(z0),
+                                         _lib.ptr(z1), C.byref(rs), ctx.seed, _lib.ptr(g_maps.contiguous()), _lib.ptr(g_c), _lib.ptr(g_f),
+                                         trunk, saved, _lib.ptr(ws), ws.numel(), N, _lib.cur_stream(dev)), "nsos_render_bwd")
         ctx.acts = None
         grads = []
         offs = list(net.nerf._flat.offsets) + (list(net.nerf_fine._flat.offsets) if fine else [])
@@ -213,6 +215,23 @@ class NeRFNet(nn.Module):
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
             self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
         return self._ws
+
+    def _status(self, device):
+        st = self.__dict__.get("_status_word")
+        if st is None or st.device != device:
+            st = self.__dict__["_status_word"] = torch.zeros(1, dtype=torch.int32, device=device)
+        return st
+
+    def range_overflow(self) -> bool:
+        """True if, since the last call, a tcgen05-mode render met a hidden activation beyond the fp16 range of its
+        activation planes (|a| > 4094; the affected maps are non-finite).  Reads and clears the kernel's sticky status word
+        (one device synchronisation) -- call it after an evaluation pass, not per step.  Such a net needs mode='simt'."""
+        st = self.__dict__.get("_status_word")
+        if st is None:
+            return False
+        v = int(st.item())
+        st.zero_()
+        return bool(v & 1)
 
     def resolve_mode(self, mode=None, n_samples=None, n_importance=None) -> int:
         mode = mode or self.mode

@@ -71,8 +71,9 @@ class _GeoCorrFn(torch.autograd.Function):
         if nb == 0:
             raise _lib.NsosError("geo correlation loss: unsupported sizes")
         ws = _workspace(nb, code.device)
-        _lib.check(L.nsos_geo_corr_loss(_lib.ptr(xyz_f), _lib.ptr(code_f), _lib.ptr(neg), _params4(params), _lib.ptr(loss), _lib.ptr(g),
-                                        B, Cc, M, _lib.ptr(ws), ws.numel(), _lib.cur_stream(code.device)), "nsos_geo_corr_loss")
+        with torch.cuda.device(code.device):        # the library launches on the calling thread's current device
+            _lib.check(L.nsos_geo_corr_loss(_lib.ptr(xyz_f), _lib.ptr(code_f), _lib.ptr(neg), _params4(params), _lib.ptr(loss), _lib.ptr(g),
+                                            B, Cc, M, _lib.ptr(ws), ws.numel(), _lib.cur_stream(code.device)), "nsos_geo_corr_loss")
         ctx.g, ctx.shape = g, code.shape
         return loss[0]
 
@@ -97,9 +98,10 @@ class _AppCorrFn(torch.autograd.Function):
         g1 = torch.empty_like(c1) if need_g else None
         g2 = torch.empty_like(c2) if need_g else None
         ws = _workspace(L.nsos_app_corr_workspace_bytes(B, Cf, Cc, S), code.device)
-        _lib.check(L.nsos_app_corr_loss(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(c1), _lib.ptr(c2), _params4(params), _lib.ptr(loss),
-                                        _lib.ptr(g1), _lib.ptr(g2), B, Cf, Cc, S, _lib.ptr(ws), ws.numel(),
-                                        _lib.cur_stream(code.device)), "nsos_app_corr_loss")
+        with torch.cuda.device(code.device):
+            _lib.check(L.nsos_app_corr_loss(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(c1), _lib.ptr(c2), _params4(params), _lib.ptr(loss),
+                                            _lib.ptr(g1), _lib.ptr(g2), B, Cf, Cc, S, _lib.ptr(ws), ws.numel(),
+                                            _lib.cur_stream(code.device)), "nsos_app_corr_loss")
         ctx.g1, ctx.g2, ctx.shape = g1, g2, code.shape
         return loss[0]
 

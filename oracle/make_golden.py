@@ -169,6 +169,145 @@ def flower():
          loss=float(loss))
 
 
+
+class ReplayRandom:
+    """Replay recorded torch.rand / torch.randn draws (in call order) inside the reference."""
+
+    def __init__(self, draws):
+        self.draws, self.i = list(draws), 0
+
+    def __enter__(self):
+        self._rand, self._randn = torch.rand, torch.randn
+
+        def nxt(*a, **k):
+            r = self.draws[self.i]; self.i += 1
+            return r.clone()
+
+        torch.rand, torch.randn = nxt, nxt
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randn = self._rand, self._randn
+
+
+def cam_rays(n, seed, t):
+    """n pixels of a 1008x756 / focal 815 view with c2w = [I | t] (same generator as llff_rays, caller-chosen origin)."""
+    g = torch.Generator().manual_seed(seed)
+    K = get_persp_intrinsic(756, 1008, 815.0)
+    c2w = torch.cat([torch.eye(3), torch.tensor(t, dtype=torch.float32)[:, None]], 1)
+    rays = get_persp_rays(756, 1008, K, c2w)
+    idx = torch.randperm(756 * 1008, generator=g)[:n]
+    return rays.reshape(2, -1, 3)[:, idx].contiguous()
+
+
+def stage1_checkpoint(tag, fname, rays, near, far):
+    """The other shipped stage-1 checkpoints (pretrained_ckpt/*.ckpt): strict=False load (the 8 semantic_linear tensors keep
+    their seeded default init, exactly what run_nerf.py does at the start of stage 2), eval maps + stage intermediates on
+    256 rays, and the largest hidden activation per trunk layer (range evidence for the fp16 split of the tcgen05 path)."""
+    ck = torch.load("/root/reference/pretrained_ckpt/" + fname, map_location="cpu")
+    torch.manual_seed(0)
+    net = NeRFNet(N_samples=64, N_importance=128, use_semantics=True, sem_with_coord=True, sem_dim=2, sem_layer=2)
+    missing = net.load_state_dict(ck["model"], strict=False)
+    assert len(missing.missing_keys) == 8 and all("semantic_linear" in k for k in missing.missing_keys), missing
+    net.eval()
+    amax = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            amax[name] = max(amax.get(name, 0.0), float(torch.relu(out).abs().max()))
+        return f
+
+    hs = []
+    for pre, m in (("nerf", net.nerf.mlp), ("nerf_fine", net.nerf_fine.mlp)):
+        for i, lin in enumerate(m.pts_linears):
+            hs.append(lin.register_forward_hook(hook(f"{pre}.pts_linears.{i}")))
+        hs.append(m.views_linears[0].register_forward_hook(hook(f"{pre}.views_linears.0")))
+        hs.append(m.semantic_linear[0].register_forward_hook(hook(f"{pre}.semantic_linear.0")))
+    n = rays.shape[1]
+    with torch.no_grad():
+        ret = net(rays, (near, far))
+        z = net.point_sampler(rays[0], rays[1], torch.tensor([[near, far]]).expand(n, 2), zvals_only=True, perturb=0.0)
+        mid = .5 * (z[..., 1:] + z[..., :-1])
+        w = ret["weights0"][..., 1:-1] + 1e-5
+        pdf = w / torch.sum(w, -1, keepdim=True)
+        cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+        u = torch.linspace(0., 1., steps=128).expand(n, 128).contiguous()
+        inds = torch.searchsorted(cdf, u, right=True)
+        z_samples = net.importance_sampler.sample_pdf(mid, ret["weights0"][..., 1:-1], det=True)
+    for h in hs:
+        h.remove()
+    print(tag, "max hidden activation per layer:", {k: round(v, 2) for k, v in amax.items()})
+    keep = {k: v for k, v in outs(ret).items() if k != "raw"}          # raw0 kept (coarse per-sample check), fine raw dropped (size)
+    save(tag + "_eval_256", sd=npsd(net), rays=rays.numpy(), near=near, far=far, out=keep,
+         stage=dict(z=z.numpy(), mid=mid.numpy(), cdf=cdf.numpy(), u=u.numpy(), inds=inds.numpy(), z_samples=z_samples.numpy()),
+         amax={k: np.float32(v) for k, v in amax.items()}, global_step=ck["global_step"])
+
+
+def other_checkpoints():
+    # fortress: LLFF forward-facing, far = 14.72 (the value quoted in models/sampler.py:45)
+    stage1_checkpoint("fortress", "fortress_00150000.ckpt", llff_rays(256, seed=31), 1.2, 14.72)
+    # co3d apple: object-centric; camera 4 units in front of the object, some rays miss it (acc < 1, depth -> 1e10 path)
+    stage1_checkpoint("co3d_apple", "co3d_apple_110_00140000.ckpt", cam_rays(256, 32, [0.1, -0.05, 4.0]), 1.0, 8.0)
+
+
+def safe_ray_mask(ret, u, margin=2e-5):
+    """Rays whose importance samples sit safely inside their cdf bins: every u at least `margin` away from both neighbouring
+    cdf knots, and no selected bin with |denom - 1e-5| < margin/10 (sampler.py:117-132).  On these rays a 1-ulp difference in
+    the coarse weights cannot flip a searchsorted index or the denom<1e-5 switch, so fine-pass outputs and gradients are
+    comparable at fp32 tolerance; the cotangents of the other rays are zeroed in the gradient fixtures."""
+    w = ret["weights0"].detach()[..., 1:-1] + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+    inds = torch.searchsorted(cdf, u.contiguous(), right=True)
+    below = torch.max(torch.zeros_like(inds - 1), inds - 1)
+    above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
+    cb, ca = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+    d_lo = (u - cb).abs()
+    d_hi = torch.where(inds < cdf.shape[-1], (ca - u).abs(), torch.ones_like(u))
+    den = ca - cb
+    ok = (d_lo > margin) & (d_hi > margin) & ((den - 1e-5).abs() > margin / 10)
+    return ok.all(-1)
+
+
+def _grads_safe(name, net, rays, draws, keys, seed):
+    net.train()
+    with ReplayRandom(draws) as rp:
+        ret = net(rays, (1.2, 12.0))
+    assert rp.i == 4
+    safe = safe_ray_mask(ret, draws[2])
+    g = torch.Generator().manual_seed(seed)
+    tgt = {k: torch.randn(ret[k].shape, generator=g) * safe.reshape(-1, *([1] * (ret[k].dim() - 1))) for k in keys}
+    loss = sum((ret[k] * tgt[k]).sum() for k in tgt)
+    loss.backward()
+    grads = {k: p.grad.numpy().copy() for k, p in net.named_parameters()}
+    print(name, f"safe rays: {int(safe.sum())} of {safe.numel()}")
+    save(name, safe=safe.numpy(), gout={k: v.numpy() for k, v in tgt.items()}, grads=grads, loss=float(loss.detach()))
+
+
+def flower_all_param_grads():
+    """All-parameter autograd gradients (stage-1 training, engines/trainer.py:201 without --fix_backbone) of the shipped
+    flower net on the rays / random draws of flower_train_64_semgrads.npz (replayed), cotangents restricted to the rays
+    whose importance samples cannot flip (safe_ray_mask).  The semantic_linear entries double as the --fix_backbone
+    gradients (they do not depend on which other parameters require grad)."""
+    g = np.load(os.path.join(OUT, "flower_train_64_semgrads.npz"))
+    ck = torch.load(CKPT, map_location="cpu")
+    net = NeRFNet(perturb=1.0, raw_noise_std=1.0, N_samples=64, N_importance=128, use_semantics=True, sem_with_coord=True,
+                  sem_dim=2, sem_layer=2)
+    net.load_state_dict(ck["model"], strict=True)
+    draws = [torch.from_numpy(g["rnd/" + k]) for k in ("t_rand", "noise0", "u", "noise1")]
+    _grads_safe("flower_train_64_allgrads", net, torch.from_numpy(g["rays"]), draws, ("rgb", "rgb0", "semantics", "semantics0", "acc", "depth0"), 17)
+
+
+def cfg1_grads_safe():
+    """Same for the tiny D=4 W=64 net of cfg1_d4w64_train_grads.npz."""
+    g = np.load(os.path.join(OUT, "cfg1_d4w64_train_grads.npz"))
+    net = NeRFNet(netdepth=4, netwidth=64, netdepth_fine=4, netwidth_fine=64, N_samples=64, N_importance=32,
+                  use_semantics=True, sem_with_coord=True, perturb=1.0, raw_noise_std=1.0)
+    net.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}, strict=True)
+    draws = [torch.from_numpy(g["rnd/" + k]) for k in ("t_rand", "noise0", "u", "noise1")]
+    _grads_safe("cfg1_d4w64_train_grads_safe", net, torch.from_numpy(g["rays"]), draws, ("rgb", "rgb0", "semantics", "semantics0", "acc", "depth0"), 19)
+
+
 class _Args:
     rand_neg = False
     self_corr_w = 1
@@ -209,6 +348,6 @@ def losses():
 
 
 if __name__ == "__main__":
-    cfg1()
-    flower()
-    losses()
+    which = sys.argv[1:] or ["cfg1", "flower", "losses", "other_checkpoints", "flower_all_param_grads", "cfg1_grads_safe"]
+    for w in which:
+        globals()[w]()

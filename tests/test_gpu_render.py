@@ -3,7 +3,11 @@
 Every call goes through the C ABI (include/nerfsos.h) via the ctypes drop-in classes.  The checker is
 the numpy oracle / the reference-generated golden fixtures; tolerances follow BASELINE.json's north_star:
 1e-4 on rgb / density-derived maps, exact inverse-CDF indices given identical cdf/u (stage-wise), and an
-end-to-end index flip rate <= 2e-3.
+end-to-end index flip rate <= 1e-3 on the 127 interior samples.  The 128th deterministic sample is
+u = 1.0 exactly, i.e. ON the end point of the cdf (cumsum(pdf)[-1] = 1 +- 1 ulp by construction): searchsorted(right=True)
+returns 63 or 62 depending on the last ulp of the sum, in 10-26 % of the rays for the numpy oracle itself against the
+reference (every other oracle index is identical) -- that column is reported separately and the affected rays are the
+"flipped" ones.  Every NON-flipped ray is held to the 1e-4 contract, gradients to 1e-3 on rays that cannot flip.
 """
 import ctypes as C
 
@@ -33,6 +37,19 @@ def flower_net(mode, **kw):
     net = NeRFNet(**args)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
     return net.to(DEV)
+
+
+def fixture_net(tag, mode, **kw):
+    """flower: shipped stage-2 checkpoint; fortress / co3d_apple: shipped stage-1 checkpoints + seeded semantic heads."""
+    if tag == "flower":
+        return flower_net(mode, **kw), load_golden("flower_eval_256")
+    _lib, NeRFNet = _imports()
+    g = load_golden(tag + "_eval_256")
+    args = dict(N_samples=64, N_importance=128, use_semantics=True, sem_with_coord=True, sem_dim=2, sem_layer=2, mode=mode)
+    args.update(kw)
+    net = NeRFNet(**args)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in g["sd"].items()}, strict=True)
+    return net.to(DEV), g
 
 
 def cfg1_net(mode, golden, n_importance=0, **kw):
@@ -107,13 +124,16 @@ def test_cfg1_eval(mode):
     close(out["raw"], g["out"]["raw"], rtol=1e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("tag", ["flower", "fortress", "co3d_apple"])
 @pytest.mark.parametrize("mode", ["simt", "exact"])
-def test_flower_eval(mode):
-    """BASELINE config[1] weights (shipped flower checkpoint), 64+128 samples, D=8 W=256 + seg head."""
-    g = load_golden("flower_eval_256")
-    net = flower_net(mode).eval()
+def test_checkpoint_eval(mode, tag):
+    """BASELINE config[1] geometry (64+128 samples, D=8 W=256 + seg head) on every kind of shipped checkpoint: the stage-2
+    flower net, and the stage-1 fortress (configs[2]) / CO3D apple (configs[4]) nets with seeded semantic heads."""
+    net, g = fixture_net(tag, mode)
+    net.eval()
+    bounds = (float(g["near"]), float(g["far"]))
     with torch.no_grad():
-        out = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), retz=True)
+        out = net(torch.from_numpy(g["rays"]).to(DEV), bounds, retz=True)
     ref, st = g["out"], g["stage"]
     assert np.array_equal(out["z_vals0"].cpu().numpy(), st["z"])                 # coarse sample positions: bit-exact
     for k in ("rgb0", "acc0", "semantics0", "weights0"):
@@ -122,17 +142,67 @@ def test_flower_eval(mode):
     close(torch.relu(out["raw0"][..., 3]), np.maximum(ref["raw0"][..., 3], 0), rtol=1e-4, atol=1e-3)
     close(torch.sigmoid(out["raw0"][..., :3]), 1 / (1 + np.exp(-ref["raw0"][..., :3])), rtol=1e-4, atol=1e-4)
     flip = out["inds"].cpu().numpy() != st["inds"]
-    assert flip.mean() <= 2e-3, flip.mean()
-    for k in ("rgb", "acc", "semantics"):
-        close(out[k], ref[k], rtol=1e-4, atol=1e-4)
-    close(out["depth"], ref["depth"], rtol=1e-4, atol=1e-3)
-    ok = ~flip.any(-1)
+    assert flip[:, :-1].mean() <= 1e-3 and flip[:, -1].mean() <= 0.5, (flip[:, :-1].mean(), flip[:, -1].mean())
+    ok = ~flip.any(-1)                                                           # rays whose 128 indices all agree
+    assert ok.mean() >= 0.85, ok.mean()
+    for k in ("rgb", "acc", "semantics", "weights"):                             # non-flipped rays: the full contract
+        close(out[k][torch.from_numpy(ok).to(DEV)], ref[k][ok], rtol=1e-4, atol=1e-4)
+    hit = ok & (ref["acc"][:, 0] > 1e-3)                                         # depth is 1e10 where acc <= 1e-10 (renderer.py:72)
+    close(out["depth"][torch.from_numpy(hit).to(DEV)], ref["depth"][hit], rtol=1e-4, atol=1e-3)
+    for k in ("rgb", "acc", "semantics"):                                        # flipped rays: continuous except across flat bins
+        close(out[k], ref[k], rtol=1e-4, atol=1e-2)
     dz = np.abs(out["z_std"].cpu().numpy() - ref["z_std"])
     assert (dz[ok] < 1e-4).mean() >= 0.97
     for k in ref:
         assert tuple(out[k].shape) == ref[k].shape, k
     mse = float(((out["rgb"].cpu().numpy() - ref["rgb"]) ** 2).mean())
     assert -10 * np.log10(max(mse, 1e-20)) > 80.0                                # PSNR(ours, reference)
+    assert not net.range_overflow()                                             # fp16 hi/lo activation planes stayed in range
+
+
+def test_activation_range_guard():
+    """Exact mode keeps activations as fp16(16*a): |a| > 4094 cannot be represented.  The shipped nets peak at 59 (fortress
+    fine layer 7, recorded in the fixtures); a net that does overflow must say so (sticky device flag + non-finite maps),
+    never return plausible numbers."""
+    for tag in ("fortress", "co3d_apple"):
+        am = load_golden(tag + "_eval_256")["amax"]
+        assert max(float(v) for v in am.values()) < 4094 / 16                    # >= 16x headroom on every shipped layer
+    net, g = fixture_net("flower", "exact")
+    net.eval()
+    rays = torch.from_numpy(g["rays"][:, :32]).to(DEV)
+    with torch.no_grad():
+        net(rays, (1.2, 12.0))
+        assert not net.range_overflow()
+        net.nerf_fine.mlp.pts_linears[3].weight.mul_(3000.0)                     # hidden activations ~1e4
+        out = net(rays, (1.2, 12.0))
+    assert net.range_overflow()
+    assert not torch.isfinite(out["rgb"]).all()
+    assert not net.range_overflow()                                              # the flag is cleared by reading it
+
+
+def test_full_size_vs_numpy_oracle():
+    """BASELINE configs[1] at its real size -- the bench's own 4096 rays -- against the numpy oracle (outside the repo's
+    kernels): persistent-CTA multi-iteration path, 14 ray pairs per CTA, tile tails."""
+    from oracle import nerf_oracle as O
+    import bench
+    rays = bench.llff_rays(4096, 100)
+    net = flower_net("exact").eval()
+    with torch.no_grad():
+        out = net(torch.from_numpy(rays).to(DEV), (bench.NEAR, bench.FAR), retz=True)
+    ref = O.nerfnet_forward(load_golden("flower_weights")["sd"], rays, (bench.NEAR, bench.FAR), extras=True)
+    assert np.array_equal(out["z_vals0"].cpu().numpy(), ref["z_vals0"])
+    for k in ("rgb0", "acc0", "semantics0", "weights0"):
+        close(out[k], ref[k], rtol=1e-4, atol=1e-4)
+    flip = out["inds"].cpu().numpy() != ref["inds"]
+    assert flip[:, :-1].mean() <= 1e-3 and flip[:, -1].mean() <= 0.5, (flip[:, :-1].mean(), flip[:, -1].mean())
+    ok = ~flip.any(-1)
+    okd = torch.from_numpy(ok).to(DEV)
+    for k in ("rgb", "acc", "semantics", "weights"):
+        close(out[k][okd], ref[k][ok], rtol=1e-4, atol=1e-4)
+    close(out["depth"][okd], ref["depth"][ok], rtol=1e-4, atol=1e-3)
+    close(out["z_vals"][okd], ref["z_vals"][ok], rtol=0, atol=2e-5)
+    mse = float(((out["rgb"].cpu().numpy() - ref["rgb"]) ** 2).mean())
+    assert -10 * np.log10(max(mse, 1e-20)) > 80.0
 
 
 def test_flower_fast_mode_psnr():
@@ -152,30 +222,52 @@ def test_flower_train_injected_randoms(mode):
     out = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), randoms=rnd)
     for k in ("rgb0", "acc0", "semantics0", "weights0"):
         close(out[k], g["out"][k], rtol=1e-4, atol=1e-4)
+    safe = load_golden("flower_train_64_allgrads")["safe"]          # rays whose random u sit >= 2e-5 away from every cdf knot
+    for k in ("rgb", "acc", "semantics", "weights"):
+        close(out[k][torch.from_numpy(safe).to(DEV)], g["out"][k][safe], rtol=1e-4, atol=1e-4)
     d = np.abs(out["rgb"].detach().cpu().numpy() - g["out"]["rgb"]).max(-1)
-    assert np.median(d) < 5e-5 and (d < 1e-4).mean() >= 0.9, (np.median(d), d.max())
+    assert np.median(d) < 5e-5 and d.max() < 2e-2, (np.median(d), d.max())
+
+
+def _safe_grad_run(net, g, gs):
+    """Forward with the recorded draws, loss = <outputs, cotangents>; the cotangents are zero on rays whose importance samples
+    sit within 2e-5 of a cdf knot (oracle/make_golden.py:safe_ray_mask), so an index flip cannot leak into the gradients."""
+    rnd = {k: torch.from_numpy(v).to(DEV) for k, v in g["rnd"].items()}
+    out = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), randoms=rnd)
+    loss = sum((out[k] * torch.from_numpy(v).to(DEV)).sum() for k, v in gs["gout"].items())
+    assert abs(loss.item() - float(gs["loss"])) <= 1e-3 * max(1.0, abs(float(gs["loss"])))
+    loss.backward()
+    return {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
 
 
 @pytest.mark.parametrize("mode", ["simt", "exact"])
 def test_flower_semantic_head_gradients(mode):
-    """--fix_backbone recipe: only semantic_linear.{0,2} of both nets receive gradients (run_nerf.py:307-318)."""
-    g = load_golden("flower_train_64_semgrads")
+    """--fix_backbone recipe: only semantic_linear.{0,2} of both nets receive gradients (run_nerf.py:307-318); 1e-3 of max
+    against reference autograd on both passes."""
+    g, gs = load_golden("flower_train_64_semgrads"), load_golden("flower_train_64_allgrads")
     net = flower_net(mode, perturb=1.0, raw_noise_std=1.0).train()
     for n, p in net.named_parameters():
         p.requires_grad_("semantic_linear" in n)
-    rnd = {k: torch.from_numpy(v).to(DEV) for k, v in g["rnd"].items()}
-    out = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), randoms=rnd)
-    loss = sum((out[k] * torch.from_numpy(v).to(DEV)).sum() for k, v in g["gout"].items())
-    assert abs(loss.item() - float(g["loss"])) <= 2e-3 * max(1.0, abs(float(g["loss"])))
-    loss.backward()
-    got = {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
-    assert set(got) == set(g["grads"])
-    for n, ref in g["grads"].items():
-        scale = np.abs(ref).max()
-        # the fine-pass gradients inherit the index-flip sensitivity of the forward pass
-        tol = 2e-3 if n.startswith("nerf.") else 3e-2
-        err = np.abs(got[n].cpu().numpy() - ref).max()
-        assert err <= tol * scale, (n, err, scale)
+    got = _safe_grad_run(net, g, gs)
+    assert set(got) == {n for n in gs["grads"] if "semantic_linear" in n} and len(got) == 8
+    for n, gr in got.items():
+        ref = gs["grads"][n]
+        err = np.abs(gr.cpu().numpy() - ref).max()
+        assert err <= 1e-3 * np.abs(ref).max(), (n, err, np.abs(ref).max())
+
+
+def test_flower_all_parameter_gradients():
+    """Stage-1 training (engines/trainer.py:201 with every parameter trainable) at D=8 W=256: all 1,274,124 gradients vs
+    reference autograd, 1e-3 of each tensor's max."""
+    g, gs = load_golden("flower_train_64_semgrads"), load_golden("flower_train_64_allgrads")
+    net = flower_net("exact", perturb=1.0, raw_noise_std=1.0).train()
+    got = _safe_grad_run(net, g, gs)
+    assert set(got) == set(gs["grads"])
+    assert sum(v.numel() for v in got.values()) == 1274124
+    for n, gr in got.items():
+        ref = gs["grads"][n]
+        err = np.abs(gr.cpu().numpy() - ref).max()
+        assert err <= 1e-3 * max(np.abs(ref).max(), 1e-8), (n, err, np.abs(ref).max())
 
 
 def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypatch):
@@ -224,19 +316,18 @@ def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypat
 
 def test_cfg1_full_gradients():
     """All-parameter backward (trunk dgrad/wgrad) vs reference autograd, tiny net, train mode, injected randoms."""
-    g = load_golden("cfg1_d4w64_train_grads")
+    g, gs = load_golden("cfg1_d4w64_train_grads"), load_golden("cfg1_d4w64_train_grads_safe")
     net = cfg1_net("simt", g, n_importance=32, perturb=1.0, raw_noise_std=1.0).train()
     rnd = {k: torch.from_numpy(v).to(DEV) for k, v in g["rnd"].items()}
     out = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), randoms=rnd)
     for k in ("rgb0", "semantics0", "acc0"):
         close(out[k], g["out"][k], rtol=1e-4, atol=1e-4)
-    loss = sum((out[k] * torch.from_numpy(v).to(DEV)).sum() for k, v in g["gout"].items())
+    loss = sum((out[k] * torch.from_numpy(v).to(DEV)).sum() for k, v in gs["gout"].items())
     loss.backward()
     for n, p in net.named_parameters():
-        ref = g["grads"][n]
-        tol = 2e-3 if n.startswith("nerf.") else 5e-2
+        ref = gs["grads"][n]
         err = np.abs(p.grad.cpu().numpy() - ref).max()
-        assert err <= tol * max(np.abs(ref).max(), 1e-6), (n, err, np.abs(ref).max())
+        assert err <= 1e-3 * max(np.abs(ref).max(), 1e-6), (n, err, np.abs(ref).max())
 
 
 # ---- edge cases the reference exercises ---------------------------------------------------------------
@@ -309,9 +400,14 @@ def test_config_variants_vs_oracle(mode, variant):
         out = net(torch.from_numpy(rays).to(DEV), (1.2, 12.0), retz=True)
     sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     ref = O.nerfnet_forward(sd, rays, (1.2, 12.0), extras=True, **okw)
-    assert set(ref) - {"cdf", "u"} >= set(out) - {"z_vals0"} or True
-    for k in ("rgb0", "acc0", "weights0", "rgb", "acc") + (("semantics0", "semantics") if variant != "no_sem" else ()):
-        close(out[k], ref[k], rtol=1e-4, atol=1e-4, frac=0.98)
+    assert set(out) <= set(ref), set(out) - set(ref)
+    sem = ("semantics",) if variant != "no_sem" else ()
+    for k in ("rgb0", "acc0", "weights0") + tuple(k + "0" for k in sem):
+        close(out[k], ref[k], rtol=1e-4, atol=1e-4)
+    ok = torch.from_numpy(~(out["inds"].cpu().numpy() != ref["inds"]).any(-1)).to(DEV)
+    assert ok.float().mean().item() >= 0.9
+    for k in ("rgb", "acc") + sem:                                   # every ray with the reference's sample set: the full contract
+        close(out[k][ok], ref[k][ok.cpu().numpy()], rtol=1e-4, atol=1e-4)
     if variant == "no_sem":
         assert "semantics" not in out and out["raw"].shape[-1] == 4
 
@@ -332,11 +428,12 @@ def test_full_size_exact_vs_same_device_fp32():
         a = flower_net("exact").eval()(rays, (1.2, 12.0), retz=True)
         b = flower_net("simt").eval()(rays, (1.2, 12.0), retz=True)
     flip = (a["inds"] != b["inds"])
-    assert flip.float().mean().item() <= 2e-3
+    assert flip[:, :-1].float().mean().item() <= 1e-3 and flip[:, -1].float().mean().item() <= 0.5
     for k in ("rgb0", "acc0", "semantics0"):
         close(a[k], b[k].cpu().numpy(), rtol=1e-4, atol=1e-4)
+    ok = ~flip.any(-1)
     for k in ("rgb", "acc", "semantics"):
-        close(a[k], b[k].cpu().numpy(), rtol=1e-4, atol=1e-4, frac=0.999)
+        close(a[k][ok], b[k][ok].cpu().numpy(), rtol=1e-4, atol=1e-4)
     # determinism and ray-permutation equivariance (rays are independent units)
     net = flower_net("exact").eval()
     with torch.no_grad():
@@ -395,3 +492,17 @@ def test_cpu_tensors_fail_loudly():
     net = NeRFNet(netdepth=2, netwidth=64, netdepth_fine=2, netwidth_fine=64, N_samples=8, N_importance=0)
     with pytest.raises(_lib.NsosError):
         net(torch.zeros(2, 4, 3), (1.0, 2.0))
+
+
+def test_wide_encodings_fail_loudly():
+    """multires > 10 / multires_views > 4 are CLI-exposed in the reference but outside both kernels' row pitch: refuse, never
+    truncate the encoding silently."""
+    _lib, NeRFNet = _imports()
+    rays = torch.rand(2, 8, 3, device=DEV)
+    for kw in (dict(multires=11), dict(multires_views=5)):
+        net = NeRFNet(netdepth=2, netwidth=64, netdepth_fine=2, netwidth_fine=64, N_samples=8, N_importance=8, **kw).to(DEV).eval()
+        with pytest.raises(_lib.NsosError):
+            with torch.no_grad():
+                net(rays, (1.0, 2.0))
+        with pytest.raises(_lib.NsosError):
+            net.nerf(torch.rand(5, 3, device=DEV), viewdirs=torch.rand(5, 3, device=DEV))

@@ -57,10 +57,10 @@ def test_flower_eval_end_to_end(flower_sd):
     out = O.nerfnet_forward(flower_sd, g["rays"], (1.2, 12.0), extras=True)
     ref = g["out"]
     flip = out["inds"] != g["stage"]["inds"]
-    # a ~1e-6 perturbation of the coarse weights flips ~1e-3 of the searchsorted indices
-    # (u lands within an ulp of a cdf knot); the inverse CDF is continuous there except across flat
-    # bins (denom<1e-5 -> 1), so the composited maps still agree on every ray.
-    assert flip.mean() <= 2e-3, flip.mean()
+    # Interior indices are identical; the last deterministic sample u = 1.0 sits ON the cdf's end point (cumsum(pdf)[-1] =
+    # 1 +- 1 ulp), so its index is 62 or 63 by the last ulp of the sum.  Across a flat last bin (denom<1e-5 -> 1,
+    # sampler.py:129-130) that moves one zero-weight sample by a bin: the composited maps still agree on every ray.
+    assert flip[:, :-1].mean() <= 1e-3 and flip[:, -1].mean() <= 0.5, (flip[:, :-1].mean(), flip[:, -1].mean())
     ok = ~flip.any(-1)
     for k in ("rgb0", "acc0", "semantics0", "depth0", "weights0"):
         close(out[k], ref[k], rtol=1e-4, atol=2e-5)
@@ -163,3 +163,50 @@ def test_feature_views_fusion_is_exact_to_fp32_rounding(flower_sd):
     e_ref, e_fused = np.abs(ref - exact).max() / scale, np.abs(fused - exact).max() / scale
     assert e_fused < 2e-6 and e_fused < 4 * e_ref + 1e-7, (e_ref, e_fused)
     assert np.abs(fused - ref).max() / scale < 4e-6
+
+
+@pytest.mark.parametrize("tag", ["fortress", "co3d_apple"])
+def test_other_shipped_checkpoints_end_to_end(tag):
+    """The oracle on the stage-1 fortress / CO3D-apple checkpoints (strict=False load + seeded semantic heads, as stage 2
+    starts): pinned to the unmodified reference's outputs, non-flipped rays at 1e-4."""
+    g = load_golden(tag + "_eval_256")
+    bounds = (float(g["near"]), float(g["far"]))
+    out = O.nerfnet_forward(g["sd"], g["rays"], bounds, extras=True)
+    ref, st = g["out"], g["stage"]
+    assert np.array_equal(out["z_vals0"], st["z"])
+    for k in ("rgb0", "acc0", "semantics0", "weights0"):
+        close(out[k], ref[k], rtol=1e-4, atol=2e-5)
+    flip = out["inds"] != st["inds"]
+    assert flip[:, :-1].mean() <= 1e-3 and flip[:, -1].mean() <= 0.5, (flip[:, :-1].mean(), flip[:, -1].mean())
+    ok = ~flip.any(-1)
+    for k in ("rgb", "acc", "semantics", "weights"):
+        close(out[k][ok], ref[k][ok], rtol=1e-4, atol=1e-4)
+    # range evidence for the fp16 activation planes of the tcgen05 path: largest hidden activation of any layer
+    assert max(float(v) for v in g["amax"].values()) < 4094 / 16
+
+
+def test_safe_ray_gradient_fixtures_are_consistent():
+    """The masked-cotangent gradient fixtures: zero cotangents exactly on the unsafe rays, semantic-head gradients of the
+    all-parameter run equal the formulas of Appendix A.1 evaluated by the oracle (cfg1 net, both passes)."""
+    g, gs = load_golden("cfg1_d4w64_train_grads"), load_golden("cfg1_d4w64_train_grads_safe")
+    safe = gs["safe"]
+    assert 0.8 < safe.mean() <= 1.0
+    for k, v in gs["gout"].items():
+        assert not v[~safe].any() and v[safe].any(), k
+    sd, rnd = g["sd"], g["rnd"]
+    out = O.nerfnet_forward(sd, g["rays"], (1.2, 12.0), randoms=rnd, extras=True, n_samples=64, n_importance=32, D=4, D_fine=4,
+                            perturb=1.0, raw_noise_std=1.0)
+    coarse, fine = O.split_state_dict(sd)
+    rays_o, rays_d = g["rays"][0], g["rays"][1]
+    vd = rays_d / np.linalg.norm(rays_d, axis=-1, keepdims=True)
+    for net, pre, sfx, zk, nz in ((coarse, "nerf", "0", "z_vals0", "noise0"), (fine, "nerf_fine", "", "z_vals", "noise1")):
+        z, raw = out[zk], out["raw" + sfx]
+        graw = O.composite_backward(raw, z, rays_d, gs["gout"]["rgb" + sfx], gs["gout"]["semantics" + sfx],
+                                    g_depth=gs["gout"]["depth0"] if sfx == "0" else None,
+                                    g_acc=gs["gout"]["acc"] if sfx == "" else None, noise=rnd[nz])
+        e = O.encode(O.points(rays_o, rays_d, z).reshape(-1, 3), 10)
+        ed = O.encode(np.repeat(vd[:, None], z.shape[1], 1).reshape(-1, 3), 4)
+        _, acts = O.mlp_forward(net, e, ed, D=4, return_acts=True)
+        for k, v in O.sem_head_backward(net, acts["sem_in"], acts["s0"], graw[..., 4:].reshape(-1, 2)).items():
+            ref = gs["grads"][f"{pre}.mlp.{k}"]
+            assert np.abs(v - ref).max() <= 1e-3 * np.abs(ref).max(), (pre, k)
