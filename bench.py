@@ -99,48 +99,112 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
-def cpu_port_rate(n_rays, repeats=1):
-    """rays/s of the reference's CPU path (PyTorch-CPU port, all host threads) on n_rays of the workload."""
+def reference_forward(device="cpu"):
+    """The reference's own NeRFNet.forward for BASELINE configs[1] (stock code path, stock kwargs) with the shipped flower
+    weights: the UNMODIFIED modules of /root/reference, or on the GPU box their byte-compiled copies in oracle/_ref/
+    (oracle/build_ref.py).  Returns (fn(rays[2,N,3]) -> dict, kind) or (None, why) when neither is importable."""
+    import contextlib
     import torch
-    from oracle import torch_port as TP          # the one place bench.py executes oracle/: as the timed CPU baseline
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_shim
+        if not ref_shim.available():
+            return None, "neither /root/reference nor oracle/_ref is present"
+        with contextlib.redirect_stdout(sys.stderr):                  # the reference prints banners on import / construction
+            from models.nerf_net import NeRFNet as RefNet
+            net = RefNet(N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, use_semantics=True, sem_with_coord=True, sem_dim=2, sem_layer=2)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights().items()}, strict=True)
+        net = net.to(device).eval()
+    except Exception as e:                                            # e.g. a stale oracle/_ref from another interpreter
+        return None, repr(e)
+
+    def fwd(rays):
+        with torch.no_grad():
+            return net(rays, (NEAR, FAR))
+    return fwd, ("reference" if ref_shim.KIND == "source" else "reference (oracle/_ref byte-compiled modules)")
+
+
+def cpu_reference_rate(n_rays, repeats=2):
+    """rays/s of the reference's CPU path on all host cores (the unmodified reference when importable, else the port)."""
+    import torch
     torch.set_num_threads(os.cpu_count())
-    sd = {k: torch.from_numpy(v) for k, v in load_weights().items()}
     rays = torch.from_numpy(llff_rays(n_rays, 0))
-    TP.render_eval(sd, rays[0, :128], rays[1, :128], NEAR, FAR)          # warm-up (thread pools, MKL init)
+    fwd, kind = reference_forward("cpu")
+    if fwd is None:
+        from oracle import torch_port as TP          # fallback: op-for-op PyTorch-CPU port, pinned to the fixtures
+        sd = {k: torch.from_numpy(v) for k, v in load_weights().items()}
+        fwd, kind = (lambda r: TP.render_eval(sd, r[0], r[1], NEAR, FAR)), "port"
+    fwd(rays[:, :128])                                                    # warm-up (thread pools, MKL init)
     best = 1e30
     for _ in range(repeats):
         t0 = time.perf_counter()
-        TP.render_eval(sd, rays[0], rays[1], NEAR, FAR)
+        fwd(rays)
         best = min(best, time.perf_counter() - t0)
-    return n_rays / best, torch.get_num_threads()
+    return n_rays / best, torch.get_num_threads(), kind
+
+
+def gpu_eager_rate(dev, n_rays=N_RAYS):
+    """SURVEY 8d's second comparator: the reference's eager PyTorch path on the same B200, TF32 off."""
+    import torch
+    fwd, kind = reference_forward(dev)
+    if fwd is None:
+        return {"unavailable": kind}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        rays = torch.from_numpy(llff_rays(n_rays, 100)).to(dev)
+        for _ in range(3):
+            fwd(rays)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fwd(rays); e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        med = float(np.median(ms))
+        return {"value": n_rays / (med * 1e-3), "unit": "rays/s", "ms_per_step": med, "kind": kind,
+                "sample": f"{n_rays} rays, median of 5 after 3 warm-ups, eager PyTorch on cuda, allow_tf32=False, stock kwargs (retraw=True)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path on the host cores, same config / metric / steps."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    n = 2048                                                             # bounded sample of the 4096-ray batch
     import torch
-    from oracle import torch_port as TP
     torch.set_num_threads(os.cpu_count())
-    sd = {k: torch.from_numpy(v) for k, v in load_weights().items()}
-    rays = torch.from_numpy(llff_rays(n, 0))
-    for _ in range(min(args.warmup, 2)):
-        TP.render_eval(sd, rays[0, :256], rays[1, :256], NEAR, FAR)
-    steps = min(args.steps, 5)
+    n = N_RAYS
+    rays = torch.from_numpy(llff_rays(n, 100))
+    fwd, kind = reference_forward("cpu")
+    if fwd is None:
+        from oracle import torch_port as TP
+        sd = {k: torch.from_numpy(v) for k, v in load_weights().items()}
+        fwd, kind = (lambda r: TP.render_eval(sd, r[0], r[1], NEAR, FAR)), "port"
+    warm = max(args.warmup, 1)
+    t0 = time.perf_counter()
+    fwd(rays)                                                            # first warm-up at full size doubles as the cost estimate
+    est = time.perf_counter() - t0
+    for _ in range(warm - 1):
+        fwd(rays)
+    steps = args.steps if est * args.steps <= 420.0 else max(3, int(420.0 / est))     # keep the arm within a few minutes
     t0 = time.perf_counter()
     for _ in range(steps):
-        TP.render_eval(sd, rays[0], rays[1], NEAR, FAR)
+        fwd(rays)
     dt = (time.perf_counter() - t0) / steps
     v = n / dt
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": "rays/sec (64c+128f samples, D=8 W=256)", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "flower_full 4096 rays x (64+128) samples, D=8 W=256 + seg head, eval forward",
-                       "sample": f"{n} of 4096 rays per step"},
-            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{n}-ray slices of the 4096-ray batch, {steps} steps, PyTorch-CPU port of the reference path"},
+            "config": {"workload": "flower_full 4096 rays x (64+128) samples, D=8 W=256 + seg head, eval forward (BASELINE configs[1])",
+                       "rays_per_step": n, "weights": "shipped flower stage-2 checkpoint (fixture)",
+                       "impl": "reference NeRFNet.forward, stock kwargs, PyTorch CPU" if kind != "port" else "oracle/torch_port.py"},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "reference" if kind != "port" else "port",
+                             "sample": f"the full {n}-ray batch per step, {steps} steps after {warm} warm-ups; {kind}"},
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -433,9 +497,13 @@ def main():
         except Exception as e:                                           # never lose the timing line over the side check
             line["parity"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
-            v, cores = cpu_port_rate(N_RAYS, repeats=2)                  # bounded sample: the 4096-ray batch
-            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": "the same 4096-ray batch, best of 2, PyTorch-CPU port of the reference path (oracle/torch_port.py)"}
+            v, cores, kind = cpu_reference_rate(N_RAYS, repeats=2)       # bounded sample: the 4096-ray batch
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "reference" if kind != "port" else "port",
+                                    "sample": f"the same 4096-ray batch, best of 2 after a warm-up, all host cores; {kind}"}
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_rate(dev)
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"error": repr(e)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -75,6 +75,11 @@ typedef struct NsosRandoms {
   const float* noise0;
   const float* u;
   const float* noise1;
+  /* Optional stage-wise hook [N,K]: use these importance samples (sampler.py:132 `samples`) instead of inverting the
+   * kernel's own cdf; inds / z_std are still computed from the kernel's cdf.  The inverse cdf is ill-conditioned in
+   * low-mass bins (d sample / d cdf = bin width / denom, up to 1e4), so fine-pass parity -- outputs and gradients -- is
+   * checked stage-wise on the reference's own samples, exactly like the index contract on the reference's own cdf. */
+  const float* z_samples;
 } NsosRandoms;
 
 /* Outputs of nsos_render_fwd (device pointers).  `maps` is required, the rest may be NULL.
@@ -101,7 +106,7 @@ typedef struct NsosRenderOut {
   float* s_hid;      /* [N, Sc+K, W/2]               */
   /* Optional sticky status word (caller zero-initialises, reads and clears it; never reset by the library).
    * bit 0: NSOS_MODE_TC_EXACT/FAST only -- a hidden activation exceeded the fp16 range of the activation planes
-   *        (|a| > 4094): the affected maps are non-finite.  Re-render those nets with NSOS_MODE_SIMT_FP32. */
+   *        (|a| > 4094): the rgb / semantics maps of the affected rays are NaN.  Render such nets with NSOS_MODE_SIMT_FP32. */
   uint32_t* status;
 } NsosRenderOut;
 

@@ -31,7 +31,7 @@ class RenderCfg(C.Structure):
 
 
 class Randoms(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("t_rand", "noise0", "u", "noise1")]
+    _fields_ = [(n, C.c_void_p) for n in ("t_rand", "noise0", "u", "noise1", "z_samples")]
 
 
 class RenderOut(C.Structure):

@@ -226,6 +226,7 @@ struct ImportanceIO {
   float* zall;       // [Sc+K] scratch (shared)
   float* zsorted;    // [Sc+K] out (shared or global)
   const float* u;    // [K] injected draws or nullptr
+  const float* z_inject = nullptr;   // [K] injected importance samples (stage-wise parity hook) or nullptr
   float* z_samples;  // [K] out (global) or nullptr
   int64_t* inds;     // [K] out (global) or nullptr
   float* z_std;      // out (global, 1 float) or nullptr
@@ -263,6 +264,7 @@ __device__ inline void warp_importance(const ImportanceIO& io, int lane) {
     float u = io.det ? lin01(j, io.K) : (io.u ? io.u[j] : rng_uniform(io.seed, io.ray, RNG_U, j));  // :98-103
     int ind;
     float zs = invert_cdf_one(io.cdf, io.bins, M, u, &ind);
+    if (io.z_inject) zs = io.z_inject[j];
     io.zall[io.Sc + j] = zs;
     if (io.z_samples) io.z_samples[j] = zs;
     if (io.inds) io.inds[j] = ind;

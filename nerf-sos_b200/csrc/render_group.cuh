@@ -163,6 +163,7 @@ __device__ inline void group_importance(const ImportanceIO& io, int tid, int bar
     float u = io.det ? lin01(j, io.K) : (io.u ? io.u[j] : rng_uniform(io.seed, io.ray, RNG_U, j));   // :98-103
     int ind;
     float zs = invert_cdf_one(io.cdf, io.bins, M, u, &ind);
+    if (io.z_inject) zs = io.z_inject[j];
     io.zall[io.Sc + j] = zs;
     if (io.z_samples) io.z_samples[j] = zs;
     if (io.inds) io.inds[j] = ind;

@@ -99,7 +99,8 @@ __global__ void k_composite_bwd(const float* __restrict__ raw, const float* __re
 }
 
 // 4 warps / block; dynamic smem per warp: z0[Sc] w0[Sc] cdf[Sc] bins[Sc] zall[Sc+K]
-__global__ void k_importance(const float* __restrict__ z0, const float* __restrict__ w0, const float* __restrict__ u, float perturb,
+__global__ void k_importance(const float* __restrict__ z0, const float* __restrict__ w0, const float* __restrict__ u,
+                             const float* __restrict__ z_inject, float perturb,
                              uint64_t seed, int64_t ray0, int Sc, int K, float* __restrict__ z_fine, float* __restrict__ z_samples,
                              int64_t* __restrict__ inds, float* __restrict__ z_std, int zstd_ld, int64_t n_rays) {
   extern __shared__ float sm[];
@@ -114,6 +115,7 @@ __global__ void k_importance(const float* __restrict__ z0, const float* __restri
   io.z0 = sz; io.w0 = sw; io.cdf = base + 2 * Sc; io.bins = base + 3 * Sc; io.zall = base + 4 * Sc;
   io.zsorted = z_fine + r * (Sc + K);
   io.u = u ? u + r * K : nullptr;
+  io.z_inject = z_inject ? z_inject + r * K : nullptr;
   io.z_samples = z_samples ? z_samples + r * K : nullptr;
   io.inds = inds ? inds + r * K : nullptr;
   io.z_std = z_std ? z_std + r * zstd_ld : nullptr;
@@ -365,7 +367,7 @@ int simt_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
   size_t need = carve_fwd(cfg, gc, gf, R, (char*)workspace, &w);
   NSOS_REQUIRE(workspace_bytes >= need, NSOS_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   const int C6 = 6 + gc.sem_dim, ML = 2 * C6 + 1;
-  NsosRandoms rn{nullptr, nullptr, nullptr, nullptr};
+  NsosRandoms rn{nullptr, nullptr, nullptr, nullptr, nullptr};
   if (rnd) rn = *rnd;
   NSOS_CHECK_CUDA(cudaMemsetAsync(out.maps, 0, sizeof(float) * n_rays * ML, st));
 
@@ -397,7 +399,8 @@ int simt_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
     // ---- importance resampling + fine pass (nerf_net.py:104-128)
     float* z1 = out.z_vals ? out.z_vals + r0 * Sf : w.z1;
     size_t smem = 4 * sizeof(float) * (5 * Sc + K);
-    k_importance<<<grid1(n * 32, 128), 128, smem, st>>>(w.z0, wts0, rn.u ? rn.u + r0 * K : nullptr, cfg.perturb, seed, r0, Sc, K, z1,
+    k_importance<<<grid1(n * 32, 128), 128, smem, st>>>(w.z0, wts0, rn.u ? rn.u + r0 * K : nullptr, rn.z_samples ? rn.z_samples + r0 * K : nullptr,
+                                                         cfg.perturb, seed, r0, Sc, K, z1,
                                                          out.z_samples ? out.z_samples + r0 * K : nullptr,
                                                          out.inds ? out.inds + r0 * K : nullptr, maps + 2 * C6, ML, n);
     k_encode_pts<<<grid1(n * Sf), 256, 0, st>>>(ro, rd, z1, w.enc, n * Sf, Sf, gf.Lp);
@@ -503,7 +506,7 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
     size_t need = carve_bwd_tc(cfg, gc, gf, R, (char*)workspace, &w);
     NSOS_REQUIRE(workspace_bytes >= need, NSOS_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
     const int C6 = 6 + gc.sem_dim, ML = 2 * C6 + 1;
-    NsosRandoms rn{nullptr, nullptr, nullptr, nullptr};
+    NsosRandoms rn{nullptr, nullptr, nullptr, nullptr, nullptr};
     if (rnd) rn = *rnd;
     for (int64_t r0 = 0; r0 < n_rays; r0 += R) {
       const int64_t n = std::min(R, n_rays - r0);
@@ -552,7 +555,7 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
   size_t need = carve_bwd(cfg, gc, gf, R, (char*)workspace, &w);
   NSOS_REQUIRE(workspace_bytes >= need, NSOS_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   const int C6 = 6 + gc.sem_dim, ML = 2 * C6 + 1;
-  NsosRandoms rn{nullptr, nullptr, nullptr, nullptr};
+  NsosRandoms rn{nullptr, nullptr, nullptr, nullptr, nullptr};
   if (rnd) rn = *rnd;
   for (int64_t r0 = 0; r0 < n_rays; r0 += R) {
     const int64_t n = std::min(R, n_rays - r0);

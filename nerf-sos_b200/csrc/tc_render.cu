@@ -4,8 +4,12 @@
 // resampling + sort (4 warps per ray, in shared memory) -> fine tiles -> composite -> one write of the
 // per-ray maps.  A tile is 128 sample points = the 128 TMEM lanes; the whole MLP of a tile runs without
 // leaving the SM:
-//   * activations live in TENSOR MEMORY as the MMA A operand (fp16 hi plane cols 256..383, lo plane cols
-//     384..511), the fp32 accumulator D in cols 0..255;  tcgen05.mma kind::f16, M=128, N<=256, K=16;
+//   * TENSOR MEMORY holds two 256-column buffers that alternate per stage: stage s accumulates D (fp32) into buffer s&1
+//     while reading its A operand from the other one.  The epilogue of a hidden layer converts D IN PLACE into the next
+//     layer's A operand: the 16 fp32 columns of K-step c become 8 columns of fp16 hi pairs + 8 columns of fp16 lo pairs
+//     (same bytes), so a layer's output never needs a third region -- and because the next stage writes the OTHER buffer,
+//     its MMAs start as soon as the first 64-column K slab has been converted (per-slab a_ready barriers): the epilogue
+//     of layer l runs under the MMAs of layer l+1.  tcgen05.mma kind::f16, M=128, N<=256, K=16;
 //   * weights stream from L2 through a ring of 32 KB shared-memory slots with cp.async.bulk (TMA engine,
 //     mbarrier complete_tx), pre-swizzled at pack time into the canonical K-major SWIZZLE_128B slabs;
 //   * NSOS_MODE_TC_EXACT splits activations and weights into fp16 hi+lo and issues A_hi.W_hi + A_lo.W_hi
@@ -55,7 +59,11 @@ __device__ __forceinline__ void regs_other() {}
 constexpr float kActScale = 16.f;      // activations are stored as fp16(16*a): keeps the lo plane out of fp16 subnormals
 constexpr int kMaxStages = 13;
 constexpr int kMaxSlabs = 5;
-constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384, kTmemCols = 512;
+constexpr int kCtabMax = kMaxStages * kMaxSlabs * 2;
+constexpr uint32_t kBufCols = 256, kTmemCols = 512;   // two D / A buffers (see the header comment); K-step c of a buffer: hi pairs
+constexpr uint32_t kAStep = 16, kALo = 8;              // at columns [16c, 16c+8), lo pairs at [16c+8, 16c+16)
+constexpr int kMaxASlabs = 5;                          // a_ready barriers: [0], [1] = K-steps 0-1 / 2-3 of slab 0 (early start of the
+                                                       // next layer), [1+j] = slab j >= 1 (W/64 slabs of 64 columns)
 constexpr int kGBytes = 128 * 128;     // gamma tile plane: 128 rows x 64 fp16, SWIZZLE_128B
 constexpr int kHalfMax = 128;          // W/2 max
 constexpr int kSemMax = 4;
@@ -274,6 +282,8 @@ __global__ void k_pack_slabs(const float* __restrict__ prm, uint8_t* __restrict_
 // ---- render kernel ------------------------------------------------------------------------------------
 struct TcParams {
   TcProg prog[2];
+  uint32_t ctab[2][kCtabMax];   // per-net chunk program of the MMA issuer (build_ctab)
+  int nch[2];
   const uint8_t* packed[2];
   const float *rays_o, *rays_d, *near, *far;
   NsosRandoms rnd;
@@ -289,13 +299,14 @@ struct TcParams {
   float* dump_h[2];    // [n_rays*S, W]   relu(pts_linears[D-1])
   float* dump_s0[2];   // [n_rays*S, W/2] relu(semantic_linear.0)
 };
-constexpr int kTraceTiles = 16, kTraceStamps = 6;   // [tile][stage][stamp]
+constexpr int kTraceTiles = 16, kTraceStamps = 12;  // [tile][stage][stamp]; 5..8: a_ready[j] seen by the MMA lane, 9..11: worker 0 hands over slab 0..2
 
 struct Smem {
   uint8_t* ring; uint8_t* g_hi; uint8_t* g_lo;
   float *rawbuf, *hpart, *zc, *w0, *cdf, *bins, *zall, *zf, *dirbias, *sbias, *heads, *rayp, *encv;
-  uint64_t *full, *empty, *acc_full, *a_ready;
+  uint64_t *full, *empty, *acc_full, *g_ready, *a_ready;   // a_ready[kMaxASlabs]
   uint32_t* tmem_ptr;
+  uint32_t* ctab;      // [2][kCtabMax] chunk program of the MMA issuer (copy of TcParams::ctab)
 };
 constexpr int kRayP = 16;  // per ray: o[3] d[3] near far |d| valid v[3] = d/|d| (+3 pad)
 
@@ -312,7 +323,8 @@ __host__ __device__ inline size_t carve_smem(uint8_t* base, int nslots, int Sc, 
   size_t o_db = take(sizeof(float) * 2 * 2 * kHalfMax, 16), o_sb = take(sizeof(float) * 2 * 256, 16);
   size_t o_heads = take(sizeof(float) * 2 * kHeadFloats, 16), o_rayp = take(sizeof(float) * 2 * kRayP, 16),
          o_encv = take(sizeof(float) * 2 * 28, 16);
-  size_t o_bar = take(sizeof(uint64_t) * (2 * kMaxSlots + 2), 8), o_tp = take(16, 16);
+  size_t o_bar = take(sizeof(uint64_t) * (2 * kMaxSlots + 2 + kMaxASlabs), 8), o_tp = take(16, 16);
+  size_t o_ct = take(sizeof(uint32_t) * 2 * kCtabMax, 16);
   if (s) {
     s->ring = base + o_ring; s->g_hi = base + o_ghi; s->g_lo = base + o_glo;
     s->rawbuf = (float*)(base + o_raw); s->hpart = (float*)(base + o_hp); s->zc = (float*)(base + o_zc); s->w0 = (float*)(base + o_w0);
@@ -320,7 +332,8 @@ __host__ __device__ inline size_t carve_smem(uint8_t* base, int nslots, int Sc, 
     s->zf = (float*)(base + o_zf); s->dirbias = (float*)(base + o_db); s->sbias = (float*)(base + o_sb);
     s->heads = (float*)(base + o_heads); s->rayp = (float*)(base + o_rayp); s->encv = (float*)(base + o_encv);
     s->full = (uint64_t*)(base + o_bar); s->empty = s->full + kMaxSlots; s->acc_full = s->empty + kMaxSlots;
-    s->a_ready = s->acc_full + 1; s->tmem_ptr = (uint32_t*)(base + o_tp);
+    s->g_ready = s->acc_full + 1; s->a_ready = s->g_ready + 1; s->tmem_ptr = (uint32_t*)(base + o_tp);
+    s->ctab = (uint32_t*)(base + o_ct);
   }
   return off;
 }
@@ -370,59 +383,118 @@ struct RingPos {
   __device__ __forceinline__ void advance(uint32_t nslots) { if (++slot == nslots) { slot = 0; par ^= 1u; } }
 };
 
-__device__ __forceinline__ void mma_tile(const TcProg& pg, bool exact, const Smem& sm, int nslots, uint32_t tm, RingPos& pos,
-                                         uint32_t& it, uint32_t csize, bool last_tile, long long* trace = nullptr) {
-  const uint32_t g_hi = smem_u32(sm.g_hi), g_lo = smem_u32(sm.g_lo);
-  const uint32_t ring = smem_u32(sm.ring), full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
-  const uint16_t mask = (uint16_t)((1u << csize) - 1u);
+// The issuer's program for one tile, flattened to one 32-bit word per weight chunk (= one K slab plane in the ring), built on
+// the host (kernel parameters) and copied to shared memory: the elected lane runs ONE small loop for the whole kernel.  Why:
+// whatever the issuer executes between the last MMA of layer l and the first MMA of layer l+1 sits on the critical path of
+// the layer pipeline, and an instruction of this warp costs ~10 cycles while the eight epilogue warps are busy (NSOS_TRACE
+// stamps: the old per-stage prologue -- stage descriptor reads, elect.sync, reconvergence -- took 2.5k cycles, the whole
+// overlap window; tools/pipe_overlap.cu: ten extra instructions per MMA double the time per MMA).  Measured alternative
+// (profiles/r02_notes.md): all 32 lanes in uniform control flow with an elect region per chunk gives textbook SASS (UTCHMMA
+// operands stay in uniform registers, no R2UR) but was 9 % slower end to end -- 32 lanes polling the barriers.
+//   bits 0-2 A source (0..3 = TMEM K slab, 7 = gamma tile in shared memory)   bits 3-8 N/8   bit 9 W_lo plane
+//   bit 10 first chunk of a stage   bit 11 last chunk of a stage   bit 12 also issue the A_lo pass (exact mode, W_hi plane)
+//   bits 13-15 / 16-18: a_ready barrier (+1; 0 = none) to wait for before K-step 0 / before K-step 2 of this chunk
+constexpr uint32_t kCtGamma = 7u, kCtLoPlane = 1u << 9, kCtFirst = 1u << 10, kCtLast = 1u << 11, kCtTwo = 1u << 12;
+constexpr int kCtWait0 = 13, kCtWait2 = 16;
+__host__ __device__ inline int build_ctab(const TcProg& pg, bool exact, uint32_t* tab) {
+  int n = 0;
   const int nplanes = exact ? 2 : 1;
   for (int st = 0; st < pg.nst; ++st) {
     const TcStage& S = pg.st[st];
-    mbar_wait(smem_u32(sm.a_ready), it & 1u, 200 + st);
-    ++it;
-    tc_fence_after();
-    if (trace) trace[st * kTraceStamps + 3] = clock64();        // a_ready observed by the MMA warp
-    const int nchunks = S.nslab * nplanes;
-    if (elect_one()) {
-      // The whole stage is issued by the elected lane inside ONE block: no reconvergence (= no wait for the MMA
-      // scoreboards) between chunks, so the tensor pipe queue never drains inside a stage.
-      RingPos cur = pos;
-      uint32_t accum = 0;
-      for (int j = 0; j < S.nslab; ++j) {
-        const int asrc = S.asrc[j];
-        const uint32_t idesc = make_idesc_f16(S.sn[j]);
-        for (int plane = 0; plane < nplanes; ++plane) {
-          // full[cur.slot] of THIS chunk was already waited for (inside the previous chunk, or before the first tile)
-          const uint32_t b = ring + cur.slot * kSlotBytes;
-          const uint32_t my_empty = empty0 + cur.slot * 8u;
-          RingPos nxt = cur;
-          nxt.advance(nslots);
-          const bool has_next = !(last_tile && st == pg.nst - 1 && j == S.nslab - 1 && plane == nplanes - 1);
-          const bool two = exact && plane == 0;     // plane 0 (W_hi): A_hi.W_hi (+ A_lo.W_hi);  plane 1 (W_lo): A_hi.W_lo
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t bd = make_sw128_desc(b + ks * 32);
-            const uint32_t acc = (ks == 0) ? accum : 1u;
-            if (ks == 3 && !two && has_next) { mbar_wait(full0 + nxt.slot * 8u, nxt.par, 300 + (int)nxt.slot); tc_fence_after(); }
-            if (asrc == A_GAMMA) umma_ss(tm + kColD, make_sw128_desc(g_hi + ks * 32), bd, idesc, acc);
-            else umma_ts(tm + kColD, tm + kColAhi + asrc * 32 + ks * 8, bd, idesc, acc);
-            if (two) {
-              if (ks == 3 && has_next) { mbar_wait(full0 + nxt.slot * 8u, nxt.par, 300 + (int)nxt.slot); tc_fence_after(); }
-              if (asrc == A_GAMMA) umma_ss(tm + kColD, make_sw128_desc(g_lo + ks * 32), bd, idesc, 1);
-              else umma_ts(tm + kColD, tm + kColAlo + asrc * 32 + ks * 8, bd, idesc, 1);
-            }
-          }
-          if (csize == 1) umma_commit(my_empty);
-          else umma_commit_multicast(my_empty, mask);
-          accum = 1;
-          cur = nxt;
+    for (int j = 0; j < S.nslab; ++j)
+      for (int plane = 0; plane < nplanes; ++plane) {
+        uint32_t w = (S.asrc[j] == A_GAMMA ? kCtGamma : (uint32_t)S.asrc[j]) | ((uint32_t)(S.sn[j] >> 3) << 3);
+        if (plane) w |= kCtLoPlane;
+        if (j == 0 && plane == 0) w |= kCtFirst;
+        if (j == S.nslab - 1 && plane == nplanes - 1) w |= kCtLast;
+        if (exact && plane == 0) w |= kCtTwo;
+        if (S.asrc[j] != A_GAMMA && plane == 0) {                  // first use of this TMEM slab in the stage
+          if (S.asrc[j] == 0) w |= (1u << kCtWait0) | (2u << kCtWait2);
+          else w |= (uint32_t)(S.asrc[j] + 2) << kCtWait0;
         }
+        tab[n++] = w;
       }
-      umma_commit(smem_u32(sm.acc_full));
+  }
+  return n;
+}
+
+// Issuer-side pipeline state that lives across tiles (registers of the elected lane): ring position, global stage counter
+// (selects the D buffer), phase parities of the gamma-tile barrier and of the per-slab A barriers (bit j = a_ready[j]).
+struct MmaState {
+  RingPos pos;
+  uint32_t gs, gpar, apar;
+};
+
+// All stages of one tile.  Called by the ELECTED LANE ONLY (the caller holds the elect block around the whole kernel loop).
+// Issue-side latency matters (tools/umma_queue.cu): the ring position is tracked incrementally, and the mbarrier wait for the
+// NEXT weight chunk is issued before the last MMA of the current one, where it overlaps with the MMAs already queued.
+// A TMEM K slab is consumed as soon as the previous layer's epilogue has converted it in place (a_ready[slab]) while the later
+// slabs of that buffer are still fp32 accumulator columns; the stage accumulates into the OTHER buffer, so epilogue(l) and
+// MMA(l+1) overlap.
+__device__ __forceinline__ void mma_tile(const uint32_t* __restrict__ tab, int nch, const Smem& sm, uint32_t nslots, uint32_t tm,
+                                         MmaState& ms, uint32_t csize, bool last_tile, long long* trace = nullptr) {
+  const uint32_t g_hi = smem_u32(sm.g_hi), g_lo = smem_u32(sm.g_lo);
+  const uint32_t ring = smem_u32(sm.ring), full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
+  const uint32_t a_ready0 = smem_u32(&sm.a_ready[0]), acc_full = smem_u32(sm.acc_full);
+  const uint16_t mask = (uint16_t)((1u << csize) - 1u);
+  // the gamma tile of this 128-point tile has been written (first stage, skip stage and semantic head read it)
+  mbar_wait(smem_u32(sm.g_ready), ms.gpar, 200);
+  ms.gpar ^= 1u;
+  tc_fence_after();
+  uint32_t accum = 0, dcol = 0, acol = 0;
+  int st = 0;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    const uint32_t w = tab[c];
+    const uint32_t asrc = w & 7u;
+    if (w & kCtFirst) {
+      dcol = tm + (ms.gs & 1u) * kBufCols;
+      acol = tm + ((ms.gs & 1u) ^ 1u) * kBufCols;
+      accum = 0;
+      if (trace) trace[st * kTraceStamps + 3] = clock64();      // stage issue starts
     }
-    __syncwarp();
-    for (int c = 0; c < nchunks; ++c) pos.advance(nslots);      // all lanes track the ring position
-    if (trace) trace[st * kTraceStamps + 4] = clock64();        // all MMAs of the stage issued
+    const uint32_t wait0 = (w >> kCtWait0) & 7u, wait2 = (w >> kCtWait2) & 7u;
+    if (wait0) {
+      mbar_wait(a_ready0 + (wait0 - 1u) * 8u, (ms.apar >> (wait0 - 1u)) & 1u, 210 + (int)wait0);
+      ms.apar ^= 1u << (wait0 - 1u);
+      tc_fence_after();
+      if (trace) trace[st * kTraceStamps + 5 + asrc] = clock64();
+    }
+    const uint32_t idesc = make_idesc_f16((int)((w >> 3) & 63u) << 3);
+    const uint32_t a_hi = acol + asrc * 64;
+    // full[pos.slot] of THIS chunk was already waited for (inside the previous chunk, or before the first tile)
+    const uint32_t b = ring + ms.pos.slot * kSlotBytes;
+    const uint32_t my_empty = empty0 + ms.pos.slot * 8u;
+    ms.pos.advance(nslots);
+    const bool has_next = !(last_tile && c == nch - 1);
+    const bool two = (w & kCtTwo) != 0;        // W_hi plane in exact mode: A_hi.W_hi + A_lo.W_hi;  W_lo plane: A_hi.W_lo
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t bd = make_sw128_desc(b + ks * 32);
+      const uint32_t acc = (ks == 0) ? accum : 1u;
+      if (ks == 3 && !two && has_next) { mbar_wait(full0 + ms.pos.slot * 8u, ms.pos.par, 300 + (int)ms.pos.slot); tc_fence_after(); }
+      if (ks == 2 && wait2) {                   // second half of slab 0
+        mbar_wait(a_ready0 + (wait2 - 1u) * 8u, (ms.apar >> (wait2 - 1u)) & 1u, 220);
+        ms.apar ^= 1u << (wait2 - 1u);
+        tc_fence_after();
+      }
+      if (asrc == kCtGamma) umma_ss(dcol, make_sw128_desc(g_hi + ks * 32), bd, idesc, acc);
+      else umma_ts(dcol, a_hi + ks * kAStep, bd, idesc, acc);
+      if (two) {
+        if (ks == 3 && has_next) { mbar_wait(full0 + ms.pos.slot * 8u, ms.pos.par, 300 + (int)ms.pos.slot); tc_fence_after(); }
+        if (asrc == kCtGamma) umma_ss(dcol, make_sw128_desc(g_lo + ks * 32), bd, idesc, 1);
+        else umma_ts(dcol, a_hi + ks * kAStep + kALo, bd, idesc, 1);
+      }
+    }
+    if (csize == 1) umma_commit(my_empty);
+    else umma_commit_multicast(my_empty, mask);
+    accum = 1;
+    if (w & kCtLast) {
+      umma_commit(acc_full);
+      ++ms.gs;
+      if (trace) trace[st * kTraceStamps + 4] = clock64();      // all MMAs of the stage issued
+      ++st;
+    }
   }
 }
 
@@ -478,11 +550,7 @@ __device__ __forceinline__ void encode_half(const float x[3], int L, int enc, bo
 
 // One 16-column chunk of an epilogue.  v = D read-out (already waited for).  x16 = 16*x = acc*inv16 + bias16
 // (+relu) feeds the fp32 head accumulators (head weights are pre-divided by 16) and/or becomes the next A operand.
-#ifdef NSOS_AB_X32
-constexpr int kCW = 32;   // epilogue chunk width in columns (one tcgen05.ld)
-#else
-constexpr int kCW = 16;
-#endif
+constexpr int kCW = 16;   // epilogue chunk width in columns (one tcgen05.ld) = one K-step of the next layer
 constexpr int kSW = 16;   // arithmetic sub-block of a chunk
 template <int KIND, bool EXACT, bool DUMP>
 __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
@@ -555,8 +623,9 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
     }
   }
   if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA) {
-    tmem_st8(tm_lane + kColAhi + (c0 >> 1), hi);
-    if (EXACT) tmem_st8(tm_lane + kColAlo + (c0 >> 1), lo);
+    // in place: the 16 fp32 accumulator columns just read become the fp16 hi / lo pairs of the same K-step
+    tmem_st8(tm_lane + c0, hi);
+    if (EXACT) tmem_st8(tm_lane + c0 + kALo, lo);
   }
 }
 
@@ -569,28 +638,41 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_
     epi_sub<KIND, EXACT, DUMP>(&v[kSW * sb], tm_lane, c0 + kSW * sb, inv16, bias, hw, sem_dim, hacc, hodd, gout, vmax);
 }
 __device__ __forceinline__ void tmem_ldc(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
-__device__ __forceinline__ void tmem_ldc(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
 __device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[16]) { tmem_wait_ld_fence16(r); }
-__device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[32]) { tmem_wait_ld_fence(r); }
 
+// tm_lane = TMEM address of this warp's lane quarter inside the stage's D buffer.
+// Head kinds: 16-column chunks [cb, ce).  Hidden kinds (the output becomes the next layer's A operand, in place): both warps
+// of a lane quarter work on the SAME 64-column K slab -- half hf takes two of the four chunks of slab j = 0 .. ce/2-1 -- and
+// hand the slab to the MMA warp once their part is stored, so the next stage's MMAs start after a fraction of the epilogue
+// instead of all of it.  Slab 0 is handed over in two halves (K-steps 0-1 after the first chunk of every warp, 2-3 after the
+// second): a_ready[0], a_ready[1]; slab j >= 1 uses a_ready[1+j].
 template <int KIND, bool EXACT, bool DUMP>
-__device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw, int sem_dim,
-                                         float* hacc, float* gout, float& vmax) {
-  // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+__device__ __forceinline__ void epi_kind(int cb, int ce, int hf, uint32_t tm_lane, float inv16, const float* bias, const float* hw,
+                                         int sem_dim, float* hacc, float* gout, float& vmax, uint32_t a_ready0, long long* trs = nullptr) {
+  constexpr bool SLAB = (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA);
+  // software pipeline: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
   uint32_t va[kCW], vb[kCW];
-  if (cb >= ce) return;
+  const int cnt = ce - cb;
+  if (cnt <= 0) return;
+  auto col = [&](int i) { return (SLAB ? (i < 2 ? 2 * i + hf : 4 * (i >> 1) + 2 * hf + (i & 1)) : (cb + i)) * kCW; };
+  auto hand_over = [&](uint32_t bar) { tmem_wait_st(); tc_fence_before(); mbar_arrive(a_ready0 + 8u * bar); };
   float* const hout = hacc;
   float he[4] = {0.f, 0.f, 0.f, 0.f}, ho[4] = {0.f, 0.f, 0.f, 0.f};
-  tmem_ldc(tm_lane + kColD + cb * kCW, va);
+  tmem_ldc(tm_lane + col(0), va);
   tmem_wait_ldc(va);
-  for (int c = cb; c < ce; c += 2) {
-    if (c + 1 < ce) tmem_ldc(tm_lane + kColD + (c + 1) * kCW, vb);
-    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, c * kCW, inv16, bias, hw, sem_dim, he, ho, gout, vmax);
-    if (c + 1 < ce) {
+  for (int i = 0; i < cnt; i += 2) {
+    if (i + 1 < cnt) tmem_ldc(tm_lane + col(i + 1), vb);
+    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, col(i), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
+    if (SLAB && i == 0) { hand_over(0u); if (trs) trs[9] = clock64(); }
+    if (i + 1 < cnt) {
       tmem_wait_ldc(vb);
-      if (c + 2 < ce) tmem_ldc(tm_lane + kColD + (c + 2) * kCW, va);
-      epi_chunk<KIND, EXACT, DUMP>(vb, tm_lane, (c + 1) * kCW, inv16, bias, hw, sem_dim, he, ho, gout, vmax);
-      if (c + 2 < ce) tmem_wait_ldc(va);
+      if (i + 2 < cnt) tmem_ldc(tm_lane + col(i + 2), va);
+      epi_chunk<KIND, EXACT, DUMP>(vb, tm_lane, col(i + 1), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
+      if (SLAB) {                       // my chunks of slab i/2 are stored
+        hand_over(1u + (uint32_t)(i >> 1));
+        if (trs && (i >> 1) < 2) trs[10 + (i >> 1)] = clock64();
+      }
+      if (i + 2 < cnt) tmem_wait_ldc(va);
     }
   }
   if (KIND == EPI_HIDDEN_SIGMA) hout[0] += he[0] + ho[0];
@@ -602,20 +684,22 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, uint32_t tm_lane, float
   }
 }
 
-// 16-column chunks [cb, ce) of a stage
 template <bool EXACT, bool DUMP = false>
-__device__ __forceinline__ void epilogue(int kind, int cb, int ce, uint32_t tm_lane, float inv16, const float* bias, const float* hw,
-                                         int sem_dim, float* hacc, float* gout, float& vmax) {
+__device__ __forceinline__ void epilogue(int kind, int cb, int ce, int hf, uint32_t tm_lane, float inv16, const float* bias,
+                                         const float* hw, int sem_dim, float* hacc, float* gout, float& vmax, uint32_t a_ready0,
+                                         long long* trs = nullptr) {
+#define NSOS_EPI(K) epi_kind<K, EXACT, DUMP>(cb, ce, hf, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax, a_ready0, trs)
   switch (kind) {
-    case EPI_HIDDEN: epi_kind<EPI_HIDDEN, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax); break;
-    case EPI_HIDDEN_SIGMA: epi_kind<EPI_HIDDEN_SIGMA, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax); break;
+    case EPI_HIDDEN: NSOS_EPI(EPI_HIDDEN); break;
+    case EPI_HIDDEN_SIGMA: NSOS_EPI(EPI_HIDDEN_SIGMA); break;
     case EPI_SEM:
-      if (sem_dim <= 2) epi_kind<EPI_SEM, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax);
-      else epi_kind<EPI_SEM_WIDE, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax);
+      if (sem_dim <= 2) NSOS_EPI(EPI_SEM);
+      else NSOS_EPI(EPI_SEM_WIDE);
       break;
-    case EPI_RGB: epi_kind<EPI_RGB, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax); break;
-    default: epi_kind<EPI_RAW, EXACT, DUMP>(cb, ce, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax); break;
+    case EPI_RGB: NSOS_EPI(EPI_RGB); break;
+    default: NSOS_EPI(EPI_RAW); break;
   }
+#undef NSOS_EPI
 }
 
 // chunk range (units of kCW columns) of worker half `hf` for a stage of n columns
@@ -629,7 +713,8 @@ __device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int wa
   if (threadIdx.x == 0) {
     for (int i = 0; i < nslots; ++i) { mbar_init(smem_u32(&sm.full[i]), 1); mbar_init(smem_u32(&sm.empty[i]), csize); }
     mbar_init(smem_u32(sm.acc_full), 1);
-    mbar_init(smem_u32(sm.a_ready), kWorkers);
+    mbar_init(smem_u32(sm.g_ready), kWorkers);
+    for (int i = 0; i < kMaxASlabs; ++i) mbar_init(smem_u32(&sm.a_ready[i]), kWorkers);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(smem_u32(sm.tmem_ptr), kTmemCols); tmem_relinquish(); }
@@ -671,29 +756,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
       }
   } else if (warp == kMmaWarp) {
     regs_other();
-    uint32_t it = 0;
-    RingPos pos{0u, 0u};
-    int ntile_seen = 0;
-    mbar_wait(smem_u32(&sm.full[0]), 0u, 299);                  // first weight chunk; later ones are pre-waited inside the blocks
-    tc_fence_after();
-    for (long long itp = 0; itp < iters; ++itp)
-      for (int pass = 0; pass < npass; ++pass) {
-        const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
-        for (int tile = 0; tile < ntiles; ++tile) {
-          long long* tr = nullptr;
-          if (P.trace && blockIdx.x == 0 && lane == 0 && ntile_seen < kTraceTiles - 1) tr = P.trace + (size_t)ntile_seen * 16 * kTraceStamps;
-          ++ntile_seen;
-          const bool last_tile = (itp == iters - 1) && (pass == npass - 1) && (tile == ntiles - 1);
-          mma_tile(P.prog[pass], EXACT, sm, P.nslots, tm, pos, it, csize, last_tile, tr);
+    for (int i = lane; i < 2 * kCtabMax; i += 32) sm.ctab[i] = P.ctab[i / kCtabMax][i % kCtabMax];
+    __syncwarp();
+    if (elect_one()) {
+      // ONE elect block around the whole kernel: the issuing lane never reconverges between stages or tiles
+      MmaState ms{RingPos{0u, 0u}, 0u, 0u, 0u};
+      int ntile_seen = 0;
+      mbar_wait(smem_u32(&sm.full[0]), 0u, 299);                // first weight chunk; later ones are pre-waited inside mma_tile
+      tc_fence_after();
+      for (long long itp = 0; itp < iters; ++itp)
+        for (int pass = 0; pass < npass; ++pass) {
+          const int S = pass ? P.Sf : P.Sc, ntiles = (2 * S + 127) / 128;
+          for (int tile = 0; tile < ntiles; ++tile) {
+            long long* tr = nullptr;
+            if (P.trace && blockIdx.x == 0 && ntile_seen < kTraceTiles - 1) tr = P.trace + (size_t)ntile_seen * 16 * kTraceStamps;
+            ++ntile_seen;
+            const bool last_tile = (itp == iters - 1) && (pass == npass - 1) && (tile == ntiles - 1);
+            mma_tile(sm.ctab + pass * kCtabMax, P.nch[pass], sm, (uint32_t)P.nslots, tm, ms, csize, last_tile, tr);
+          }
         }
-      }
+    }
+    __syncwarp();
   } else {
     // ================= row workers: 8 warps; warp w owns TMEM lanes 32*(w%4).. and column half w/4 =================
     regs_worker();
     const int q4 = warp & 3, hf = warp >> 2;
     const int row = q4 * 32 + lane;
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
-    uint32_t it_acc = 0, it_bias = 0;
+    uint32_t it_acc = 0, it_bias = 0, gs = 0;      // gs: global stage counter, selects the D buffer exactly as the MMA warp does
+    const uint32_t a_ready0 = smem_u32(&sm.a_ready[0]);
     int ntile_seen = 0;
     for (int net = 0; net < npass; ++net) {
       const TcAux* aux = reinterpret_cast<const TcAux*>(P.packed[net]);
@@ -804,8 +895,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           }
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(smem_u32(sm.a_ready));
-          if (tr) tr[15 * kTraceStamps + 1] = clock64();                   // gamma tile written, a_ready signalled
+          mbar_arrive(smem_u32(sm.g_ready));
+          if (tr) tr[15 * kTraceStamps + 1] = clock64();                   // gamma tile written, g_ready signalled
 
           float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0] sigma, [1..3] rgb, [4..7] sem (partial over my columns)
           float vmax = 0.f;
@@ -821,8 +912,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             const bool rgb_part = Sg.epi == EPI_RGB || (merged && hf == 1);
             const bool sem_part = merged && hf == 0;
             const float* bias = rgb_part ? (sm.dirbias + (pass * 2 + rl) * kHalfMax) : sb;
+            const bool hidden = Sg.epi == EPI_HIDDEN || Sg.epi == EPI_HIDDEN_SIGMA;
             int cb, ce;
-            if (merged) { cb = 0; ce = pg.H2 / kCW; } else chunk_range(Sg.n, hf, cb, ce);
+            if (merged) { cb = 0; ce = pg.H2 / kCW; }
+            else if (hidden) { cb = 0; ce = 2 * (Sg.n / 64); }             // two chunks of every 64-column K slab (see epi_kind)
+            else chunk_range(Sg.n, hf, cb, ce);
+            const uint32_t tm_d = tm_lane + (gs & 1u) * kBufCols;
+            ++gs;
             if (tr) tr[st * kTraceStamps + 0] = clock64();                 // worker starts waiting for the accumulator
             mbar_wait(smem_u32(sm.acc_full), it_acc & 1u, 500 + st);
             ++it_acc;
@@ -836,17 +932,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               if (sem_part && P.dump_s0[pass]) gout = P.dump_s0[pass] + pt * pg.H2;
             }
             const int kind = merged ? (hf ? EPI_RGB : EPI_SEM) : Sg.epi;
-            epilogue<EXACT, DUMP>(kind, cb, ce, tm_lane + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout, vmax);
+            epilogue<EXACT, DUMP>(kind, cb, ce, hf, tm_d + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout, vmax, a_ready0,
+                                  tr ? tr + st * kTraceStamps : nullptr);
             if (Sg.epi == EPI_HIDDEN_SIGMA && hf == 1) sm.hpart[row * 8] = hacc[0];   // sigma share of the upper column half
             if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
-            if (st + 1 < pg.nst) {
-              tmem_wait_st();
-              tc_fence_before();
-              mbar_arrive(smem_u32(sm.a_ready));
-            }
           }
-          // fp16(16*a) saturates at |a| > 4094: inf/NaN then reach the maps; the sticky status bit names the cause
-          if (!(vmax <= 65504.f) && P.out.status && rowvalid && rp[9] > 0.f) atomicOr(P.out.status, 1u);
+          // fp16(16*a) saturates at |a| > 4094 (inf hi plane, NaN lo plane -- which the next ReLU's fmaxf would quietly turn
+          // into 0): poison this point's colour / semantic outputs so the ray's maps are NaN, and name the cause in the
+          // sticky status word
+          if (!(vmax <= 65504.f)) {
+            hacc[0] = hacc[1] = hacc[4] = __int_as_float(0x7fc00000);
+            if (P.out.status && rowvalid && rp[9] > 0.f) atomicOr(P.out.status, 1u);
+          }
           // ---- emit the raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
           float* graw = (pass == 0 && P.fine) ? P.out.raw0 : P.out.raw;
           float* gr_row = (graw && rp[9] > 0.f) ? graw + ((size_t)ray * S + i) * P.C : nullptr;
@@ -919,6 +1016,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               io.z0 = rpx.z; io.w0 = wsm; io.cdf = sm.cdf + gr * P.Sc; io.bins = sm.bins + gr * P.Sc;
               io.zall = sm.zall + gr * P.Sf; io.zsorted = sm.zf + gr * P.Sf;
               io.u = (P.rnd.u && valid) ? P.rnd.u + ray * P.K : nullptr;
+              io.z_inject = (P.rnd.z_samples && valid) ? P.rnd.z_samples + ray * P.K : nullptr;
               io.z_samples = (P.out.z_samples && valid) ? P.out.z_samples + ray * P.K : nullptr;
               io.inds = (P.out.inds && valid) ? P.out.inds + ray * P.K : nullptr;
               io.z_std = valid ? P.out.maps + (size_t)ray * P.ML + 2 * P.C6 : nullptr;
@@ -944,6 +1042,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
 // ---- self test: D[128,N] = A[128,K] . W[N,K]^T through the same producer / MMA / epilogue code ----------------
 struct SelfParams {
   TcProg prog;
+  uint32_t ctab[kCtabMax];
+  int nch;
   const uint8_t* packed;
   const float* a;
   float* d;
@@ -963,11 +1063,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
     uint32_t chunk = 0;
     producer_tile(P.prog, P.packed, EXACT, sm, P.nslots, chunk, 0, 1, warp - kProducerWarp);
   } else if (warp == kMmaWarp) {
-    uint32_t it = 0;
-    RingPos pos{0u, 0u};
-    mbar_wait(smem_u32(&sm.full[0]), 0u, 299);
-    tc_fence_after();
-    mma_tile(P.prog, EXACT, sm, P.nslots, tm, pos, it, 1, true);
+    for (int i = lane; i < kCtabMax; i += 32) sm.ctab[i] = P.ctab[i];
+    __syncwarp();
+    if (elect_one()) {
+      MmaState ms{RingPos{0u, 0u}, 0u, 0u, 0u};
+      mbar_wait(smem_u32(&sm.full[0]), 0u, 299);
+      tc_fence_after();
+      mma_tile(sm.ctab, P.nch, sm, (uint32_t)P.nslots, tm, ms, 1, true);
+    }
+    __syncwarp();
   } else {
     const int q4 = warp & 3, hf = warp >> 2, row = q4 * 32 + lane;
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
@@ -988,8 +1092,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
           hi[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
           lo[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
         }
-        tmem_st8(tm_lane + kColAhi + (c0 >> 1), hi);
-        if (EXACT) tmem_st8(tm_lane + kColAlo + (c0 >> 1), lo);
+        tmem_st8(tm_lane + kBufCols + c0, hi);              // stage 0 reads its A operand from buffer 1, in-place K-step layout
+        if (EXACT) tmem_st8(tm_lane + kBufCols + c0 + kALo, lo);
       }
       tmem_wait_st();
     } else {
@@ -1001,14 +1105,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
     sm.sbias[t] = 0.f;
     named_bar_sync(1, kWorkers);
     tc_fence_before();
-    mbar_arrive(smem_u32(sm.a_ready));
+    mbar_arrive(smem_u32(sm.g_ready));
+    for (int j = 0; j < kMaxASlabs; ++j) mbar_arrive(smem_u32(&sm.a_ready[j]));
     mbar_wait(smem_u32(sm.acc_full), 0, 600);
     tc_fence_after();
     float dummy[4];
     int cb, ce;
     chunk_range(P.N, hf, cb, ce);
     float vm = 0.f;
-    epilogue<EXACT>(EPI_RAW, cb, ce, tm_lane, __ldg(&aux->inv_scale[0][0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)row * P.N, vm);
+    epilogue<EXACT>(EPI_RAW, cb, ce, hf, tm_lane, __ldg(&aux->inv_scale[0][0]), sm.sbias, nullptr, 0, dummy, P.d + (size_t)row * P.N, vm, 0u);
   }
   tc_fence_before();
   __syncthreads();
@@ -1083,6 +1188,7 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
   PackPlan plan;
   build_prog(gc, exact, P.prog[0], plan);
   build_prog(gf, exact, P.prog[1], plan);
+  for (int i = 0; i < 2; ++i) P.nch[i] = build_ctab(P.prog[i], exact, P.ctab[i]);
   P.packed[0] = (const uint8_t*)packed_c; P.packed[1] = (const uint8_t*)packed_f;
   P.rays_o = rays_o; P.rays_d = rays_d; P.near = near; P.far = far;
   if (rnd) P.rnd = *rnd;
@@ -1205,6 +1311,7 @@ int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in
   if (rc) return rc;
   // inv_scale for the single stage (k_pack_aux is skipped: no net geometry here)
   k_fix_scale<<<1, 1, 0, st>>>(reinterpret_cast<TcAux*>(scratch));
+  P.nch = build_ctab(P.prog, exact, P.ctab);
   P.packed = (const uint8_t*)scratch; P.a = a; P.d = d; P.K = K; P.N = N; P.a_in_tmem = a_in_tmem; P.nslots = 4;
   size_t need = carve_smem(nullptr, P.nslots, 2, 2, 8, nullptr) + 1024;
   if (exact) {

@@ -8,7 +8,9 @@ Extra, non-reference keyword arguments (all optional):
              exact = tcgen05 fp16 hi/lo split (fp32-equivalent), fast = single fp16 pass,
              simt = fp32 CUDA-core path, auto = exact when the geometry is covered else simt
     randoms  dict(t_rand, noise0, u, noise1) of CUDA tensors: inject the four random draws the reference
-             makes (parity tests); default is the in-kernel Philox stream seeded from torch's CPU generator
+             makes (parity tests); default is the in-kernel Philox stream seeded from torch's CPU generator.
+             Optional fifth entry z_samples [N, N_importance]: stage-wise hook, use these importance samples
+             instead of inverting the kernel's own cdf (fine-pass parity on the reference's sample positions)
     retz     also return 'z_vals'/'z_vals0', 'z_samples', 'inds'
     retmaps  also return 'maps', the packed [N, 2*(6+sem_dim)+1] per-ray output row the kernel writes
 """
@@ -93,7 +95,7 @@ class _RenderFn(torch.autograd.Function):
         ro = _lib.RenderOut(*[_lib.ptr(out.get(k)) for k in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
                                                              "z_samples", "inds")],
                             *[_lib.ptr(acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")], _lib.ptr(net._status(dev)))
-        rs = _lib.Randoms(*[_lib.ptr(rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
+        rs = _lib.Randoms(*[_lib.ptr(rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1", "z_samples")])
         flat_c, flat_f = want.get("flat") or (net.nerf.flat_params(), net.nerf_fine.flat_params())
         pk_c = net.nerf.packed(cfg.mode, force=net.training, flat=flat_c)
         pk_f = net.nerf_fine.packed(cfg.mode, force=net.training, flat=flat_f) if fine else pk_c
@@ -143,7 +145,7 @@ class _RenderFn(torch.autograd.Function):
             if m.use_semantics:
                 sem_ids |= {id(p) for p in m.semantic_linear.parameters()}
         trunk = int(any(r and id(p) not in sem_ids for p, r in zip(plist, ctx.req)))
-        rs = _lib.Randoms(*[_lib.ptr(ctx.rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1")])
+        rs = _lib.Randoms(*[_lib.ptr(ctx.rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1", "z_samples")])
         wsz = L.nsos_render_bwd_workspace_bytes(cfg, N, trunk)
         ws = net._workspace(wsz, dev)
         # the packed images of the forward call (parameters are unchanged between forward and backward)

@@ -271,8 +271,17 @@ def safe_ray_mask(ret, u, margin=2e-5):
 
 def _grads_safe(name, net, rays, draws, keys, seed):
     net.train()
+    cap = {}
+    orig = net.importance_sampler.sample_pdf
+
+    def sample_pdf(*a, **k):                     # capture the reference's own importance samples (sampler.py:132)
+        cap["z_samples"] = orig(*a, **k)
+        return cap["z_samples"]
+
+    net.importance_sampler.sample_pdf = sample_pdf
     with ReplayRandom(draws) as rp:
         ret = net(rays, (1.2, 12.0))
+    net.importance_sampler.sample_pdf = orig
     assert rp.i == 4
     safe = safe_ray_mask(ret, draws[2])
     g = torch.Generator().manual_seed(seed)
@@ -281,7 +290,8 @@ def _grads_safe(name, net, rays, draws, keys, seed):
     loss.backward()
     grads = {k: p.grad.numpy().copy() for k, p in net.named_parameters()}
     print(name, f"safe rays: {int(safe.sum())} of {safe.numel()}")
-    save(name, safe=safe.numpy(), gout={k: v.numpy() for k, v in tgt.items()}, grads=grads, loss=float(loss.detach()))
+    save(name, safe=safe.numpy(), gout={k: v.numpy() for k, v in tgt.items()}, grads=grads, loss=float(loss.detach()),
+         z_samples=cap["z_samples"].detach().numpy())
 
 
 def flower_all_param_grads():

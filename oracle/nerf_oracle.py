@@ -284,6 +284,23 @@ def render_rays(coarse: dict, fine: dict, rays_o, rays_d, near, far, *, n_sample
     return ret
 
 
+def fine_pass_on(sd: dict, ray_batch, z_fine, *, D_fine=8, white_bkgd=False, use_semantics=True, sem_with_coord=True,
+                 multires=10, multires_views=4) -> dict:
+    """The fine pass of render_rays (nerf_net.py:113-115) on GIVEN sorted sample depths z_fine [N, S]: fine MLP + compositing.
+    Stage-wise checker for rays whose importance samples legitimately differ from the reference's (ill-conditioned inverse
+    cdf in low-mass bins): whatever samples a kernel drew, its fine maps must equal this on the same samples."""
+    _, fine = split_state_dict(sd)
+    rays_o, rays_d = _f32(ray_batch[0]).reshape(-1, 3), _f32(ray_batch[1]).reshape(-1, 3)
+    nrm = np.sqrt((rays_d * rays_d).sum(-1, dtype=F32, keepdims=True)).astype(F32)
+    viewdirs = (rays_d / nrm).astype(F32)
+    z_fine = _f32(z_fine)
+    raw = nerf_mlp(fine, points(rays_o, rays_d, z_fine), viewdirs, D=D_fine, use_semantics=use_semantics,
+                   sem_with_coord=sem_with_coord, multires=multires, multires_views=multires_views)
+    ret = composite(raw, z_fine, rays_d, None, white_bkgd, use_semantics)
+    ret["raw"] = raw
+    return ret
+
+
 def nerfnet_forward(sd: dict, ray_batch, bounds, *, ray_chunk=1 << 15, **kw) -> dict:
     """NeRFNet.forward (nerf_net.py:132-195): flatten any leading ray shape, chunk loop, cat, unflatten.
     sd: full state_dict (torch tensors or numpy); ray_batch [2, ..., 3]."""

@@ -124,35 +124,64 @@ def test_cfg1_eval(mode):
     close(out["raw"], g["out"]["raw"], rtol=1e-4, atol=2e-4)
 
 
+def _same_samples(z_ours, z_ref, tol=1e-5):
+    """Rays whose importance samples equal the reference's to `tol`.  The inverse cdf is ill-conditioned in low-mass bins
+    (d sample / d cdf = bin width / denom, up to 1e4: a 1e-7 difference in a coarse weight moves such a sample by 1e-3 with
+    no index flip), so end-to-end fine-pass comparisons are made on these rays; the fine stage itself is pinned on ALL rays
+    by injecting the reference's samples (NsosRandoms.z_samples)."""
+    z_ours = z_ours.detach().cpu().numpy() if torch.is_tensor(z_ours) else z_ours
+    return np.abs(z_ours - z_ref).max(-1) <= tol
+
+
 @pytest.mark.parametrize("tag", ["flower", "fortress", "co3d_apple"])
 @pytest.mark.parametrize("mode", ["simt", "exact"])
 def test_checkpoint_eval(mode, tag):
     """BASELINE config[1] geometry (64+128 samples, D=8 W=256 + seg head) on every kind of shipped checkpoint: the stage-2
-    flower net, and the stage-1 fortress (configs[2]) / CO3D apple (configs[4]) nets with seeded semantic heads."""
+    flower net, and the stage-1 fortress (configs[2]) / CO3D apple (configs[4]) nets with seeded semantic heads.
+    Stage-wise contract: (a) coarse pass vs the reference, (b) sampler indices, (c) fine pass on the reference's own sample
+    positions -- each at 1e-4 on every ray -- then (d) the end-to-end maps."""
     net, g = fixture_net(tag, mode)
     net.eval()
     bounds = (float(g["near"]), float(g["far"]))
-    with torch.no_grad():
-        out = net(torch.from_numpy(g["rays"]).to(DEV), bounds, retz=True)
+    rays = torch.from_numpy(g["rays"]).to(DEV)
     ref, st = g["out"], g["stage"]
+    with torch.no_grad():
+        out = net(rays, bounds, retz=True)
+        fin = net(rays, bounds, retz=True, randoms={"z_samples": torch.from_numpy(st["z_samples"])})
+    # (a) coarse pass
     assert np.array_equal(out["z_vals0"].cpu().numpy(), st["z"])                 # coarse sample positions: bit-exact
     for k in ("rgb0", "acc0", "semantics0", "weights0"):
         close(out[k], ref[k], rtol=1e-4, atol=1e-4)
     # per-sample density: compare relu(sigma) with abs+rel tolerance (raw sigma crosses 0)
     close(torch.relu(out["raw0"][..., 3]), np.maximum(ref["raw0"][..., 3], 0), rtol=1e-4, atol=1e-3)
     close(torch.sigmoid(out["raw0"][..., :3]), 1 / (1 + np.exp(-ref["raw0"][..., :3])), rtol=1e-4, atol=1e-4)
+    # (b) sampler: interior indices (the u = 1.0 column sits on the cdf's end point, see the module docstring)
     flip = out["inds"].cpu().numpy() != st["inds"]
     assert flip[:, :-1].mean() <= 1e-3 and flip[:, -1].mean() <= 0.5, (flip[:, :-1].mean(), flip[:, -1].mean())
-    ok = ~flip.any(-1)                                                           # rays whose 128 indices all agree
-    assert ok.mean() >= 0.85, ok.mean()
-    for k in ("rgb", "acc", "semantics", "weights"):                             # non-flipped rays: the full contract
-        close(out[k][torch.from_numpy(ok).to(DEV)], ref[k][ok], rtol=1e-4, atol=1e-4)
-    hit = ok & (ref["acc"][:, 0] > 1e-3)                                         # depth is 1e10 where acc <= 1e-10 (renderer.py:72)
-    close(out["depth"][torch.from_numpy(hit).to(DEV)], ref["depth"][hit], rtol=1e-4, atol=1e-3)
-    for k in ("rgb", "acc", "semantics"):                                        # flipped rays: continuous except across flat bins
-        close(out[k], ref[k], rtol=1e-4, atol=1e-2)
-    dz = np.abs(out["z_std"].cpu().numpy() - ref["z_std"])
-    assert (dz[ok] < 1e-4).mean() >= 0.97
+    # (c) fine pass on the reference's samples: every ray, every map, per-sample weights
+    zf = np.sort(np.concatenate([st["z"], st["z_samples"]], -1), -1)
+    assert np.array_equal(fin["z_vals"].cpu().numpy(), zf)
+    for k in ("rgb", "acc", "semantics", "weights"):
+        close(fin[k], ref[k], rtol=1e-4, atol=1e-4)
+    hit = ref["acc"][:, 0] > 1e-3                                                # depth is 1e10 where acc <= 1e-10 (renderer.py:72)
+    close(fin["depth"][torch.from_numpy(hit).to(DEV)], ref["depth"][hit], rtol=1e-4, atol=1e-3)
+    close(fin["z_std"], ref["z_std"], rtol=1e-5, atol=1e-5)
+    # (d) end to end with the kernel's own sampler
+    same = _same_samples(out["z_samples"], st["z_samples"]) & ~flip.any(-1)
+    assert same.mean() >= 0.2, same.mean()
+    sd_ = torch.from_numpy(same).to(DEV)
+    for k in ("rgb", "acc", "semantics"):                                        # same sample set: the full contract on the maps
+        close(out[k][sd_], ref[k][same], rtol=1e-4, atol=1e-4)                   # (per-sample weights: pinned in (c); at a sharp
+                                                                                 # surface d w / d z ~ 30, so 1e-5 in z is 3e-4 in w)
+    # every other ray drew at least one sample elsewhere (moved low-mass sample, or the u = 1.0 knife edge): whatever it drew,
+    # its fine maps must equal the oracle's fine pass on the SAME sample depths
+    from oracle import nerf_oracle as O
+    oth = np.where(~same)[0]
+    if len(oth):
+        own = O.fine_pass_on(g["sd"] if tag != "flower" else load_golden("flower_weights")["sd"], g["rays"][:, oth],
+                             out["z_vals"][torch.from_numpy(oth).to(DEV)].cpu().numpy())
+        for k in ("rgb", "acc", "semantics", "weights"):
+            close(out[k][torch.from_numpy(oth).to(DEV)], own[k], rtol=1e-4, atol=1e-4)
     for k in ref:
         assert tuple(out[k].shape) == ref[k].shape, k
     mse = float(((out["rgb"].cpu().numpy() - ref["rgb"]) ** 2).mean())
@@ -163,7 +192,7 @@ def test_checkpoint_eval(mode, tag):
 def test_activation_range_guard():
     """Exact mode keeps activations as fp16(16*a): |a| > 4094 cannot be represented.  The shipped nets peak at 59 (fortress
     fine layer 7, recorded in the fixtures); a net that does overflow must say so (sticky device flag + non-finite maps),
-    never return plausible numbers."""
+    never return plausible numbers (inf/NaN planes alone would not do: fmaxf in the next ReLU maps NaN to 0)."""
     for tag in ("fortress", "co3d_apple"):
         am = load_golden(tag + "_eval_256")["amax"]
         assert max(float(v) for v in am.values()) < 4094 / 16                    # >= 16x headroom on every shipped layer
@@ -176,33 +205,42 @@ def test_activation_range_guard():
         net.nerf_fine.mlp.pts_linears[3].weight.mul_(3000.0)                     # hidden activations ~1e4
         out = net(rays, (1.2, 12.0))
     assert net.range_overflow()
-    assert not torch.isfinite(out["rgb"]).all()
+    assert torch.isnan(out["rgb"]).any() and torch.isnan(out["semantics"]).any()   # poisoned, not silently zeroed by the ReLUs
     assert not net.range_overflow()                                              # the flag is cleared by reading it
 
 
 def test_full_size_vs_numpy_oracle():
     """BASELINE configs[1] at its real size -- the bench's own 4096 rays -- against the numpy oracle (outside the repo's
-    kernels): persistent-CTA multi-iteration path, 14 ray pairs per CTA, tile tails."""
+    kernels): persistent-CTA multi-iteration path, 14 ray pairs per CTA, tile tails.  Same stage-wise protocol as above."""
     from oracle import nerf_oracle as O
     import bench
-    rays = bench.llff_rays(4096, 100)
+    rays_np = bench.llff_rays(4096, 100)
+    rays = torch.from_numpy(rays_np).to(DEV)
     net = flower_net("exact").eval()
+    ref = O.nerfnet_forward(load_golden("flower_weights")["sd"], rays_np, (bench.NEAR, bench.FAR), extras=True)
     with torch.no_grad():
-        out = net(torch.from_numpy(rays).to(DEV), (bench.NEAR, bench.FAR), retz=True)
-    ref = O.nerfnet_forward(load_golden("flower_weights")["sd"], rays, (bench.NEAR, bench.FAR), extras=True)
+        out = net(rays, (bench.NEAR, bench.FAR), retz=True)
+        fin = net(rays, (bench.NEAR, bench.FAR), retz=True, randoms={"z_samples": torch.from_numpy(ref["z_samples"])})
     assert np.array_equal(out["z_vals0"].cpu().numpy(), ref["z_vals0"])
     for k in ("rgb0", "acc0", "semantics0", "weights0"):
         close(out[k], ref[k], rtol=1e-4, atol=1e-4)
     flip = out["inds"].cpu().numpy() != ref["inds"]
     assert flip[:, :-1].mean() <= 1e-3 and flip[:, -1].mean() <= 0.5, (flip[:, :-1].mean(), flip[:, -1].mean())
-    ok = ~flip.any(-1)
-    okd = torch.from_numpy(ok).to(DEV)
+    assert np.array_equal(fin["z_vals"].cpu().numpy(), ref["z_vals"])
+    for k in ("rgb", "acc", "semantics", "weights"):                             # fine pass on the oracle's samples: all 4096 rays
+        close(fin[k], ref[k], rtol=1e-4, atol=1e-4)
+    close(fin["depth"], ref["depth"], rtol=1e-4, atol=1e-3)
+    same = _same_samples(out["z_samples"], ref["z_samples"]) & ~flip.any(-1)
+    assert same.mean() >= 0.2, same.mean()
+    sd_ = torch.from_numpy(same).to(DEV)
+    for k in ("rgb", "acc", "semantics"):
+        close(out[k][sd_], ref[k][same], rtol=1e-4, atol=1e-4)
+    oth = np.where(~same)[0]                                                     # rays that drew other samples: oracle on THEIR samples
+    own = O.fine_pass_on(load_golden("flower_weights")["sd"], rays_np[:, oth], out["z_vals"][torch.from_numpy(oth).to(DEV)].cpu().numpy())
     for k in ("rgb", "acc", "semantics", "weights"):
-        close(out[k][okd], ref[k][ok], rtol=1e-4, atol=1e-4)
-    close(out["depth"][okd], ref["depth"][ok], rtol=1e-4, atol=1e-3)
-    close(out["z_vals"][okd], ref["z_vals"][ok], rtol=0, atol=2e-5)
+        close(out[k][torch.from_numpy(oth).to(DEV)], own[k], rtol=1e-4, atol=1e-4)
     mse = float(((out["rgb"].cpu().numpy() - ref["rgb"]) ** 2).mean())
-    assert -10 * np.log10(max(mse, 1e-20)) > 80.0
+    assert -10 * np.log10(max(mse, 1e-20)) > 60.0     # one u = 1.0 knife-edge ray in 4096 can differ by 5e-2 (67 dB); checked above
 
 
 def test_flower_fast_mode_psnr():
@@ -222,20 +260,23 @@ def test_flower_train_injected_randoms(mode):
     out = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), randoms=rnd)
     for k in ("rgb0", "acc0", "semantics0", "weights0"):
         close(out[k], g["out"][k], rtol=1e-4, atol=1e-4)
-    safe = load_golden("flower_train_64_allgrads")["safe"]          # rays whose random u sit >= 2e-5 away from every cdf knot
-    for k in ("rgb", "acc", "semantics", "weights"):
-        close(out[k][torch.from_numpy(safe).to(DEV)], g["out"][k][safe], rtol=1e-4, atol=1e-4)
     d = np.abs(out["rgb"].detach().cpu().numpy() - g["out"]["rgb"]).max(-1)
     assert np.median(d) < 5e-5 and d.max() < 2e-2, (np.median(d), d.max())
+    # fine pass on the reference's own importance samples: every ray at the full contract
+    rnd["z_samples"] = torch.from_numpy(load_golden("flower_train_64_allgrads")["z_samples"]).to(DEV)
+    fin = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), randoms=rnd)
+    for k in ("rgb", "acc", "semantics", "weights"):
+        close(fin[k], g["out"][k], rtol=1e-4, atol=1e-4)
 
 
 def _safe_grad_run(net, g, gs):
-    """Forward with the recorded draws, loss = <outputs, cotangents>; the cotangents are zero on rays whose importance samples
-    sit within 2e-5 of a cdf knot (oracle/make_golden.py:safe_ray_mask), so an index flip cannot leak into the gradients."""
+    """Forward with the recorded draws and the reference's importance samples, loss = <outputs, cotangents> (the cotangents
+    are additionally zero on rays whose u sit within 2e-5 of a cdf knot, oracle/make_golden.py:safe_ray_mask)."""
     rnd = {k: torch.from_numpy(v).to(DEV) for k, v in g["rnd"].items()}
+    rnd["z_samples"] = torch.from_numpy(gs["z_samples"]).to(DEV)       # stage-wise: the fine pass runs on the reference's samples
     out = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), randoms=rnd)
     loss = sum((out[k] * torch.from_numpy(v).to(DEV)).sum() for k, v in gs["gout"].items())
-    assert abs(loss.item() - float(gs["loss"])) <= 1e-3 * max(1.0, abs(float(gs["loss"])))
+    assert abs(loss.item() - float(gs["loss"])) <= 1e-4 * max(1.0, abs(float(gs["loss"])))
     loss.backward()
     return {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
 
@@ -256,11 +297,12 @@ def test_flower_semantic_head_gradients(mode):
         assert err <= 1e-3 * np.abs(ref).max(), (n, err, np.abs(ref).max())
 
 
-def test_flower_all_parameter_gradients():
+@pytest.mark.parametrize("mode", ["simt", "exact"])
+def test_flower_all_parameter_gradients(mode):
     """Stage-1 training (engines/trainer.py:201 with every parameter trainable) at D=8 W=256: all 1,274,124 gradients vs
     reference autograd, 1e-3 of each tensor's max."""
     g, gs = load_golden("flower_train_64_semgrads"), load_golden("flower_train_64_allgrads")
-    net = flower_net("exact", perturb=1.0, raw_noise_std=1.0).train()
+    net = flower_net(mode, perturb=1.0, raw_noise_std=1.0).train()
     got = _safe_grad_run(net, g, gs)
     assert set(got) == set(gs["grads"])
     assert sum(v.numel() for v in got.values()) == 1274124
@@ -319,8 +361,9 @@ def test_cfg1_full_gradients():
     g, gs = load_golden("cfg1_d4w64_train_grads"), load_golden("cfg1_d4w64_train_grads_safe")
     net = cfg1_net("simt", g, n_importance=32, perturb=1.0, raw_noise_std=1.0).train()
     rnd = {k: torch.from_numpy(v).to(DEV) for k, v in g["rnd"].items()}
+    rnd["z_samples"] = torch.from_numpy(gs["z_samples"]).to(DEV)
     out = net(torch.from_numpy(g["rays"]).to(DEV), (1.2, 12.0), randoms=rnd)
-    for k in ("rgb0", "semantics0", "acc0"):
+    for k in ("rgb0", "semantics0", "acc0", "rgb", "semantics", "acc"):
         close(out[k], g["out"][k], rtol=1e-4, atol=1e-4)
     loss = sum((out[k] * torch.from_numpy(v).to(DEV)).sum() for k, v in gs["gout"].items())
     loss.backward()
@@ -404,8 +447,9 @@ def test_config_variants_vs_oracle(mode, variant):
     sem = ("semantics",) if variant != "no_sem" else ()
     for k in ("rgb0", "acc0", "weights0") + tuple(k + "0" for k in sem):
         close(out[k], ref[k], rtol=1e-4, atol=1e-4)
-    ok = torch.from_numpy(~(out["inds"].cpu().numpy() != ref["inds"]).any(-1)).to(DEV)
-    assert ok.float().mean().item() >= 0.9
+    okn = ~(out["inds"].cpu().numpy() != ref["inds"]).any(-1) & _same_samples(out["z_samples"], ref["z_samples"])
+    ok = torch.from_numpy(okn).to(DEV)
+    assert ok.float().mean().item() >= 0.2
     for k in ("rgb", "acc") + sem:                                   # every ray with the reference's sample set: the full contract
         close(out[k][ok], ref[k][ok.cpu().numpy()], rtol=1e-4, atol=1e-4)
     if variant == "no_sem":
@@ -431,9 +475,11 @@ def test_full_size_exact_vs_same_device_fp32():
     assert flip[:, :-1].float().mean().item() <= 1e-3 and flip[:, -1].float().mean().item() <= 0.5
     for k in ("rgb0", "acc0", "semantics0"):
         close(a[k], b[k].cpu().numpy(), rtol=1e-4, atol=1e-4)
-    ok = ~flip.any(-1)
+    ok = ~flip.any(-1) & ((a["z_samples"] - b["z_samples"]).abs().amax(-1) <= 1e-5)
+    assert ok.float().mean().item() >= 0.2
     for k in ("rgb", "acc", "semantics"):
         close(a[k][ok], b[k][ok].cpu().numpy(), rtol=1e-4, atol=1e-4)
+        close(a[k], b[k].cpu().numpy(), rtol=1e-4, atol=5e-3)
     # determinism and ray-permutation equivariance (rays are independent units)
     net = flower_net("exact").eval()
     with torch.no_grad():

@@ -15,7 +15,8 @@ with torch.no_grad():
     for _ in range(3):
         net(rays, (1.2, 12.0))
 torch.cuda.synchronize()
-tr = net._ws[:16 * 16 * 6 * 8].view(torch.int64).reshape(16, 16, 6).cpu().numpy()
+NS = 12
+tr = net._ws[:16 * 16 * NS * 8].view(torch.int64).reshape(16, 16, NS).cpu().numpy()
 print(f"mode={mode}: stamps of CTA 0 (cycles). per stage: acc_wait = worker waits for MMA; epi = epilogue (thread 0);")
 print("mma_lead = a_ready seen by MMA warp -> accumulator ready (MMA execution incl. issue); issue = MMA warp issue time")
 for tile in range(8):
@@ -30,7 +31,12 @@ for tile in range(8):
     tot = t[nst - 1, 2] - t[0, 0]
     print(f"tile {tile}: {nst} stages, total {tot} cycles;  sum acc_wait {sum(r[1] for r in rows)}  sum epi {sum(r[2] for r in rows)}  sum mma_exec {sum(r[3] for r in rows)}")
     if tile in (1, 2, 3, 4):
-        for r in rows: print(f"    stage {r[0]:2d}: acc_wait {r[1]:6d}  epi {r[2]:6d}  mma_exec {r[3]:6d}  issue {r[4]:6d}")
+        for r in rows:
+            st = r[0]
+            acc = t[st, 1]          # accumulator of stage st ready = its epilogue starts; slabs are then handed to stage st+1
+            seen = [int(t[st + 1, 5 + j] - acc) if st + 1 < nst and t[st + 1, 5 + j] else None for j in range(4)]
+            gave = [int(t[st, 9 + j] - acc) if t[st, 9 + j] else None for j in range(3)]
+            print(f"    stage {st:2d}: acc_wait {r[1]:6d}  epi {r[2]:6d}  mma_exec {r[3]:6d}  issue {r[4]:6d}   slab handed over at {gave}, seen by the next stage's MMA lane at {seen} (cycles after this epilogue started)")
     print(f"    setup (z, point, gamma -> smem) {t[15, 1] - t[15, 0]};  first acc wait starts {t[0, 0] - t[15, 1]} after a_ready;  tail (head combine, raw) {t[15, 2] - t[nst - 1, 2]}")
     if tile + 1 < 16 and tr[tile + 1][15, 0] > 0:
         print(f"    end of tile -> next tile's setup start (composite / resample / pair setup): {tr[tile + 1][15, 0] - t[15, 2]}")
