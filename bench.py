@@ -226,14 +226,89 @@ class _Loader:
         def radii(): return None
 
 
+def train_bench(dev, local, rank, world, dist, mode, steps, warmup, all_params=False, collect_clocks=True):
+    """Time the shipped stage-2 training step (the public train_one_step call, pinned host batch in, host read of the loss out)
+    with `world` ranks x 8 patches; returns the fields of a JSON line / of the default line's `train` block."""
+    import torch
+    from nerfsos_b200.engines.lr import LRScheduler
+    from nerfsos_b200.engines.optim import FusedAdam
+    from nerfsos_b200.engines.trainer import train_one_step
+    from nerfsos_b200.models.extractor import VitExtractor
+    from nerfsos_b200.models.nerf_net import NeRFNet
+    from nerfsos_b200.utils.image import CorrelationLoss, GeoCorrelationLoss
+
+    a = _TrainArgs()
+    B, Ps = a.batch_size, a.patch_size
+    n_rays = B * Ps * Ps
+    net = NeRFNet(N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, use_semantics=True, sem_with_coord=True, sem_dim=2, perturb=1.0,
+                  raw_noise_std=1.0, mode=mode)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights().items()}, strict=True)
+    net = net.to(dev)
+    for n, p in net.named_parameters():
+        p.requires_grad_(all_params or "semantic_linear" in n)           # --fix_backbone (run_nerf.py:307-318) unless all_params
+    train_p = [p for p in net.parameters() if p.requires_grad]
+    opt = FusedAdam(train_p, lr=5e-4)
+    sched = LRScheduler(opt, 5e-4, 0.1, 250000)
+    losses = [None, None, CorrelationLoss(a), GeoCorrelationLoss(a)]
+    dino = VitExtractor("dino_vits16", device=dev)                   # seeded random-init ViT-S/16: no DINO checkpoint offline
+    rays_host = torch.from_numpy(llff_rays(n_rays, 200 + rank)).permute(1, 0, 2).reshape(B, Ps * Ps, 2, 3).contiguous().pin_memory()
+    gt_host = torch.rand(B, Ps * Ps, 3, generator=torch.Generator().manual_seed(rank)).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    it = [0]
+
+    def step():
+        # host -> device copy of the batch (what the DataLoader hands over), forward, losses, backward, all-reduce, Adam,
+        # and the host read of the logged loss: the whole train_one_step, end to end
+        it[0] += 1
+        out = train_one_step((rays_host, gt_host), [net, dino], opt, sched, _Loader(), it[0], losses, dev, a)
+        return float(out["loss"].detach())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warmup = max(warmup, 3)
+    for _ in range(warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0 and collect_clocks:
+        clocks.start()
+    evs = []
+    barrier()
+    for _ in range(steps):
+        flush.fill_(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    total_ms = float(sum(x.elapsed_time(y) for x, y in evs))
+    clk = clocks.stop() if (rank == 0 and collect_clocks) else None
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = tt.item() / steps
+    n_grad = sum(p.numel() for p in train_p)
+    sd = 2
+    gather_row = 2 * Ps * Ps * sd + 7 * Ps * Ps + 196 * 384 + 384          # floats per patch in the packed all-gather
+    return {
+        "ms_per_step": ms_step, "rays_per_s": world * n_rays / (ms_step * 1e-3), "rays_per_gpu": n_rays, "steps": steps, "warmup": warmup,
+        "trainable_params": n_grad, "recipe": "all parameters" if all_params else "--fix_backbone (semantic heads)",
+        "collectives_per_step": 0 if world == 1 else 4,
+        "allgather_bytes_per_rank": 0 if world == 1 else 4 * B * gather_row,
+        "allreduce_bytes": 0 if world == 1 else 4 * (n_grad + 2 * world * B * sd * Ps * Ps + 6 + 16),
+        "h2d_bytes_per_step": int((rays_host.numel() + gt_host.numel()) * 4), "d2h_bytes_per_step": 4,
+        "final_loss": loss, "clocks": clk,
+    }
+
+
 def run_train(args):
     import torch
     import nerfsos_b200  # noqa: F401
     from nerfsos_b200 import _lib
-    from nerfsos_b200.engines.lr import LRScheduler
-    from nerfsos_b200.engines.trainer import train_one_step
-    from nerfsos_b200.models.nerf_net import NeRFNet
-    from nerfsos_b200.utils.image import CorrelationLoss, GeoCorrelationLoss
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -247,93 +322,45 @@ def run_train(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
-    a = _TrainArgs()
-    B, Ps = a.batch_size, a.patch_size
-    n_rays = B * Ps * Ps
-    net = NeRFNet(N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, use_semantics=True, sem_with_coord=True, sem_dim=2, perturb=1.0,
-                  raw_noise_std=1.0, mode=args.mode)
-    net.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights().items()}, strict=True)
-    net = net.to(dev)
-    for n, p in net.named_parameters():
-        p.requires_grad_("semantic_linear" in n)                          # --fix_backbone (run_nerf.py:307-318)
-    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=5e-4)
-    sched = LRScheduler(opt, 5e-4, 0.1, 250000)
-    losses = [None, None, CorrelationLoss(a), GeoCorrelationLoss(a)]
-    from nerfsos_b200.models.extractor import VitExtractor
-    dino = VitExtractor("dino_vits16", device=dev)                   # seeded random-init ViT-S/16: no DINO checkpoint offline
-    rays_host = torch.from_numpy(llff_rays(n_rays, 200 + rank)).permute(1, 0, 2).reshape(B, Ps * Ps, 2, 3).contiguous().pin_memory()
-    gt_host = torch.rand(B, Ps * Ps, 3, generator=torch.Generator().manual_seed(rank)).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    it = [0]
-
-    def step():
-        # host -> device copy of the batch (what the DataLoader hands over), forward, losses, backward, all-reduce, Adam,
-        # and the .item() reads of the logged scalars: the whole train_one_step, end to end
-        it[0] += 1
-        out = train_one_step((rays_host, gt_host), [net, dino], opt, sched, _Loader(), it[0], losses, dev, a)
-        return float(out["loss"].detach()) if hasattr(out["loss"], "detach") else float(out["loss"])
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    clocks = ClockSampler(local)
+    r = train_bench(dev, local, rank, world, dist, args.mode, args.steps, args.warmup, all_params=args.all_params)
     if rank == 0:
-        clocks.start()
-    evs = []
-    barrier()
-    for _ in range(args.steps):
-        flush.fill_(0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        loss = step()
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
-    total_ms = float(sum(x.elapsed_time(y) for x, y in evs))
-    clk = clocks.stop() if rank == 0 else None
-    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms = tt.item()
-    if rank == 0:
-        ms_step = total_ms / args.steps
-        value = world * n_rays * args.steps / (total_ms * 1e-3)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        # forward as the reference evaluates it + semantic-head backward (dW0, dW2, d s_hid): 2*(128*319 + 2*128 + 2*128) FLOP/point
-        flop_ray = FLOP_PER_RAY + 256 * 2 * (128 * 319 + 2 * 2 * 128)
-        achieved = n_rays * flop_ray / (ms_step * 1e-3) / 1e12
-        line = {
-            "metric": "rays/sec fwd+bwd (training step, 64c+128f samples, D=8 W=256)", "value": value, "unit": "rays/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
-            "dtype": {"exact": "f16x2-split forward, bf16x2-split weight gradients (fp32 accumulate)", "fast": "f16 forward", "simt": "f32"}[args.mode],
-            "data": "synthetic",
-            "config": {"workload": "stage-2 training step: 8 patches x 64x64 rays per GPU, (64+128) samples, D=8 W=256 + seg head, "
-                                   "--fix_backbone, appearance + geometry correlation losses, Adam (BASELINE configs[2])",
-                       "rays_per_gpu": n_rays, "mode": args.mode, "weights": "shipped flower stage-2 checkpoint (fixture)",
-                       "features": "DINO ViT-S/16 provider (nerfsos_b200.models.extractor) with seeded random-init weights (no checkpoint offline)",
-                       "l2": "256 MB buffer written between timed steps (L2 flush, untimed)", "parallelism": f"patch-sharded x{world}"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                         "note": "whole step (render forward, both losses, backward, optimiser) against the tensor peak"},
-            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": int((rays_host.numel() + gt_host.numel()) * 4),
-                    "d2h_bytes_per_step": 4 * 8,
-                    "note": "the timed step IS the public train_one_step call with pinned host batches and host reads of the logged scalars"},
-            "gpu_launches": 99 * args.steps,       # own kernels per step, counted in profiles/r01_launches_bench_train_v3_summary.csv
-            "clocks": clk, "final_loss": loss,
-        }
-        print(json.dumps(line))
+        print(json.dumps(train_line(r, args, world)))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def train_line(r, args, world):
+    """JSON line of `--workload train` from train_bench()'s numbers (pure function: covered by a CPU test)."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    n_rays, ms_step = r["rays_per_gpu"], r["ms_per_step"]
+    # forward as the reference evaluates it + backward: semantic-head only (dW0, dW2, d s_hid: 2*(128*319 + 2*128 + 2*128) FLOP/point)
+    # or the full 2x forward of dgrad + wgrad
+    all_params = r["recipe"] == "all parameters"
+    flop_ray = (3 * FLOP_PER_RAY) if all_params else (FLOP_PER_RAY + 256 * 2 * (128 * 319 + 2 * 2 * 128))
+    achieved = n_rays * flop_ray / (ms_step * 1e-3) / 1e12
+    return {
+        "metric": "rays/sec fwd+bwd (training step, 64c+128f samples, D=8 W=256)", "value": r["rays_per_s"], "unit": "rays/s", "n_gpus": world,
+        "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"exact": "f16x2-split forward, bf16x2-split weight gradients (fp32 accumulate)", "fast": "f16 forward", "simt": "f32"}[args.mode],
+        "data": "synthetic",
+        "config": {"workload": "stage-2 training step: 8 patches x 64x64 rays per GPU, (64+128) samples, D=8 W=256 + seg head, "
+                               f"{r['recipe']}, appearance + geometry correlation losses, fused Adam (BASELINE configs[2])",
+                   "rays_per_gpu": n_rays, "mode": args.mode, "weights": "shipped flower stage-2 checkpoint (fixture)",
+                   "features": "DINO ViT-S/16 provider (nerfsos_b200.models.extractor) with seeded random-init weights (no checkpoint offline)",
+                   "l2": "256 MB buffer written between timed steps (L2 flush, untimed)", "parallelism": f"patch-sharded x{world}"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "note": "whole step (render forward, both losses, backward, optimiser) against the sustained tensor peak"},
+        "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"],
+                "note": "the timed step IS the public train_one_step call with pinned host batches and a host read of the logged loss"},
+        "collectives": {k: r[k] for k in ("collectives_per_step", "allgather_bytes_per_rank", "allreduce_bytes")},
+        "gpu_launches": None, "clocks": r["clocks"], "final_loss": r["final_loss"],
+    }
 
 
 def main():
@@ -344,6 +371,8 @@ def main():
     ap.add_argument("--mode", default="exact", choices=["exact", "fast", "simt"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-block", action="store_true", help="skip the secondary training-step measurement of the default line")
+    ap.add_argument("--all-params", action="store_true", help="--workload train: every parameter trainable (stage-1 recipe)")
     ap.add_argument("--workload", default="eval", choices=["eval", "train", "image"],
                     help="eval = BASELINE configs[1] (headline, default); train = one --fix_backbone training step "
                          "(8 patches of 64x64 rays per GPU, correlation losses, Adam; BASELINE configs[2]); image = one "
@@ -403,6 +432,15 @@ def main():
             maps_host.copy_(out["maps"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    def step_e2e_dropin():
+        # the drop-in's own defaults (render_kwargs_test of the reference: retraw=True, nerf_net.py:57-69): every key the
+        # reference returns, incl. raw [N,192,6] / raw0 / weights, and the same host round trip of the ray maps
+        with torch.no_grad():
+            r = rays_host.to(dev, non_blocking=True)
+            out = net(r, (NEAR, FAR), retmaps=True)
+            maps_host.copy_(out["maps"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -430,60 +468,36 @@ def main():
     ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(ms))
     # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region) ----
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e = []
+    for fn in (step_e2e, step_e2e_dropin):
+        for _ in range(3):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        e2e.append(time.perf_counter() - t0)
     clk = clocks.stop() if rank == 0 else None
 
-    tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms] + e2e, dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s = tt.tolist()
+    total_ms, e2e_s, e2e_dropin_s = tt.tolist()
+    # ---- secondary measurement in the same run: the shipped training step (north_star's collective path: packed all-gather,
+    # old_mean / code-gradient / parameter-gradient all-reduces) with the real train_one_step, 8 patches per GPU
+    train = None
+    if not image and not args.no_train_block:
+        try:
+            train = train_bench(dev, local, rank, world, dist, args.mode, steps=min(args.steps, 8), warmup=3, collect_clocks=False)
+        except Exception as e:                                           # never lose the headline over the secondary block
+            train = {"error": repr(e)}
+            if dist is not None:
+                raise
     if rank == 0:
-        ms_step = total_ms / args.steps
-        value = n_total * args.steps / (total_ms * 1e-3)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_src = "measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-        achieved = n_local * FLOP_PER_RAY / (ms_step * 1e-3) / 1e12       # per GPU (rank 0's shard), algorithmic FLOPs of the reference
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(args.mode)
-        except Exception:
-            pass
-        passes = {"exact": 3, "fast": 1, "simt": 1}[args.mode]
-        line = {
-            "metric": "rays/sec (64c+128f samples, D=8 W=256)", "value": value, "unit": "rays/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if image else "weak", "vs_baseline": None,
-            "dtype": {"exact": "f16x2-split (fp32-equivalent, fp32 accumulate)", "fast": "f16 (fp32 accumulate)", "simt": "f32"}[args.mode],
-            "data": "synthetic",
-            "config": {"workload": ("synthetic LLFF 1008x756 full-image render (762048 rays sharded over the GPUs), (64+128) samples, D=8 W=256 "
-                                    "+ seg head, eval forward (BASELINE configs[3])") if image else
-                                   "flower_full 4096 rays x (64+128) samples, D=8 W=256 + seg head, eval forward (BASELINE configs[1])",
-                       "rays_per_gpu": n_local, "mode": args.mode, "weights": "shipped flower stage-2 checkpoint (fixture)",
-                       "l2": "256 MB buffer written between timed steps (L2 flush, untimed)", "parallelism": f"ray-sharded x{world}"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "note": f"algorithmic FLOPs (324.86 MFLOP/ray as the reference evaluates them); mode '{args.mode}' issues "
-                                 f"{passes} fp16 MMA pass(es) over 552,320 of the reference's 634,496 MACs per point (feature_linear is "
-                                 f"folded into views_linears.0 at pack time): {achieved * passes * ISSUED_FRAC:.1f} TFLOP/s issued = "
-                                 f"{achieved * passes * ISSUED_FRAC / peak:.3f} of peak"},
-            "e2e": {"value": n_total * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": int(rays_host.numel() * 4),
-                    "d2h_bytes_per_step": int(maps_host.numel() * 4)},
-            "gpu_launches": args.steps * 1,
-            "clocks": clk,
-            "wall_s_timed_region": t_wall,
-        }
+        m = dict(total_ms=total_ms, e2e_s=e2e_s, e2e_dropin_s=e2e_dropin_s, n_total=n_total, n_local=n_local, t_wall=t_wall, clk=clk,
+                 h2d=int(rays_host.numel() * 4), d2h=int(maps_host.numel() * 4))
+        line = eval_line(m, args, world, image, train)
         # parity beside the speed (BASELINE metric: "rays/sec ...; PSNR vs ref"): the same net and mode on the 256 rays whose
         # outputs the unmodified reference produced (tests/golden/flower_eval_256.npz, generated by oracle/make_golden.py)
         try:
@@ -507,6 +521,60 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def eval_line(m, args, world, image, train):
+    """JSON line of the default / image workload from the measured numbers (pure function: covered by a CPU test so that a
+    typo in the line-building code cannot take down a multi-GPU run)."""
+    ms_step = m["total_ms"] / args.steps
+    value = m["n_total"] * args.steps / (m["total_ms"] * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # isolated 3 ms launches run at burst clocks -> burst peak; the 0.5 s full-image launch runs under the power cap -> sustained
+    key = "bf16_tflops_sustained" if image else "bf16_tflops"
+    peak = float(peaks.get(key, 1400.0 if image else 1650.0))
+    peak_src = (f"measured {key} (MEASURED_PEAKS.json)" if key in peaks else
+                "fallback (B200_PROFILING.md): 1.4 PFLOP/s sustained / 1.65 PFLOP/s burst dense bf16")
+    achieved = m["n_local"] * FLOP_PER_RAY / (ms_step * 1e-3) / 1e12      # per GPU (rank 0's shard), algorithmic FLOPs of the reference
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(args.mode)
+    except Exception:
+        pass
+    passes = {"exact": 3, "fast": 1, "simt": 1}[args.mode]
+    line = {
+        "metric": "rays/sec (64c+128f samples, D=8 W=256)", "value": value, "unit": "rays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if image else "weak", "vs_baseline": None,
+        "dtype": {"exact": "f16x2-split (fp32-equivalent, fp32 accumulate)", "fast": "f16 (fp32 accumulate)", "simt": "f32"}[args.mode],
+        "data": "synthetic",
+        "config": {"workload": ("synthetic LLFF 1008x756 full-image render (762048 rays sharded over the GPUs), (64+128) samples, D=8 W=256 "
+                                "+ seg head, eval forward (BASELINE configs[3])") if image else
+                               "flower_full 4096 rays x (64+128) samples, D=8 W=256 + seg head, eval forward (BASELINE configs[1])",
+                   "rays_per_gpu": m["n_local"], "mode": args.mode, "weights": "shipped flower stage-2 checkpoint (fixture)",
+                   "l2": "256 MB buffer written between timed steps (L2 flush, untimed)", "parallelism": f"ray-sharded x{world}"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "frac_vs_sustained": achieved / float(peaks.get("bf16_tflops_sustained", 1400.0)),
+                     "note": f"algorithmic FLOPs (324.86 MFLOP/ray as the reference evaluates them); mode '{args.mode}' issues "
+                             f"{passes} fp16 MMA pass(es) over 552,320 of the reference's 634,496 MACs per point (feature_linear is "
+                             f"folded into views_linears.0 at pack time): {achieved * passes * ISSUED_FRAC:.1f} TFLOP/s issued = "
+                             f"{achieved * passes * ISSUED_FRAC / peak:.3f} of peak"},
+        "e2e": {"value": m["n_total"] * args.steps / m["e2e_s"], "unit": "rays/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                "note": "NeRFNet.forward(host rays) -> host maps, retraw=False (north_star's single per-ray output row)"},
+        "e2e_dropin_defaults": {"value": m["n_total"] * args.steps / m["e2e_dropin_s"], "unit": "rays/s",
+                                "note": "same round trip with the reference's default kwargs (retraw=True: raw [N,192,6], raw0, weights "
+                                        "are also written, 25 MB per 4096 rays) -- what an unmodified eval_one_view / trainer caller gets"},
+        "gpu_launches": args.steps * 1,
+        "clocks": m["clk"],
+        "wall_s_timed_region": m["t_wall"],
+    }
+    if train is not None:
+        line["train"] = train
+    return line
 
 
 if __name__ == "__main__":

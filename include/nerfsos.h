@@ -192,6 +192,42 @@ int nsos_app_corr_loss(const float* feats, const float* nfeats, const float* cod
                        int32_t Cf, int32_t C, int32_t S, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* Sharded evaluation of the two losses (data-parallel training: every rank owns B_total/G whole patches; negatives may live on
+ * another rank, utils/image.py:354,359,473).  phase 1 computes the row means of this rank's query patches and writes the partial
+ * sums of the two helpers (negative, self) to sums[0..1]; the caller all-reduces them (one scalar pair per loss call -- the
+ * batch-wide `old_mean` of image.py:316-319 / :420-424) and calls phase 2 with the SAME workspace, which evaluates this rank's
+ * share of the loss (already divided by the GLOBAL pair count) and the code gradients.  Summing loss and g_code over the ranks
+ * gives exactly the single-GPU result on the global batch.
+ *   geometry loss:   xyz / code / neg_idx / g_code describe all B = B_total patches (gathered); queries are [q0, q0+nq)
+ *   appearance loss: the sampled tensors describe this rank's B query patches; q0 / nq are ignored */
+typedef struct NsosLossShard {
+  int32_t q0, nq;
+  int32_t B_total;
+  int32_t phase;      /* 0: everything in one call; 1: row means + partial sums; 2: loss + gradients from the global sums */
+  double* sums;       /* [2] DEVICE */
+} NsosLossShard;
+int nsos_geo_corr_loss_sharded(const float* xyz, const float* code, const int64_t* neg_idx, const float* params, float* loss,
+                               float* g_code, int32_t B, int32_t C, int32_t M, const NsosLossShard* shard, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int nsos_app_corr_loss_sharded(const float* feats, const float* nfeats, const float* code, const float* ncode, const float* params,
+                               float* loss, float* g_code, float* g_ncode, int32_t B, int32_t Cf, int32_t C, int32_t S,
+                               const NsosLossShard* shard, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- optimiser step ------------------------------------------------------------------------------ */
+/* torch.optim.Adam(params, lr, betas=(0.9, 0.999)).step() of run_nerf.py:320 for a list of fp32 tensors in ONE launch, with the
+ * learning rate of this step (engines/lr.py:20-23: lr * decay_rate ** (step / decay_steps), evaluated by the caller).  `tensors`
+ * is a HOST array of device pointers; exp_avg / exp_avg_sq are the optimiser's state tensors (torch's state_dict names);
+ * `step` counts from 1 (bias corrections 1 - beta^step). */
+typedef struct NsosAdamTensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} NsosAdamTensor;
+int nsos_adam_multi(const NsosAdamTensor* tensors, int32_t n_tensors, float lr, float beta1, float beta2, float eps, int64_t step,
+                    void* stream);
+
 /* ---- self test of the tcgen05 building blocks ------------------------------------------------ */
 /* One CTA: D[128,N] = A[128,K] * W[N,K]^T through the same pack / bulk-copy / UMMA / TMEM code the
  * render kernel uses.  a [128,K], w [N,K] fp32 device; d [128,N] fp32 device.  a_in_tmem selects the

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "lib", "libnerfsos.so")
 if os.environ.get("NSOS_LIB"):      # A/B testing of kernel variants: load another build of the same library
     LIB_PATH = os.path.abspath(os.environ["NSOS_LIB"])
-SOURCES = ["api.cu", "simt_gemm.cu", "simt_render.cu", "tc_render.cu", "tc_wgrad.cu", "corr_loss.cu"]
+SOURCES = ["api.cu", "simt_gemm.cu", "simt_render.cu", "tc_render.cu", "tc_wgrad.cu", "corr_loss.cu", "optim.cu"]
 
 MODE_SIMT, MODE_TC_EXACT, MODE_TC_FAST = 0, 1, 2
 MODES = {"simt": MODE_SIMT, "exact": MODE_TC_EXACT, "fast": MODE_TC_FAST}
@@ -37,6 +37,14 @@ class Randoms(C.Structure):
 class RenderOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
                                           "z_samples", "inds", "h_last0", "s_hid0", "h_last", "s_hid", "status")]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("n", C.c_int64)]
+
+
+class LossShard(C.Structure):
+    _fields_ = [("q0", C.c_int32), ("nq", C.c_int32), ("B_total", C.c_int32), ("phase", C.c_int32), ("sums", C.c_void_p)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -93,6 +101,9 @@ def lib() -> C.CDLL:
         "nsos_geo_corr_loss": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),
         "nsos_app_corr_workspace_bytes": (sz, [i32, i32, i32, i32]),
         "nsos_app_corr_loss": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]),
+        "nsos_geo_corr_loss_sharded": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, P(LossShard), vp, sz, vp]),
+        "nsos_app_corr_loss_sharded": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, P(LossShard), vp, sz, vp]),
+        "nsos_adam_multi": (C.c_int, [P(AdamTensor), i32, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]),
         "nsos_selftest_umma": (C.c_int, [vp, vp, vp, i32, i32, C.c_int, C.c_int, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
@@ -108,7 +119,7 @@ EXPORTS = ["nsos_abi_version", "nsos_last_error", "nsos_param_count", "nsos_para
            "nsos_pack_weights", "nsos_render_workspace_bytes", "nsos_render_fwd", "nsos_render_bwd_workspace_bytes",
            "nsos_render_bwd", "nsos_invert_cdf", "nsos_mlp_workspace_bytes", "nsos_mlp_query",
            "nsos_geo_corr_workspace_bytes", "nsos_geo_corr_loss", "nsos_app_corr_workspace_bytes", "nsos_app_corr_loss",
-           "nsos_selftest_umma"]
+           "nsos_geo_corr_loss_sharded", "nsos_app_corr_loss_sharded", "nsos_adam_multi", "nsos_selftest_umma"]
 
 
 def check(rc: int, what: str):

@@ -136,15 +136,35 @@ size_t nsos_geo_corr_workspace_bytes(int32_t B, int32_t C, int32_t M) { return g
 int nsos_geo_corr_loss(const float* xyz, const float* code, const int64_t* neg_idx, const float* params, float* loss, float* g_code,
                        int32_t B, int32_t C, int32_t M, void* workspace, size_t workspace_bytes, void* stream) {
   NSOS_REQUIRE(xyz && code && neg_idx && params && loss, NSOS_ERR_BAD_ARG, "nsos_geo_corr_loss: null argument");
-  return geo_corr_loss(xyz, code, neg_idx, params, loss, g_code, B, C, M, workspace, workspace_bytes, (cudaStream_t)stream);
+  return geo_corr_loss(xyz, code, neg_idx, params, loss, g_code, B, C, M, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int nsos_geo_corr_loss_sharded(const float* xyz, const float* code, const int64_t* neg_idx, const float* params, float* loss,
+                               float* g_code, int32_t B, int32_t C, int32_t M, const NsosLossShard* shard, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  NSOS_REQUIRE(xyz && code && neg_idx && params && shard, NSOS_ERR_BAD_ARG, "nsos_geo_corr_loss_sharded: null argument");
+  return geo_corr_loss(xyz, code, neg_idx, params, loss, g_code, B, C, M, shard, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 size_t nsos_app_corr_workspace_bytes(int32_t B, int32_t Cf, int32_t C, int32_t S) { return app_corr_workspace_bytes(B, Cf, C, S); }
 int nsos_app_corr_loss(const float* feats, const float* nfeats, const float* code, const float* ncode, const float* params,
                        float* loss, float* g_code, float* g_ncode, int32_t B, int32_t Cf, int32_t C, int32_t S, void* workspace,
                        size_t workspace_bytes, void* stream) {
   NSOS_REQUIRE(feats && nfeats && code && ncode && params && loss, NSOS_ERR_BAD_ARG, "nsos_app_corr_loss: null argument");
-  return app_corr_loss(feats, nfeats, code, ncode, params, loss, g_code, g_ncode, B, Cf, C, S, workspace, workspace_bytes,
+  return app_corr_loss(feats, nfeats, code, ncode, params, loss, g_code, g_ncode, B, Cf, C, S, nullptr, workspace, workspace_bytes,
                        (cudaStream_t)stream);
+}
+int nsos_app_corr_loss_sharded(const float* feats, const float* nfeats, const float* code, const float* ncode, const float* params,
+                               float* loss, float* g_code, float* g_ncode, int32_t B, int32_t Cf, int32_t C, int32_t S,
+                               const NsosLossShard* shard, void* workspace, size_t workspace_bytes, void* stream) {
+  NSOS_REQUIRE(feats && nfeats && code && ncode && params && shard, NSOS_ERR_BAD_ARG, "nsos_app_corr_loss_sharded: null argument");
+  return app_corr_loss(feats, nfeats, code, ncode, params, loss, g_code, g_ncode, B, Cf, C, S, shard, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+
+int nsos_adam_multi(const NsosAdamTensor* tensors, int32_t n_tensors, float lr, float beta1, float beta2, float eps, int64_t step,
+                    void* stream) {
+  NSOS_REQUIRE(tensors || n_tensors == 0, NSOS_ERR_BAD_ARG, "nsos_adam_multi: null tensor list");
+  if (n_tensors <= 0) return NSOS_OK;
+  return adam_multi(tensors, n_tensors, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
 }
 
 int nsos_selftest_umma(const float* a, const float* w, float* d, int32_t N, int32_t K, int a_in_tmem, int mode, void* scratch,

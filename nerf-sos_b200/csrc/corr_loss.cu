@@ -46,9 +46,9 @@ __global__ void k_normalize(const float* __restrict__ code, float* __restrict__ 
 }
 
 // pass 1: rowmean[h,n,p] = mean_q min(15, 1/(|X_p - X'_q|_1 + 0.05))
-__global__ void __launch_bounds__(kT) k_geo_rowmean(const float* __restrict__ xyz, const int64_t* __restrict__ neg, GeoWs w, int B, int M) {
+__global__ void __launch_bounds__(kT) k_geo_rowmean(const float* __restrict__ xyz, const int64_t* __restrict__ neg, GeoWs w, int B, int M, int q0) {
   __shared__ float sx[3][kT];
-  const int n = blockIdx.y, h = blockIdx.z;
+  const int n = q0 + blockIdx.y, h = blockIdx.z;
   const int nb = (h == 0) ? (int)neg[n] : n;
   const int p = blockIdx.x * kT + threadIdx.x;
   const bool act = p < M;
@@ -73,19 +73,24 @@ __global__ void __launch_bounds__(kT) k_geo_rowmean(const float* __restrict__ xy
   if ((threadIdx.x & 31) == 0) atomicAdd(&w.acc[h], (double)v);
 }
 
-__global__ void k_oldmean(GeoWs w, int count) {
-  if (threadIdx.x < 2) w.oldmean[threadIdx.x] = (float)(w.acc[threadIdx.x] / (double)count);
+// old_mean[h] = (sum of all row means of the GLOBAL batch) / count; `sums` = w.acc on one GPU, the all-reduced partial sums
+// of every rank when the query patches are sharded
+__global__ void k_oldmean(GeoWs w, const double* sums, double count) {
+  if (threadIdx.x < 2) w.oldmean[threadIdx.x] = (float)(sums[threadIdx.x] / count);
+}
+__global__ void k_export_sums(const double* acc, double* sums) {
+  if (threadIdx.x < 2) sums[threadIdx.x] = acc[threadIdx.x];
 }
 
 // pass 2 (SECOND=false): thread per p of the first patch, loop over q of the second: loss + grad wrt chat[n,:,p]
 // pass 3 (SECOND=true):  thread per q of the second patch, loop over p of the first: grad wrt chat[nb,:,q]
 template <bool SECOND>
 __global__ void __launch_bounds__(kT) k_geo_pairs(const float* __restrict__ xyz, const int64_t* __restrict__ neg, GeoWs w, int B, int C, int M,
-                                                  float shift0, float shift1, float coef0, float coef1, int want_grad) {
+                                                  float shift0, float shift1, float coef0, float coef1, int want_grad, int q0) {
   __shared__ float sx[3][kT];
   __shared__ float sc[kCMax][kT];
   __shared__ float srm[kT];
-  const int n = blockIdx.y, h = blockIdx.z;
+  const int n = q0 + blockIdx.y, h = blockIdx.z;
   const int nb = (h == 0) ? (int)neg[n] : n;
   const float shift = h ? shift1 : shift0;
   const float coef = h ? coef1 : coef0;                  // weight_h / (B*M*M)
@@ -273,26 +278,37 @@ size_t geo_corr_workspace_bytes(int B, int C, int M) {
   return carve_geo(nullptr, B, C, M, nullptr);
 }
 
+// Sharding (NsosLossShard, include/nerfsos.h): the arrays hold all B patches of the global batch, this call evaluates the query
+// patches [q0, q0+nq); phase 1 leaves this rank's partial sums of the row means in sh->sums, the caller all-reduces them, phase 2
+// turns the GLOBAL sums into old_mean and evaluates loss + gradients with the global denominators.  Row means and normalised
+// codes stay in the workspace between the two phases.  sh == NULL: the whole batch in one call.
 int geo_corr_loss(const float* xyz, const float* code, const int64_t* neg_idx, const float* params, float* loss, float* g_code,
-                  int B, int C, int M, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                  int B, int C, int M, const NsosLossShard* sh, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   NSOS_REQUIRE(B > 0 && M > 0 && C > 0 && C <= kCMax, NSOS_ERR_UNSUPPORTED, "geo_corr_loss: need 1<=C<=%d", kCMax);
+  const int q0 = sh ? sh->q0 : 0, nq = sh ? sh->nq : B, phase = sh ? sh->phase : 0, Bt = sh ? sh->B_total : B;
+  NSOS_REQUIRE(q0 >= 0 && nq >= 0 && q0 + nq <= B && Bt >= B && phase >= 0 && phase <= 2, NSOS_ERR_BAD_ARG, "geo_corr_loss: bad shard descriptor");
+  NSOS_REQUIRE(phase == 0 || (sh && sh->sums), NSOS_ERR_BAD_ARG, "geo_corr_loss: phases 1/2 need shard->sums");
   GeoWs w;
   size_t need = carve_geo((char*)workspace, B, C, M, &w);
   NSOS_REQUIRE(workspace && workspace_bytes >= need, NSOS_ERR_WORKSPACE, "geo_corr_loss: workspace too small (%zu < %zu)", workspace_bytes, need);
   const float self_shift = params[0], self_w = params[1], neg_shift = params[2], neg_w = params[3];   // HOST array
-  NSOS_CHECK_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 4, st));
-  if (g_code) NSOS_CHECK_CUDA(cudaMemsetAsync(w.g_chat, 0, sizeof(float) * B * C * M, st));
   const int nb = (B * M + 255) / 256;
-  k_normalize<<<nb, 256, 0, st>>>(code, w.chat, w.invn, B, C, M);
-  dim3 grid((M + kT - 1) / kT, B, 2);
-  k_geo_rowmean<<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, M);
-  k_oldmean<<<1, 32, 0, st>>>(w, B * M);
-  const double denom = (double)B * M * M;
+  dim3 grid((M + kT - 1) / kT, nq, 2);
+  if (phase != 2) {
+    NSOS_CHECK_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 4, st));
+    k_normalize<<<nb, 256, 0, st>>>(code, w.chat, w.invn, B, C, M);
+    if (nq > 0) k_geo_rowmean<<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, M, q0);
+    if (phase == 1) { k_export_sums<<<1, 32, 0, st>>>(w.acc, sh->sums); NSOS_CHECK_CUDA(cudaGetLastError()); return NSOS_OK; }
+  }
+  NSOS_REQUIRE(loss, NSOS_ERR_BAD_ARG, "geo_corr_loss: loss pointer missing");
+  if (g_code) NSOS_CHECK_CUDA(cudaMemsetAsync(w.g_chat, 0, sizeof(float) * B * C * M, st));
+  k_oldmean<<<1, 32, 0, st>>>(w, phase == 2 ? sh->sums : w.acc, (double)Bt * M);
+  const double denom = (double)Bt * M * M;
   // helper 0 = negative pair (neg_shift, neg_weight), helper 1 = self pair (image.py:476-482)
   const float coef0 = (float)(neg_w / denom), coef1 = (float)(self_w / denom);
-  k_geo_pairs<false><<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, g_code != nullptr);
+  if (nq > 0) k_geo_pairs<false><<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, g_code != nullptr, q0);
   if (g_code) {
-    k_geo_pairs<true><<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, 1);
+    if (nq > 0) k_geo_pairs<true><<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, 1, q0);
     k_normalize_bwd<<<nb, 256, 0, st>>>(w.chat, w.invn, w.g_chat, g_code, B, C, M);
   }
   k_finish_loss<<<1, 32, 0, st>>>(w.acc, loss, neg_w / denom, self_w / denom);
@@ -305,24 +321,33 @@ size_t app_corr_workspace_bytes(int B, int Cf, int C, int S) {
   return carve_app(nullptr, B, Cf, C, S, nullptr);
 }
 
+// Sharded use: feats / nfeats / code / ncode hold this rank's B query patches (and their negatives, sampled by the caller from the
+// gathered tensors); only the denominators (B_total) and old_mean (global sums of the row means, phases 1/2) are global.
 int app_corr_loss(const float* feats, const float* nfeats, const float* code, const float* ncode, const float* params, float* loss,
-                  float* g_code, float* g_ncode, int B, int Cf, int C, int S, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                  float* g_code, float* g_ncode, int B, int Cf, int C, int S, const NsosLossShard* sh, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
   NSOS_REQUIRE(B > 0 && Cf > 0 && C > 0 && S > 0, NSOS_ERR_BAD_ARG, "app_corr_loss: bad sizes");
+  const int phase = sh ? sh->phase : 0, Bt = sh ? sh->B_total : B;
+  NSOS_REQUIRE(Bt >= B && phase >= 0 && phase <= 2 && (phase == 0 || (sh && sh->sums)), NSOS_ERR_BAD_ARG, "app_corr_loss: bad shard descriptor");
   AppWs w;
   size_t need = carve_app((char*)workspace, B, Cf, C, S, &w);
   NSOS_REQUIRE(workspace && workspace_bytes >= need, NSOS_ERR_WORKSPACE, "app_corr_loss: workspace too small (%zu < %zu)", workspace_bytes, need);
   const float self_shift = params[0], self_w = params[1], neg_shift = params[2], neg_w = params[3];   // HOST array
   const bool want = g_code != nullptr && g_ncode != nullptr;
-  NSOS_CHECK_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 4, st));
-  NSOS_CHECK_CUDA(cudaMemsetAsync(w.g_chat, 0, sizeof(float) * 2 * B * C * S, st));
   const int nb = (B * S + 255) / 256;
-  k_app_normalize<<<nb, 256, 0, st>>>(feats, w.fhat, nullptr, B, Cf, S);
-  k_app_normalize<<<nb, 256, 0, st>>>(nfeats, w.fhat + (size_t)B * Cf * S, nullptr, B, Cf, S);
-  k_app_normalize<<<nb, 256, 0, st>>>(code, w.chat, w.invn, B, C, S);
-  k_app_normalize<<<nb, 256, 0, st>>>(ncode, w.chat + (size_t)B * C * S, w.invn + (size_t)B * S, B, C, S);
-  k_app_fd<<<dim3(S, B, 2), 128, 0, st>>>(w, B, Cf, S);
-  k_oldmean<<<1, 32, 0, st>>>(GeoWs{nullptr, nullptr, nullptr, nullptr, w.acc, w.oldmean}, B * S);
-  const double denom = (double)B * S * S;
+  if (phase != 2) {
+    NSOS_CHECK_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 4, st));
+    k_app_normalize<<<nb, 256, 0, st>>>(feats, w.fhat, nullptr, B, Cf, S);
+    k_app_normalize<<<nb, 256, 0, st>>>(nfeats, w.fhat + (size_t)B * Cf * S, nullptr, B, Cf, S);
+    k_app_normalize<<<nb, 256, 0, st>>>(code, w.chat, w.invn, B, C, S);
+    k_app_normalize<<<nb, 256, 0, st>>>(ncode, w.chat + (size_t)B * C * S, w.invn + (size_t)B * S, B, C, S);
+    k_app_fd<<<dim3(S, B, 2), 128, 0, st>>>(w, B, Cf, S);
+    if (phase == 1) { k_export_sums<<<1, 32, 0, st>>>(w.acc, sh->sums); NSOS_CHECK_CUDA(cudaGetLastError()); return NSOS_OK; }
+  }
+  NSOS_REQUIRE(loss, NSOS_ERR_BAD_ARG, "app_corr_loss: loss pointer missing");
+  NSOS_CHECK_CUDA(cudaMemsetAsync(w.g_chat, 0, sizeof(float) * 2 * B * C * S, st));
+  k_oldmean<<<1, 32, 0, st>>>(GeoWs{nullptr, nullptr, nullptr, nullptr, w.acc, w.oldmean}, phase == 2 ? sh->sums : w.acc, (double)Bt * S);
+  const double denom = (double)Bt * S * S;
   const float coef0 = (float)(neg_w / denom), coef1 = (float)(self_w / denom);
   k_app_pairs<<<dim3(B, 2), 256, 0, st>>>(w, B, C, S, neg_shift, self_shift, coef0, coef1, want);
   if (want) {

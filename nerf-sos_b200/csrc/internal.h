@@ -39,13 +39,16 @@ int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* 
 int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,
                 cudaStream_t st);
 
+// optim.cu
+int adam_multi(const NsosAdamTensor* t, int n_tensors, float lr, float beta1, float beta2, float eps, int64_t step, cudaStream_t st);
+
 // corr_loss.cu
 size_t geo_corr_workspace_bytes(int B, int C, int M);
 int geo_corr_loss(const float* xyz, const float* code, const int64_t* neg_idx, const float* params, float* loss, float* g_code,
-                  int B, int C, int M, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                  int B, int C, int M, const NsosLossShard* sh, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t app_corr_workspace_bytes(int B, int Cf, int C, int S);
 int app_corr_loss(const float* feats, const float* nfeats, const float* code, const float* ncode, const float* params, float* loss,
-                  float* g_code, float* g_ncode, int B, int Cf, int C, int S, void* workspace, size_t workspace_bytes,
-                  cudaStream_t st);
+                  float* g_code, float* g_ncode, int B, int Cf, int C, int S, const NsosLossShard* sh, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace nsos

@@ -26,8 +26,7 @@ def eval_one_view(model, batch, near_far, radii, device, clus_no_sfm=False, N_cl
         rays = batch["rays"].to(device)                                   # [2, H, W, 3]
         render_kwargs.setdefault("retraw", False)
         if P.world(group)[1] > 1:
-            ret = P.render_sharded(model, rays, (near, far), group=group, keys=("rgb", "disp", "acc", "depth", "semantics", "rgb0"),
-                                   **render_kwargs)
+            ret = P.render_sharded(model, rays, (near, far), group=group, keys=None, radii=radii, **render_kwargs)   # every per-ray key
         else:
             ret = model(rays, (near, far), radii=radii, **render_kwargs)
         ret = dict(ret)

@@ -6,11 +6,13 @@ The reference has no distributed code on its live path: ra
     collective; the per-ray outputs are all-gathered once at the end (`render_sharded`);
   * training shards whole 64x64 patches across ranks.  The correlation losses pick their negative from
     ANOTHER patch of the global batch (utils/image.py:354,359,473), so the small per-patch tensors
-    (semantic code, XYZ, DINO features) are all-gathered (`gather_cat`, autograd-aware) and every rank
-    evaluates the identical global-batch loss; its backward needs no communication (each rank keeps the
-    slice of the gathered gradient that belongs to its own patches);
+    (semantic code, depth, rays, DINO features; 0.5 MB per patch) travel in ONE packed all-gather
+    (`all_gather_rows`, static shapes, no host synchronisation); every rank then evaluates only the loss
+    rows of ITS OWN patches (kernel B's sharded phases, one all-reduce of the batch-wide `old_mean` sums) and
+    the code gradients that land on remote negatives come home in one all-reduce (`engines/trainer.py`);
   * parameter gradients are then summed with ONE all-reduce over a single flat fp32 buffer
     (`allreduce_gradients`; 0.33 MB under --fix_backbone, 5.1 MB for all parameters).
+  Four collectives per training step in total, none of them followed by a host read.
 """
 from __future__ import annotations
 
@@ -31,17 +33,36 @@ def shard_bounds(n: int, rank: int, world_size: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
+    """[n, L] on every rank (same n everywhere) -> [G*n, L], rank-major.  One collective, static shapes, no gradient."""
+    rank, ws = world(group)
+    if ws == 1:
+        return x
+    x = x.contiguous()
+    out = x.new_empty((ws * x.shape[0],) + tuple(x.shape[1:]))
+    dist.all_gather_into_tensor(out, x, group=group)
+    return out
+
+
+def all_reduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    if world(group)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
 class _GatherCat(torch.autograd.Function):
     """all-gather along dim 0 (ragged sizes allowed).  Backward: every rank holds the gradient of the SAME
-    global loss w.r.t. the gathered tensor, so it keeps its own slice -- no collective in backward."""
+    global loss w.r.t. the gathered tensor, so it keeps its own slice -- no collective in backward.
+    `sizes` (rows per rank) makes the gather static; without it the sizes are exchanged first (one host sync)."""
 
     @staticmethod
-    def forward(ctx, x, group):
+    def forward(ctx, x, group, sizes=None):
         rank, ws = world(group)
-        n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
-        sizes = [torch.zeros_like(n) for _ in range(ws)]
-        dist.all_gather(sizes, n, group=group)
-        sizes = [int(s.item()) for s in sizes]
+        if sizes is None:
+            n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
+            sz = [torch.zeros_like(n) for _ in range(ws)]
+            dist.all_gather(sz, n, group=group)
+            sizes = [int(s.item()) for s in sz]
         mx = max(sizes)
         pad = x.new_zeros((mx,) + tuple(x.shape[1:]))
         pad[:x.shape[0]] = x
@@ -53,14 +74,14 @@ class _GatherCat(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g[ctx.lo:ctx.lo + ctx.n].contiguous(), None
+        return g[ctx.lo:ctx.lo + ctx.n].contiguous(), None, None
 
 
-def gather_cat(x: torch.Tensor, group=None) -> torch.Tensor:
+def gather_cat(x: torch.Tensor, group=None, sizes=None) -> torch.Tensor:
     """Differentiable all-gather + concat along dim 0; identity when not distributed."""
     if world(group)[1] == 1:
         return x
-    return _GatherCat.apply(x, group)
+    return _GatherCat.apply(x, group, sizes)
 
 
 def allreduce_gradients(params, group=None, average: bool = False):
@@ -97,14 +118,18 @@ def render_sharded(net, ray_batch, bound_batch, group=None, keys=("rgb", "depth"
     n = ro.shape[0]
     lo, hi = shard_bounds(n, rank, ws)
     near, far = bound_batch
+    empty = hi == lo                    # more ranks than rays: render one ray for the output shapes and contribute none of it
+    sl = slice(0, 1) if empty else slice(lo, hi)
     if torch.is_tensor(near):
-        near = near.reshape(n, -1)[lo:hi]
+        near = near.reshape(n, -1)[sl]
     if torch.is_tensor(far):
-        far = far.reshape(n, -1)[lo:hi]
-    out = net(torch.stack([ro[lo:hi], rd[lo:hi]], 0), (near, far), **kwargs)
+        far = far.reshape(n, -1)[sl]
+    out = net(torch.stack([ro[sl], rd[sl]], 0), (near, far), **kwargs)
+    sizes = [b - a for a, b in (shard_bounds(n, r, ws) for r in range(ws))]        # static: no size exchange, no host sync
     res = {}
-    for k in keys:
+    for k in (keys if keys is not None else out.keys()):
         if k in out:
-            full = gather_cat(out[k].contiguous(), group)
+            part = out[k][:0] if empty else out[k]
+            full = gather_cat(part.contiguous(), group, sizes)
             res[k] = full.reshape(*lead, *full.shape[1:])
     return res

@@ -1,7 +1,9 @@
 """Multi-GPU equivalence worker (launched by tests/test_gpu_dist.py through torchrun, one rank per GPU):
   1. ray-sharded render == single-GPU render, bitwise per ray;
-  2. one data-parallel training step (patches sharded, per-patch tensors gathered, flat NCCL gradient
-     all-reduce) reproduces the single-GPU loss (1e-6 rel) and gradients (1e-5 rel of max) on the global batch.
+  2. one data-parallel training step (patches sharded; ONE packed all-gather of the per-patch tensors, kernel B evaluated
+     per rank on its own patches with the batch-wide old_mean all-reduced, code gradients of remote negatives all-reduced,
+     flat NCCL gradient all-reduce) reproduces the single-GPU loss (1e-6 rel) and gradients (1e-5 rel of max) on the
+     global batch -- appearance AND geometry correlation losses on, same sample coordinates on every rank.
 """
 import os
 import sys
@@ -22,7 +24,7 @@ from conftest import load_golden  # noqa: E402
 
 class Args:
     patch_tune = True; patch_size = 8; patch_stride = 6; batch_size = 4
-    use_dino = True; use_correlation = False; use_geoCorr = True; use_contrast = False
+    use_dino = True; use_correlation = True; use_geoCorr = True; use_contrast = False
     rgb_w = 1.0; correlation_w = 1.0; Gcorrelation_w = 0.01; contrast_w = 0.0
     rand_neg = False; self_corr_w = 1; use_sim_matrix = True
     app_corr_params = [0.18, 1, 0.46, 1]; geo_corr_params = [0.5, 1, 3, 1]
@@ -85,7 +87,8 @@ def main():
 
     def run(lo, hi, group):
         net = make_net(dev)
-        opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=5e-4)
+        from nerfsos_b200.engines.optim import FusedAdam
+        opt = FusedAdam([p for p in net.parameters() if p.requires_grad], lr=5e-4)
         losses = [None, None, CorrelationLoss(a), GeoCorrelationLoss(a)]
         sl = slice(lo * Ps * Ps, hi * Ps * Ps)
         r = {k: v[sl] for k, v in rnd.items()}

@@ -122,3 +122,64 @@ def test_losses_refuse_cpu():
     with pytest.raises(_lib.NsosError):
         I.GeoCorrelationLoss(Args())(torch.ones(2, 1, 4, 4), torch.randn(2, 2, 4, 4), [torch.zeros(2, 3, 4, 4), torch.ones(2, 3, 4, 4), None],
                                      torch.eye(2))
+
+
+@pytest.mark.parametrize("split", [(0, 2, 4), (0, 1, 4), (0, 3, 4)])
+def test_sharded_phases_sum_to_the_single_call(split):
+    """Data-parallel evaluation of both losses (NsosLossShard): two 'ranks' evaluate disjoint query ranges of the same gathered
+    batch; the all-reduce of the old_mean sums is emulated by adding the two partial sums.  Sum of the shares == one call on
+    the whole batch, for the loss (1e-6) and for the code gradient of every patch (1e-5 of max) -- including gradients that
+    land on a negative patch owned by the other 'rank'."""
+    I = _mods()
+    g = load_golden("losses_b4_p16")
+    feat = torch.from_numpy(g["feat"]).to(DEV)
+    sim = torch.from_numpy(g["sim"]).to(DEV)
+    c1 = torch.from_numpy(g["rand1"]).to(DEV) * 2 - 1
+    c2 = torch.from_numpy(g["rand2"]).to(DEV) * 2 - 1
+    ray_o, ray_d = torch.from_numpy(g["ray_o"]).to(DEV), torch.from_numpy(g["ray_d"]).to(DEV)
+    app, geo = I.CorrelationLoss(Args()), I.GeoCorrelationLoss(Args())
+    code = torch.from_numpy(g["code"]).to(DEV).requires_grad_(True)
+    whole = app(feat, code, sim, coords=(c1, c2)) + 0.5 * geo(torch.from_numpy(g["depth"]).to(DEV), code, [ray_o, ray_d, None], sim)
+    whole.backward()
+    g_whole = code.grad.clone()
+    bounds = list(zip(split[:-1], split[1:]))
+    code2 = torch.from_numpy(g["code"]).to(DEV).requires_grad_(True)
+    pa = [app.begin(feat, code2, sim, lo, hi - lo, coords=(c1, c2)) for lo, hi in bounds]
+    pg = [geo.begin(torch.from_numpy(g["depth"]).to(DEV), code2, [ray_o, ray_d, None], sim, lo, hi - lo) for lo, hi in bounds]
+    for group in (pa, pg):
+        tot = sum(p.sums for p in group)                     # the all-reduce
+        for p in group:
+            p.sums = tot.clone()
+    shares = sum(app.finish(p) for p in pa) + 0.5 * sum(geo.finish(p) for p in pg)
+    assert abs(shares.item() - whole.item()) <= 1e-6 * max(1.0, abs(whole.item())), (shares.item(), whole.item())
+    shares.backward()
+    err = (code2.grad - g_whole).abs().max().item()
+    assert err <= 1e-5 * g_whole.abs().max().item(), (err, g_whole.abs().max().item())
+
+
+def test_fused_adam_matches_torch_adam():
+    """One launch per step for all tensors (run_nerf.py:320 + engines/lr.py) == torch.optim.Adam, 20 steps with a decaying lr;
+    state_dict keys are torch's."""
+    import nerfsos_b200  # noqa: F401
+    from nerfsos_b200.engines.lr import LRScheduler
+    from nerfsos_b200.engines.optim import FusedAdam
+    gen = torch.Generator().manual_seed(0)
+    shapes = [(128, 319), (128,), (2, 128), (2,), (7,), (300, 257)]
+    pa = [torch.randn(s, generator=gen).to(DEV).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa, ob = FusedAdam(pa, lr=5e-4, betas=(0.9, 0.999)), torch.optim.Adam(pb, lr=5e-4, betas=(0.9, 0.999))
+    sa, sb = LRScheduler(oa, 5e-4, 0.1, 50), LRScheduler(ob, 5e-4, 0.1, 50)
+    for step in range(1, 21):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=gen).to(DEV) * (1.0 + step)
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step(); sa.step(step); sb.step(step)
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() <= 2e-6 * y.abs().max().item()
+    ka = oa.state_dict()["state"][0]
+    assert set(ka) == {"step", "exp_avg", "exp_avg_sq"} and int(ka["step"]) == 20
+    ob2 = torch.optim.Adam(pb, lr=5e-4)
+    ob2.load_state_dict(oa.state_dict())                      # checkpoints are interchangeable
+    v = pa[0]._version
+    pa[0].grad = torch.zeros_like(pa[0]); oa.step()
+    assert pa[0]._version > v                                 # the weight-pack cache sees the update

@@ -17,7 +17,8 @@ def test_train_steps_update_only_semantic_head_and_reduce_loss():
     a.use_correlation = True
     net = W.make_net(dev)
     before = {n: p.detach().clone() for n, p in net.named_parameters()}
-    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=2e-3)
+    from nerfsos_b200.engines.optim import FusedAdam
+    opt = FusedAdam([p for p in net.parameters() if p.requires_grad], lr=2e-3)
     from nerfsos_b200.engines.lr import LRScheduler
     sched = LRScheduler(opt, 2e-3, 0.1, 250000)
     losses = [None, None, W.CorrelationLoss(a), W.GeoCorrelationLoss(a)]

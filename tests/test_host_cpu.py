@@ -170,17 +170,41 @@ def test_bench_has_no_undefined_names():
 
 
 def test_bench_reference_arm_prints_one_contract_line():
-    """`bench.py --impl reference` (the oracle port on the host cores) runs without a GPU and prints exactly one JSON line
-    with the contract's keys."""
+    """`bench.py --impl reference` (the unmodified reference on the host cores -- from /root/reference here, from the
+    byte-compiled oracle/_ref on the GPU box, the oracle port only if neither imports) runs without a GPU and prints exactly
+    one JSON line with the contract's keys, on the FULL 4096-ray configuration."""
     import json
     import subprocess
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["unit"] == "rays/s" and j["value"] > 0 and j["higher_is_better"] is True
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["e2e"]["h2d_bytes_per_step"] == 0
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1 and j["e2e"]["h2d_bytes_per_step"] == 0
+    assert j["config"]["rays_per_step"] == 4096 and j["steps"] == 1
     assert {"metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"} <= set(j)
+
+
+def test_bench_line_builders_run_on_cpu():
+    """Every --workload arm's line-building code executes here, so that a NameError cannot take down an 8-GPU run."""
+    import argparse
+    import json
+    import bench
+    for mode in ("exact", "fast"):
+        args = argparse.Namespace(steps=10, warmup=3, mode=mode, all_params=False)
+        m = dict(total_ms=30.0, e2e_s=0.04, e2e_dropin_s=0.06, n_total=8 * 4096, n_local=4096, t_wall=0.1, clk={"sm_mhz": 1900.0},
+                 h2d=98304, d2h=278528)
+        train = dict(ms_per_step=50.0, rays_per_s=1e6, rays_per_gpu=32768, steps=5, warmup=3, trainable_params=82436,
+                     recipe="--fix_backbone (semantic heads)", collectives_per_step=4, allgather_bytes_per_rank=1, allreduce_bytes=2,
+                     h2d_bytes_per_step=3, d2h_bytes_per_step=4, final_loss=0.1, clocks=None)
+        for image in (False, True):
+            line = bench.eval_line(m, args, 8, image, None if image else train)
+            json.dumps(line)
+            assert line["n_gpus"] == 8 and line["roofline"]["frac"] > 0 and ("train" in line) == (not image)
+        for rec in ("--fix_backbone (semantic heads)", "all parameters"):
+            tl = bench.train_line(dict(train, recipe=rec), args, 8)
+            json.dumps(tl)
+            assert tl["collectives"]["collectives_per_step"] == 4 and tl["roofline"]["frac"] > 0
