@@ -4,9 +4,9 @@
 TEST / BASELINE INFRASTRUCTURE ONLY.  The reference is pure Python and /root/reference does not exist on the GPU box, so
 `bench.py --impl reference` could otherwise only time the op-for-op port (oracle/torch_port.py).  This recipe is the
 Python analogue of compiling a C reference into oracle/_ref/*.so: the UNMODIFIED sources are compiled where they lie
-(py_compile, no source text is written anywhere in this repo) and only the resulting .pyc binaries -- importable as
-sourceless modules by the same interpreter version -- land in oracle/_ref/.  `oracle/ref_shim.py` puts that directory on
-sys.path when /root/reference is absent.  Run by __graft_entry__.build() whenever /root/reference is present.
+(py_compile, no source text is written anywhere in this repo) and only the resulting bytecode binaries (*.pyc.bin, loaded by
+importlib's SourcelessFileLoader under the same interpreter version) land in oracle/_ref/.  `oracle/ref_shim.py` installs an
+importer for them when /root/reference is absent.  Run by __graft_entry__.build() whenever /root/reference is present.
 """
 import os
 import py_compile
@@ -27,7 +27,7 @@ def build(verbose=True) -> bool:
         return False
     for rel in FILES:
         src = os.path.join(REF, rel)
-        dst = os.path.join(OUT, rel + "c")                      # models/nerf_net.pyc next to where the .py would be
+        dst = os.path.join(OUT, rel[:-3] + ".pyc.bin")          # models/nerf_net.pyc.bin (gpurun's snapshot skips *.pyc)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
             continue

@@ -41,6 +41,31 @@ class _LPIPS:
         raise RuntimeError("lpips is stubbed")
 
 
+class _RefFinder:
+    """Import `models.x` / `utils.x` / `engines.x` from oracle/_ref/<pkg>/<x>.pyc.bin (byte-compiled reference modules)."""
+
+    @staticmethod
+    def find_spec(name, path=None, target=None):
+        import importlib.machinery as M
+        import importlib.util as U
+        parts = name.split(".")
+        if parts[0] not in ("models", "utils", "engines") or len(parts) > 2:
+            return None
+        if len(parts) == 1:
+            d = os.path.join(REF, parts[0])
+            if not os.path.isdir(d):
+                return None
+            spec = M.ModuleSpec(name, None, is_package=True)
+            spec.submodule_search_locations = [d]
+            return spec
+        f = os.path.join(REF, parts[0], parts[1] + ".pyc.bin")
+        if not os.path.isfile(f):
+            return None
+        return U.spec_from_file_location(name, f, loader=M.SourcelessFileLoader(name, f))
+
+
+if available() and KIND == "pyc":
+    sys.meta_path.insert(0, _RefFinder)
 if available():
     _stub("imageio")
     mp = _stub("matplotlib")
