@@ -357,7 +357,108 @@ def losses():
          app_params=np.array([0.18, 1, 0.46, 1.0]), geo_params=np.array([0.5, 1, 3, 1.0]))
 
 
+class StandInDino:
+    """Deterministic feature provider with the extractor's interface (no DINO weights offline); duplicated in tests/."""
+
+    def __init__(self):
+        self.proj = torch.randn(3, 384, generator=torch.Generator().manual_seed(0))
+
+    def get_vit_attn_feat(self, x):
+        B = x.shape[0]
+        p = torch.nn.functional.adaptive_avg_pool2d(x, 14).reshape(B, 3, 196).permute(0, 2, 1)      # [B,196,3]
+        feat = p @ self.proj.to(x.device)
+        return {"attn": feat[..., :1].permute(0, 2, 1), "cls_": feat.mean(1), "feat": feat}
+
+
+def train_steps():
+    """SURVEY Appendix B 'end-to-end': five consecutive steps of the UNMODIFIED reference trainer (engines/trainer.py:32-213,
+    engines/lr.py, torch.optim.Adam) in the shipped stage-2 recipe (--fix_backbone, both correlation losses) on the flower
+    checkpoint, CPU.  Every random draw is recorded per step (4 render draws + 2x2 sample-coordinate draws of the appearance
+    loss); the per-step loss terms and the trained semantic-head tensors are the targets."""
+    import engines.trainer as RT
+    from engines.lr import LRScheduler as RefLR
+    ck = torch.load(CKPT, map_location="cpu")
+    net = NeRFNet(perturb=1.0, raw_noise_std=1.0, N_samples=64, N_importance=128, use_semantics=True, sem_with_coord=True,
+                  sem_dim=2, sem_layer=2)
+    net.load_state_dict(ck["model"], strict=True)
+    for n, p in net.named_parameters():
+        p.requires_grad_("semantic_linear" in n)
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=5e-4, betas=(0.9, 0.999))
+    sched = RefLR(opt, 5e-4, 0.1, 250000)
+
+    class A(_Args):
+        patch_tune = True; patch_size = 8; batch_size = 2; use_dino = True; use_correlation = True; use_geoCorr = True
+        use_contrast = False; rgb_w = 1.0; correlation_w = 1.0; Gcorrelation_w = 0.01; contrast_w = 0.0; i_print = 100000
+        clus_no_sfm = False; N_cluster = 2
+
+    class DS:
+        height, width, K = 756, 1008, None
+        def near_far(self): return 1.2, 12.0
+        def radii(self): return None
+
+    class Loader:
+        dataset = DS()
+
+    losses = [None, None, ref_image.CorrelationLoss(A()), ref_image.GeoCorrelationLoss(A())]
+    B, P = A.batch_size, A.patch_size
+    rays = torch.stack([llff_rays(0, seed=70 + b, patch=(P, 6)) for b in range(B)], 0)          # [B,2,P,P,3]
+    batch_rays = rays.permute(0, 2, 3, 1, 4).reshape(B, P * P, 2, 3).contiguous()
+    g = torch.Generator().manual_seed(71)
+    gt = torch.rand(B, P * P, 3, generator=g)
+    masks = torch.zeros(B, P * P, 1)
+    steps, rec = [], {}
+    dino = StandInDino()
+    for k in range(5):
+        with RecordRandom() as rr:
+            out = RT.train_one_step((batch_rays, gt, masks), [net, dino], opt, sched, Loader(), 2 + k, losses, "cpu", A())
+        kinds = [a for a, _ in rr.draws]
+        assert kinds == ["rand", "randn", "rand", "randn", "rand", "rand", "rand", "rand"], kinds
+        for name, (_, t) in zip(("t_rand", "noise0", "u", "noise1", "c0_1", "c0_2", "c1_1", "c1_2"), rr.draws):
+            rec[f"s{k}_{name}"] = t.numpy()
+        steps.append([float(out[n].detach()) for n in ("loss", "img0", "img1", "corr0", "corr1", "geo_corr0", "geo_corr1")])
+        print("step", 2 + k, steps[-1])
+    final = {n: p.detach().numpy().copy() for n, p in net.named_parameters() if p.requires_grad}
+    save("flower_train_steps", rays=batch_rays.numpy(), gt=gt.numpy(), steps=np.array(steps), rnd=rec, final=final,
+         lr_last=opt.param_groups[0]["lr"])
+
+
+def metrics():
+    """Evaluation metrics exactly as the reference computes them (engines/eval.py:60-95): utils/ssim.py:7-40, sklearn
+    adjusted_rand_score, utils/misc.py:40-50 (sklearn KMeans, random_state=0) and utils/get_metrics.py:15-26 (compute_iou)."""
+    from sklearn.metrics import adjusted_rand_score
+    from utils import ssim as ref_ssim
+    # utils/get_metrics.py runs a hard-coded evaluation script at import time: take its compute_iou function alone
+    import ast
+    from sklearn.metrics import confusion_matrix
+    src = open(os.path.join(ref_shim.REF, "utils", "get_metrics.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "compute_iou")
+    ns = {"np": np, "confusion_matrix": confusion_matrix}
+    exec(compile(ast.Module([fn], []), "utils/get_metrics.py", "exec"), ns)
+    compute_iou = ns["compute_iou"]
+    from utils.misc import segmap_cluster
+    g = torch.Generator().manual_seed(41)
+    H, W = 48, 64
+    img1 = torch.rand(2, 3, H, W, generator=g)
+    img2 = (img1 + 0.1 * torch.randn(2, 3, H, W, generator=g)).clamp(0, 1)
+    s_all = float(ref_ssim.ssim(img1, img2))
+    s_each = ref_ssim.ssim(img1, img2, size_average=False).numpy()
+    # a blobby ground-truth mask, logits that mostly agree with it
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    gt = (((yy - 20) ** 2 + (xx - 30) ** 2) < 15 ** 2).long()
+    logits = torch.stack([1.5 - 3.0 * gt.float(), 3.0 * gt.float() - 1.5], -1) + 0.8 * torch.randn(H, W, 2, generator=g)
+    prob = logits.softmax(-1)
+    clus = segmap_cluster(prob.numpy(), n_clusters=2)                       # [H,W,1] int
+    sem_pred = prob.argmax(-1, keepdim=True).numpy()
+    gt_np = gt.numpy()[..., None]
+    fg = gt_np == 1
+    out = dict(clus_ari=adjusted_rand_score(gt_np.reshape(-1), clus.reshape(-1)), clus_ari_fg=adjusted_rand_score(gt_np[fg].reshape(-1), clus[fg].reshape(-1)),
+               sem_ari=adjusted_rand_score(gt_np.reshape(-1), sem_pred.reshape(-1)), sem_ari_fg=adjusted_rand_score(gt_np[fg].reshape(-1), sem_pred[fg].reshape(-1)))
+    iou_a, iou_b = compute_iou(clus, gt_np), compute_iou(1 - clus, gt_np)   # clustering has no polarity: both assignments
+    save("metrics_ref", img1=img1.numpy(), img2=img2.numpy(), ssim=s_all, ssim_each=s_each, logits=logits.numpy(), gt=gt_np, clus=clus,
+         sem_pred=sem_pred, iou_fg=max(float(iou_a[1]), float(iou_b[1])), **{k: float(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg1", "flower", "losses", "other_checkpoints", "flower_all_param_grads", "cfg1_grads_safe"]
+    which = sys.argv[1:] or ["cfg1", "flower", "losses", "other_checkpoints", "flower_all_param_grads", "cfg1_grads_safe", "metrics", "train_steps"]
     for w in which:
         globals()[w]()

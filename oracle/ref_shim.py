@@ -71,7 +71,7 @@ if available():
     mp = _stub("matplotlib")
     mp.pyplot = _stub("matplotlib.pyplot")
     _stub("lpips", LPIPS=_LPIPS)
-    _stub("sacrebleu")
+    _stub("sacrebleu", dataset=None)          # engines/trainer.py:8 `from sacrebleu import dataset` (unused there)
     _stub("configargparse")
     if REF not in sys.path:
         sys.path.insert(0, REF)

@@ -125,3 +125,31 @@ def test_two_means_matches_sklearn_partition():
     assert sk(ref, lab.reshape(-1).numpy()) == 1.0
     gt = torch.from_numpy(ref).reshape(20, 40, 1)
     assert float(M.binary_iou(lab, gt)) == 1.0 and float(M.binary_iou(1 - lab, gt)) == 1.0
+
+
+def test_metrics_match_the_reference_metric_code():
+    """utils/metrics.py against outputs of the reference's OWN metric code (utils/ssim.py:7-40, sklearn ARI as called by
+    engines/eval.py:70-74, utils/misc.py:40-50 KMeans, utils/get_metrics.py:15-26 compute_iou), generated through the shim by
+    oracle/make_golden.py:metrics."""
+    import numpy as np
+    import torch
+    from conftest import load_golden
+    from nerfsos_b200.utils import metrics as M
+    g = load_golden("metrics_ref")
+    a, b = torch.from_numpy(g["img1"]), torch.from_numpy(g["img2"])
+    assert abs(float(M.ssim(a, b)) - float(g["ssim"])) <= 1e-6
+    np.testing.assert_allclose(M.ssim(a, b, size_average=False).numpy(), g["ssim_each"], rtol=0, atol=1e-6)
+    assert abs(float(M.ssim(a[0].permute(1, 2, 0), b[0].permute(1, 2, 0), format="HWC")) - float(g["ssim_each"][0])) <= 1e-6
+    logits, gt = torch.from_numpy(g["logits"]), torch.from_numpy(g["gt"]).long()
+    prob = logits.softmax(-1)
+    clus = M.kmeans_labels(prob, n_clusters=2)
+    ref_clus = torch.from_numpy(g["clus"]).long()
+    assert clus.shape == ref_clus.shape
+    same = (clus == ref_clus).float().mean().item()
+    assert max(same, 1 - same) >= 0.999                                   # the same partition (labels may be swapped)
+    sem_pred = prob.argmax(-1, keepdim=True)
+    assert torch.equal(sem_pred, torch.from_numpy(g["sem_pred"]).long())
+    fg = gt == 1
+    for k, (x, y) in dict(clus_ari=(gt, ref_clus), clus_ari_fg=(gt[fg], ref_clus[fg]), sem_ari=(gt, sem_pred), sem_ari_fg=(gt[fg], sem_pred[fg])).items():
+        assert abs(float(M.adjusted_rand_score(x, y)) - float(g[k])) <= 1e-6, k
+    assert abs(float(M.binary_iou(ref_clus, gt)) - float(g["iou_fg"])) <= 1e-6

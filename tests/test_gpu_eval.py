@@ -67,3 +67,26 @@ def test_training_loop_fed_by_device_resident_patch_sampler(scene):
         assert rays.is_cuda and rays.shape == (4, 64, 2, 3)
         out = W.train_one_step((rays, rgbs, masks), [net, W.FakeDino()], opt, sched, Loader(), step + 1, losses, DEV, a)
         assert torch.isfinite(out["loss"])
+
+
+def test_device_metrics_match_reference_metric_code():
+    """The same fixture as tests/test_data_eval_cpu.py (reference ssim / sklearn ARI / KMeans / compute_iou outputs), with the
+    tensors on the GPU -- the path eval_one_view takes."""
+    import numpy as np
+    from conftest import load_golden
+    from nerfsos_b200.utils import metrics as M
+    g = load_golden("metrics_ref")
+    dev = "cuda:0"
+    a, b = torch.from_numpy(g["img1"]).to(dev), torch.from_numpy(g["img2"]).to(dev)
+    assert abs(float(M.ssim(a, b)) - float(g["ssim"])) <= 2e-6
+    logits, gt = torch.from_numpy(g["logits"]).to(dev), torch.from_numpy(g["gt"]).long().to(dev)
+    prob = logits.softmax(-1)
+    clus = M.kmeans_labels(prob, n_clusters=2)
+    ref_clus = torch.from_numpy(g["clus"]).long().to(dev)
+    same = (clus == ref_clus).float().mean().item()
+    assert max(same, 1 - same) >= 0.999
+    sem_pred = prob.argmax(-1, keepdim=True)
+    fg = gt == 1
+    for k, (x, y) in dict(clus_ari=(gt, clus), clus_ari_fg=(gt[fg], clus[fg]), sem_ari=(gt, sem_pred), sem_ari_fg=(gt[fg], sem_pred[fg])).items():
+        assert abs(float(M.adjusted_rand_score(x, y)) - float(g[k])) <= 1e-3, k
+    assert abs(float(M.binary_iou(clus, gt)) - float(g["iou_fg"])) <= 1e-3
