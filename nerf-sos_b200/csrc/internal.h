@@ -32,10 +32,22 @@ bool tc_net_supported(const NsosNetDesc& net);
 int tc_render_replay(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
                      const float* z0, const float* z1, float* raw0, float* raw1, float* h0, float* s00, float* h1, float* s01,
                      int64_t n_rays, cudaStream_t st);
+int tc_render_replay_all(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
+                         const float* z0, const float* z1, float* const raw[2], float* const* const h_all[2], float* const hv[2],
+                         float* const s0[2], int64_t n_rays, cudaStream_t st);
+// row GEMM on tcgen05 (bf16 hi/lo, fp32 accumulate) for the all-parameter backward: C[P,N] (=|+=) epi(A[P,K] . B), B(k,n) = B[k*b_rs + n*b_cs]
+size_t tc_rowgemm_scratch_bytes(int K, int N);
+bool tc_rowgemm_supported(int K, int N, int64_t lda, int64_t ldc, int64_t mask_ld);
+int tc_rowgemm(const float* A, int64_t lda, int K, const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int N,
+               const float* mask, int64_t mask_ld, const float* bias, int relu, int accumulate, int64_t P, void* scratch,
+               size_t scratch_bytes, cudaStream_t st);
 // tc_wgrad.cu (semantic-head weight gradients on tcgen05)
 bool tc_sem_wgrad_supported(const NetGeom& g);
 int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, const float* s0,
                  const float* g_raw, int64_t P, cudaStream_t st);
+bool tc_wgrad_gen_supported(int Mo, int64_t ldy, int main_w, int64_t ld_main, int aux_w);
+int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_t ld_main, int main_col, const float* aux, int64_t ld_aux,
+                 int aux_w, int aux_col, float* dW, int64_t ldw, int64_t P, cudaStream_t st);
 int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,
                 cudaStream_t st);
 

@@ -156,6 +156,24 @@ __global__ void k_relu_mask(float* __restrict__ G, const float* __restrict__ H, 
 
 inline dim3 grid1(int64_t n, int bs = 256) { return dim3((unsigned)((n + bs - 1) / bs)); }
 
+// ---- tensor-core dispatch for the large GEMMs of the all-parameter backward ------------------------
+// NSOS_MODE_TC_*: products with a 64..256-wide contraction and a 32..256-wide output run on tcgen05 (tc_rowgemm / tc_wgrad_gen:
+// bf16 hi/lo operands, 3 MMAs per product, fp32 accumulate); everything narrow (the 1-, 3- and sem_dim-wide heads, the per-ray
+// direction encoding) stays on the fp32 CUDA-core GEMM.
+struct TcCtx {
+  bool on = false;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+int gemm_dispatch(const GemmArgs& a, const TcCtx* tc, cudaStream_t st) {
+  if (tc && tc->on && !a.A2 && a.a1_cs == 1 && a.a1_rowdiv <= 1 && a.b_rowdiv <= 1 && a.c_cs == 1 && a.split_k <= 1 && a.K1 % 64 == 0 &&
+      tc_rowgemm_supported(a.K1, a.N, a.a1_rs, a.c_rs, a.mask ? a.mask_ld : 0) &&
+      tc->scratch_bytes >= tc_rowgemm_scratch_bytes(a.K1, a.N))
+    return tc_rowgemm(a.A1, a.a1_rs, a.K1, a.B, a.b_rs, a.b_cs, a.C, a.c_rs, a.N, a.mask, a.mask_ld, a.bias, a.relu, a.accumulate, a.M,
+                      tc->scratch, tc->scratch_bytes, st);
+  return launch_gemm(a, st);
+}
+
 // ---- MLP forward over P points -----------------------------------------------------------------
 struct MlpBufs {
   float* h[16];   // per-layer post-ReLU activations [P,W]; forward-only mode aliases two buffers
@@ -176,7 +194,7 @@ GemmArgs lin(const float* A1, int64_t lda1, int K1, const float* A2, int64_t lda
 
 // MLP.forward (nerf_mlp.py:67-100).  enc [P,kEncLd], encv [P/S rows, kEncVLd] broadcast per ray via rowdiv=S.
 int mlp_forward(const NetGeom& g, const float* prm, const float* enc, const float* encv, int S, int64_t P, const MlpBufs& b,
-                float* raw, cudaStream_t st) {
+                float* raw, cudaStream_t st, const TcCtx* tc = nullptr) {
   const int W = g.W;
   const float* h = nullptr;
   for (int i = 0; i < g.D; ++i) {
@@ -184,7 +202,7 @@ int mlp_forward(const NetGeom& g, const float* prm, const float* enc, const floa
     if (i == 0) a = lin(enc, kEncLd, g.enc, nullptr, 0, 0, 1, prm + g.w_pts[i], prm + g.b_pts[i], b.h[i], W, P, W, 1);
     else if (g.in_pts[i] == W) a = lin(h, W, W, nullptr, 0, 0, 1, prm + g.w_pts[i], prm + g.b_pts[i], b.h[i], W, P, W, 1);
     else a = lin(enc, kEncLd, g.enc, h, W, W, 1, prm + g.w_pts[i], prm + g.b_pts[i], b.h[i], W, P, W, 1);  // [enc, h] :74
-    int rc = launch_gemm(a, st); if (rc) return rc;
+    int rc = gemm_dispatch(a, tc, st); if (rc) return rc;
     h = b.h[i];
   }
   if (!g.use_viewdirs) {
@@ -196,11 +214,11 @@ int mlp_forward(const NetGeom& g, const float* prm, const float* enc, const floa
   if (g.use_sem) {                                                                                             // :79-80
     GemmArgs a = g.sem_coord ? lin(h, W, W, enc, kEncLd, g.enc, 1, prm + g.w_s0, prm + g.b_s0, b.s0, W / 2, P, W / 2, 1)
                              : lin(h, W, W, nullptr, 0, 0, 1, prm + g.w_s0, prm + g.b_s0, b.s0, W / 2, P, W / 2, 1);
-    rc = launch_gemm(a, st); if (rc) return rc;
+    rc = gemm_dispatch(a, tc, st); if (rc) return rc;
     rc = launch_gemm(lin(b.s0, W / 2, W / 2, nullptr, 0, 0, 1, prm + g.w_s2, prm + g.b_s2, raw + 4, g.C, P, g.sem_dim, 0), st);
     if (rc) return rc;
   }
-  rc = launch_gemm(lin(h, W, W, nullptr, 0, 0, 1, prm + g.w_feat, prm + g.b_feat, b.feat, W, P, W, 0), st);       // :86
+  rc = gemm_dispatch(lin(h, W, W, nullptr, 0, 0, 1, prm + g.w_feat, prm + g.b_feat, b.feat, W, P, W, 0), tc, st);       // :86
   if (rc) return rc;
   rc = launch_gemm(lin(b.feat, W, W, encv, kEncVLd, g.encv, S, prm + g.w_views, prm + g.b_views, b.hv, W / 2, P, W / 2, 1), st);
   if (rc) return rc;                                                                                           // :87-90
@@ -209,11 +227,30 @@ int mlp_forward(const NetGeom& g, const float* prm, const float* enc, const floa
 
 // dW[N,K] += dY[P,N]^T . X[P,K]  (X possibly two sources)   -- split-K over P with atomics
 int wgrad(const float* dY, int64_t ldy, int N, const float* X1, int64_t ldx1, int K1, const float* X2, int64_t ldx2, int K2,
-          int x2_rowdiv, float* dW, int64_t P, cudaStream_t st) {
+          int x2_rowdiv, float* dW, int64_t P, cudaStream_t st, const TcCtx* tc = nullptr) {
+  // tensor cores: the 256-wide source is `main`, a <= 64-wide source of per-point rows is `aux` (gamma(x)); one launch for both
+  bool done[2] = {false, false};
+  if (tc && tc->on && (N == 128 || N == 256) && ldy % 4 == 0) {
+    const float* X[2] = {X1, X2}; const int64_t ld[2] = {ldx1, ldx2}; const int K[2] = {K1, K2}; const int col[2] = {0, K1};
+    const int rd[2] = {1, x2_rowdiv};
+    int im = -1, ia = -1;
+    for (int part = 0; part < 2; ++part) {
+      if (!X[part] || K[part] == 0 || rd[part] > 1) continue;
+      if (K[part] == 256 && ld[part] % 4 == 0 && im < 0) im = part;
+      else if (K[part] <= 64 && ia < 0) ia = part;
+    }
+    if (im >= 0 || ia >= 0) {
+      int rc = tc_wgrad_gen(dY, ldy, N, im >= 0 ? X[im] : nullptr, im >= 0 ? ld[im] : 0, im >= 0 ? col[im] : 0, ia >= 0 ? X[ia] : nullptr,
+                            ia >= 0 ? ld[ia] : 0, ia >= 0 ? K[ia] : 0, ia >= 0 ? col[ia] : 0, dW, K1 + K2, P, st);
+      if (rc) return rc;
+      if (im >= 0) done[im] = true;
+      if (ia >= 0) done[ia] = true;
+    }
+  }
   // as a GEMM: M=N (rows of dW), N=K (cols), K=P.  A(m,k)=dY[k*ldy+m]; B(k,n)=X[k*ldx+n]
   for (int part = 0; part < 2; ++part) {
     const float* X = part ? X2 : X1; int64_t ldx = part ? ldx2 : ldx1; int Kp = part ? K2 : K1;
-    if (!X || Kp == 0) continue;
+    if (!X || Kp == 0 || done[part]) continue;
     GemmArgs g{};
     g.A1 = dY; g.a1_rs = 1; g.a1_cs = ldy; g.K1 = (int)P; g.a1_rowdiv = 1; g.a2_rowdiv = 1;
     g.B = X; g.b_rs = ldx; g.b_cs = 1; g.b_rowdiv = part ? x2_rowdiv : 1;
@@ -231,13 +268,13 @@ int bgrad(const float* dY, int64_t ldy, int N, float* db, int64_t P, cudaStream_
 }
 // dX[P,K] (=|+=) dY[P,N] . W[N, k0:k0+K]   with optional relu mask from H
 int dgrad(const float* dY, int64_t ldy, int N, const float* Wt, int ldw, int k0, int K, float* dX, int64_t ldx, const float* mask,
-          int accumulate, int64_t P, cudaStream_t st) {
+          int accumulate, int64_t P, cudaStream_t st, const TcCtx* tc = nullptr) {
   GemmArgs g{};
   g.A1 = dY; g.a1_rs = ldy; g.a1_cs = 1; g.K1 = N; g.a1_rowdiv = 1; g.a2_rowdiv = 1;
   g.B = Wt + k0; g.b_rs = ldw; g.b_cs = 1; g.b_rowdiv = 1;   // B(k=n_out, n=k_in) = W[n_out*ldw + k0 + k_in]
   g.C = dX; g.c_rs = ldx; g.c_cs = 1; g.M = (int)P; g.N = K; g.mask = mask; g.mask_ld = ldx; g.accumulate = accumulate;
   g.split_k = 1;
-  return launch_gemm(g, st);
+  return gemm_dispatch(g, tc, st);
 }
 
 struct BwdBufs {
@@ -245,6 +282,7 @@ struct BwdBufs {
   float* G[2];   // [P,W] ping-pong grads w.r.t. post-ReLU trunk activations
   float* g_half; // [P,W/2] grads w.r.t. hv / s0
   float* g_feat; // [P,W]
+  TcCtx tc;      // tensor-core dispatch of the large products (all-parameter backward in a tcgen05 mode)
 };
 
 // Backward of mlp_forward given g_raw; accumulates into grads (flat layout).  trunk=0: semantic head only.
@@ -255,39 +293,39 @@ int mlp_backward(const NetGeom& g, const float* prm, float* grads, const float* 
   int rc;
   if (!g.use_viewdirs) {
     if (!trunk) return NSOS_OK;
-    if ((rc = wgrad(w.g_raw, C, 4, hl, W, W, nullptr, 0, 0, 1, grads + g.w_out, P, st))) return rc;
+    if ((rc = wgrad(w.g_raw, C, 4, hl, W, W, nullptr, 0, 0, 1, grads + g.w_out, P, st, &w.tc))) return rc;
     if ((rc = bgrad(w.g_raw, C, 4, grads + g.b_out, P, st))) return rc;
-    if ((rc = dgrad(w.g_raw, C, 4, prm + g.w_out, W, 0, W, w.G[0], W, hl, 0, P, st))) return rc;
+    if ((rc = dgrad(w.g_raw, C, 4, prm + g.w_out, W, 0, W, w.G[0], W, hl, 0, P, st, &w.tc))) return rc;
   } else {
     bool have_G = false;
     if (g.use_sem) {
       // sem = W_s2 . s0 + b ; s0 = relu(W_s0 . [h, enc] + b)
-      if ((rc = wgrad(w.g_raw + 4, C, g.sem_dim, b.s0, H, H, nullptr, 0, 0, 1, grads + g.w_s2, P, st))) return rc;
+      if ((rc = wgrad(w.g_raw + 4, C, g.sem_dim, b.s0, H, H, nullptr, 0, 0, 1, grads + g.w_s2, P, st, &w.tc))) return rc;
       if ((rc = bgrad(w.g_raw + 4, C, g.sem_dim, grads + g.b_s2, P, st))) return rc;
-      if ((rc = dgrad(w.g_raw + 4, C, g.sem_dim, prm + g.w_s2, H, 0, H, w.g_half, H, b.s0, 0, P, st))) return rc;
+      if ((rc = dgrad(w.g_raw + 4, C, g.sem_dim, prm + g.w_s2, H, 0, H, w.g_half, H, b.s0, 0, P, st, &w.tc))) return rc;
       if ((rc = wgrad(w.g_half, H, H, hl, W, W, g.sem_coord ? enc : nullptr, kEncLd, g.sem_coord ? g.enc : 0, 1,
-                      grads + g.w_s0, P, st))) return rc;
+                      grads + g.w_s0, P, st, &w.tc))) return rc;
       if ((rc = bgrad(w.g_half, H, H, grads + g.b_s0, P, st))) return rc;
       if (trunk) {
-        if ((rc = dgrad(w.g_half, H, H, prm + g.w_s0, g.sem_in, 0, W, w.G[0], W, nullptr, 0, P, st))) return rc;
+        if ((rc = dgrad(w.g_half, H, H, prm + g.w_s0, g.sem_in, 0, W, w.G[0], W, nullptr, 0, P, st, &w.tc))) return rc;
         have_G = true;
       }
     }
     if (!trunk) return NSOS_OK;
     // rgb = W_rgb . hv + b ; hv = relu(W_v . [feat, encv] + b) ; feat = W_f . h + b
-    if ((rc = wgrad(w.g_raw, C, 3, b.hv, H, H, nullptr, 0, 0, 1, grads + g.w_rgb, P, st))) return rc;
+    if ((rc = wgrad(w.g_raw, C, 3, b.hv, H, H, nullptr, 0, 0, 1, grads + g.w_rgb, P, st, &w.tc))) return rc;
     if ((rc = bgrad(w.g_raw, C, 3, grads + g.b_rgb, P, st))) return rc;
-    if ((rc = dgrad(w.g_raw, C, 3, prm + g.w_rgb, H, 0, H, w.g_half, H, b.hv, 0, P, st))) return rc;
-    if ((rc = wgrad(w.g_half, H, H, b.feat, W, W, encv, kEncVLd, g.encv, S, grads + g.w_views, P, st))) return rc;
+    if ((rc = dgrad(w.g_raw, C, 3, prm + g.w_rgb, H, 0, H, w.g_half, H, b.hv, 0, P, st, &w.tc))) return rc;
+    if ((rc = wgrad(w.g_half, H, H, b.feat, W, W, encv, kEncVLd, g.encv, S, grads + g.w_views, P, st, &w.tc))) return rc;
     if ((rc = bgrad(w.g_half, H, H, grads + g.b_views, P, st))) return rc;
-    if ((rc = dgrad(w.g_half, H, H, prm + g.w_views, W + g.encv, 0, W, w.g_feat, W, nullptr, 0, P, st))) return rc;
-    if ((rc = wgrad(w.g_feat, W, W, hl, W, W, nullptr, 0, 0, 1, grads + g.w_feat, P, st))) return rc;
+    if ((rc = dgrad(w.g_half, H, H, prm + g.w_views, W + g.encv, 0, W, w.g_feat, W, nullptr, 0, P, st, &w.tc))) return rc;
+    if ((rc = wgrad(w.g_feat, W, W, hl, W, W, nullptr, 0, 0, 1, grads + g.w_feat, P, st, &w.tc))) return rc;
     if ((rc = bgrad(w.g_feat, W, W, grads + g.b_feat, P, st))) return rc;
-    if ((rc = dgrad(w.g_feat, W, W, prm + g.w_feat, W, 0, W, w.G[0], W, nullptr, have_G ? 1 : 0, P, st))) return rc;
+    if ((rc = dgrad(w.g_feat, W, W, prm + g.w_feat, W, 0, W, w.G[0], W, nullptr, have_G ? 1 : 0, P, st, &w.tc))) return rc;
     // alpha = w_a . h + b
-    if ((rc = wgrad(w.g_raw + 3, C, 1, hl, W, W, nullptr, 0, 0, 1, grads + g.w_alpha, P, st))) return rc;
+    if ((rc = wgrad(w.g_raw + 3, C, 1, hl, W, W, nullptr, 0, 0, 1, grads + g.w_alpha, P, st, &w.tc))) return rc;
     if ((rc = bgrad(w.g_raw + 3, C, 1, grads + g.b_alpha, P, st))) return rc;
-    if ((rc = dgrad(w.g_raw + 3, C, 1, prm + g.w_alpha, W, 0, W, w.G[0], W, nullptr, 1, P, st))) return rc;
+    if ((rc = dgrad(w.g_raw + 3, C, 1, prm + g.w_alpha, W, 0, W, w.G[0], W, nullptr, 1, P, st, &w.tc))) return rc;
     k_relu_mask<<<grid1(P * W), 256, 0, st>>>(w.G[0], hl, P * W);
     NSOS_CHECK_CUDA(cudaGetLastError());
   }
@@ -296,13 +334,13 @@ int mlp_backward(const NetGeom& g, const float* prm, float* grads, const float* 
   for (int i = g.D - 1; i >= 0; --i) {
     const float* dpre = w.G[cur];
     const float* hin = (i > 0) ? b.h[i - 1] : nullptr;
-    if (i == 0) { if ((rc = wgrad(dpre, W, W, enc, kEncLd, g.enc, nullptr, 0, 0, 1, grads + g.w_pts[i], P, st))) return rc; }
-    else if (g.in_pts[i] == W) { if ((rc = wgrad(dpre, W, W, hin, W, W, nullptr, 0, 0, 1, grads + g.w_pts[i], P, st))) return rc; }
-    else { if ((rc = wgrad(dpre, W, W, enc, kEncLd, g.enc, hin, W, W, 1, grads + g.w_pts[i], P, st))) return rc; }
+    if (i == 0) { if ((rc = wgrad(dpre, W, W, enc, kEncLd, g.enc, nullptr, 0, 0, 1, grads + g.w_pts[i], P, st, &w.tc))) return rc; }
+    else if (g.in_pts[i] == W) { if ((rc = wgrad(dpre, W, W, hin, W, W, nullptr, 0, 0, 1, grads + g.w_pts[i], P, st, &w.tc))) return rc; }
+    else { if ((rc = wgrad(dpre, W, W, enc, kEncLd, g.enc, hin, W, W, 1, grads + g.w_pts[i], P, st, &w.tc))) return rc; }
     if ((rc = bgrad(dpre, W, W, grads + g.b_pts[i], P, st))) return rc;
     if (i > 0) {
       int k0 = (g.in_pts[i] == W) ? 0 : g.enc;   // h part of [enc, h]
-      if ((rc = dgrad(dpre, W, W, prm + g.w_pts[i], g.in_pts[i], k0, W, w.G[cur ^ 1], W, hin, 0, P, st))) return rc;
+      if ((rc = dgrad(dpre, W, W, prm + g.w_pts[i], g.in_pts[i], k0, W, w.G[cur ^ 1], W, hin, 0, P, st, &w.tc))) return rc;
       cur ^= 1;
     }
   }
@@ -421,7 +459,9 @@ int simt_render_fwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
 namespace {
 struct BwdWs {
   float *enc, *encv, *dnorm, *raw, *g_raw, *h[16], *feat, *hv, *s0, *G0, *G1, *g_half, *g_feat;
+  uint8_t* tc_scratch;
 };
+constexpr size_t kTcScratch = 2 * 256 * 256 * 2 * 2 + 4096;      // tc_rowgemm_scratch_bytes(256, 256) and some
 size_t carve_bwd(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& gf, int64_t R, char* base, BwdWs* ws) {
   int Sc = cfg.n_samples, Sf = cfg.n_samples + cfg.n_importance;
   int64_t P = R * (cfg.n_importance > 0 ? Sf : Sc);
@@ -434,8 +474,47 @@ size_t carve_bwd(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& gf,
   w.feat = c.take<float>(P * Wm); w.hv = c.take<float>(P * (Wm / 2 + 1)); w.s0 = c.take<float>(P * (Wm / 2 + 1));
   w.G0 = c.take<float>(P * Wm); w.G1 = c.take<float>(P * Wm); w.g_half = c.take<float>(P * (Wm / 2 + 1));
   w.g_feat = c.take<float>(P * Wm);
+  w.tc_scratch = c.take<uint8_t>(kTcScratch);
   if (ws) *ws = w;
   return align_up(c.off, 256);
+}
+}  // namespace
+
+// All-parameter backward in a tcgen05 mode: the recompute is ONE replay launch of kernel A per chunk that saves every hidden
+// layer of both nets (fp16 hi/lo arithmetic: the same activations, ReLU masks and raw outputs as the forward call), and the
+// large dgrad / wgrad products run on tc_rowgemm / tc_wgrad_gen.
+namespace {
+struct BwdAllWs {
+  float *enc, *encv, *dnorm, *g_raw, *G0, *G1, *g_half, *g_feat, *feat;
+  float *raw[2], *h[2][16], *hv[2], *s0[2];
+  uint8_t* scratch;
+};
+size_t carve_bwd_all(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& gf, int64_t R, char* base, BwdAllWs* ws) {
+  const bool fine = cfg.n_importance > 0;
+  const int Sc = cfg.n_samples, Sf = cfg.n_samples + cfg.n_importance;
+  const int64_t Pp[2] = {R * Sc, fine ? R * Sf : 0}, Pm = std::max(Pp[0], Pp[1]);
+  const int Wm = std::max(gc.W, gf.W), Cm = std::max(gc.C, gf.C);
+  Carver c{base, 0, 0};
+  BwdAllWs w{};
+  w.enc = c.take<float>(Pm * kEncLd); w.encv = c.take<float>(R * kEncVLd); w.dnorm = c.take<float>(R);
+  w.g_raw = c.take<float>(Pm * Cm);
+  w.G0 = c.take<float>(Pm * Wm); w.G1 = c.take<float>(Pm * Wm); w.g_half = c.take<float>(Pm * (Wm / 2 + 1));
+  w.g_feat = c.take<float>(Pm * Wm); w.feat = c.take<float>(Pm * Wm);
+  for (int p = 0; p < 2; ++p) {
+    const NetGeom& g = p ? gf : gc;
+    w.raw[p] = c.take<float>(Pp[p] * g.C + 1);
+    for (int i = 0; i < g.D; ++i) w.h[p][i] = c.take<float>(Pp[p] * g.W + 1);
+    w.hv[p] = c.take<float>(Pp[p] * (g.W / 2) + 1); w.s0[p] = c.take<float>(Pp[p] * (g.W / 2) + 1);
+  }
+  w.scratch = c.take<uint8_t>(kTcScratch);
+  if (ws) *ws = w;
+  return align_up(c.off, 256);
+}
+bool bwd_all_uses_tc(const NsosRenderCfg& cfg, int trunk, const NetGeom& gc, const NetGeom& gf, const void* packed_c, const void* packed_f) {
+  if (!trunk || !(cfg.mode == NSOS_MODE_TC_EXACT || cfg.mode == NSOS_MODE_TC_FAST) || getenv("NSOS_BWD_SIMT")) return false;
+  if (!packed_c || (cfg.n_importance > 0 && !packed_f) || cfg.n_samples > 128) return false;
+  if (gc.W != 256 || gf.W != 256 || !gc.use_viewdirs || !gf.use_viewdirs) return false;
+  return tc_net_supported(cfg.coarse) && (cfg.n_importance == 0 || tc_net_supported(cfg.fine));
 }
 }  // namespace
 
@@ -473,6 +552,9 @@ size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays,
   NetGeom gc, gf;
   if (!make_geom(cfg.coarse, gc)) return 0;
   if (cfg.n_importance > 0) { if (!make_geom(cfg.fine, gf)) return 0; } else gf = gc;
+  if (trunk && (cfg.mode == NSOS_MODE_TC_EXACT || cfg.mode == NSOS_MODE_TC_FAST))        // either all-parameter path may run
+    return std::max(carve_bwd_all(cfg, gc, gf, bwd_chunk_rays(n_rays), nullptr, nullptr),
+                    carve_bwd(cfg, gc, gf, bwd_chunk_rays(n_rays), nullptr, nullptr));
   if (bwd_uses_tc(cfg, trunk, gc, gf)) return carve_bwd_tc(cfg, gc, gf, bwd_tc_chunk_rays(n_rays), nullptr, nullptr);
   return carve_bwd(cfg, gc, gf, bwd_chunk_rays(n_rays), nullptr, nullptr);
 }
@@ -542,9 +624,59 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
         } else {
           MlpBufs b{};
           b.h[g.D - 1] = const_cast<float*>(h_p[pass]); b.s0 = const_cast<float*>(s_p[pass]);
-          BwdBufs bw{w.g_raw, {nullptr, nullptr}, w.g_half, nullptr};
+          BwdBufs bw{w.g_raw, {nullptr, nullptr}, w.g_half, nullptr, TcCtx{}};
           rc = mlp_backward(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, w.enc, w.encv, S, P, b, bw, 0, st);
         }
+        if (rc) return rc;
+      }
+    }
+    return NSOS_OK;
+  }
+  if (bwd_all_uses_tc(cfg, trunk, gc, gf, packed_c, packed_f)) {
+    const int64_t R = bwd_chunk_rays(n_rays);
+    BwdAllWs w;
+    size_t need = carve_bwd_all(cfg, gc, gf, R, (char*)workspace, &w);
+    NSOS_REQUIRE(workspace_bytes >= need, NSOS_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+    const int C6 = 6 + gc.sem_dim, ML = 2 * C6 + 1;
+    NsosRandoms rn{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (rnd) rn = *rnd;
+    TcCtx tcx;
+    tcx.on = true; tcx.scratch = w.scratch; tcx.scratch_bytes = kTcScratch;
+    for (int64_t r0 = 0; r0 < n_rays; r0 += R) {
+      const int64_t n = std::min(R, n_rays - r0);
+      const float* ro = rays_o + r0 * 3; const float* rd = rays_d + r0 * 3;
+      const float* zc = (fine ? z_vals0 : z_vals) + r0 * Sc;
+      const float* zf = fine ? z_vals + r0 * Sf : nullptr;
+      float* const raw2[2] = {w.raw[0], w.raw[1]};
+      float* const* const hall[2] = {w.h[0], w.h[1]};
+      float* const hv2[2] = {w.hv[0], w.hv[1]};
+      float* const s02[2] = {w.s0[0], w.s0[1]};
+      int rc = tc_render_replay_all(cfg, packed_c, fine ? packed_f : packed_c, ro, rd, zc, zf, raw2, hall, hv2, s02, n, st);
+      if (rc) return rc;
+      k_encode_dirs<<<grid1(n), 256, 0, st>>>(rd, w.encv, w.dnorm, n, gc.Lv);
+      for (int pass = 0; pass < (fine ? 2 : 1); ++pass) {
+        const bool is_fine = fine && pass == 1;
+        const NetGeom& g = is_fine ? gf : gc;
+        const float* prm = is_fine ? pf : pc;
+        float* grads = is_fine ? grads_f : grads_c;
+        const int S = is_fine ? Sf : Sc;
+        const float* z = is_fine ? zf : zc;
+        const float* noise = is_fine ? rn.noise1 : rn.noise0;
+        const int moff = (fine && !is_fine) ? C6 : 0;
+        const int64_t P = n * S;
+        k_encode_pts<<<grid1(P), 256, 0, st>>>(ro, rd, z, w.enc, P, S, g.Lp);
+        k_composite_bwd<<<grid1(n * 32, 128), 128, 0, st>>>(w.raw[pass], z, w.dnorm, noise ? noise + r0 * S : nullptr, cfg.raw_noise_std,
+                                                             seed, r0, is_fine ? RNG_NOISE1 : RNG_NOISE0, S, g.C, g.sem_dim,
+                                                             cfg.white_bkgd, g_maps + r0 * ML, ML, moff, w.g_raw, n);
+        NSOS_CHECK_CUDA(cudaGetLastError());
+        MlpBufs b{};
+        for (int i = 0; i < g.D; ++i) b.h[i] = w.h[pass][i];
+        b.feat = w.feat; b.hv = w.hv[pass]; b.s0 = w.s0[pass];
+        // feature_linear's output is folded away in the forward kernel (views fusion); the views weight gradient needs it
+        rc = gemm_dispatch(lin(b.h[g.D - 1], g.W, g.W, nullptr, 0, 0, 1, prm + g.w_feat, prm + g.b_feat, b.feat, g.W, P, g.W, 0), &tcx, st);
+        if (rc) return rc;
+        BwdBufs bw{w.g_raw, {w.G0, w.G1}, w.g_half, w.g_feat, tcx};
+        rc = mlp_backward(g, prm, grads, w.enc, w.encv, S, P, b, bw, trunk, st);
         if (rc) return rc;
       }
     }
@@ -576,13 +708,17 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
       MlpBufs b{};
       for (int i = 0; i < g.D; ++i) b.h[i] = w.h[i];
       b.feat = w.feat; b.hv = w.hv; b.s0 = w.s0;
-      int rc = mlp_forward(g, prm, w.enc, w.encv, S, P, b, w.raw, st);
+      // all-parameter backward in a tcgen05 mode: the large GEMMs of the recompute, of dgrad and of wgrad run on the tensor cores
+      TcCtx tcx;
+      tcx.on = false;                     // reached only in NSOS_MODE_SIMT_FP32 / NSOS_BWD_SIMT / unsupported geometry: all fp32
+      tcx.scratch = w.tc_scratch; tcx.scratch_bytes = kTcScratch;
+      int rc = mlp_forward(g, prm, w.enc, w.encv, S, P, b, w.raw, st, &tcx);
       if (rc) return rc;
       k_composite_bwd<<<grid1(n * 32, 128), 128, 0, st>>>(w.raw, z, w.dnorm, noise ? noise + r0 * S : nullptr, cfg.raw_noise_std, seed,
                                                            r0, is_fine ? RNG_NOISE1 : RNG_NOISE0, S, g.C, g.sem_dim, cfg.white_bkgd,
                                                            g_maps + r0 * ML, ML, moff, w.g_raw, n);
       NSOS_CHECK_CUDA(cudaGetLastError());
-      BwdBufs bw{w.g_raw, {w.G0, w.G1}, w.g_half, w.g_feat};
+      BwdBufs bw{w.g_raw, {w.G0, w.G1}, w.g_half, w.g_feat, tcx};
       rc = mlp_backward(g, prm, grads, w.enc, w.encv, S, P, b, bw, trunk, st);
       if (rc) return rc;
     }

@@ -31,6 +31,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "internal.h"
 #include "render_device.cuh"
 #include "render_group.cuh"
@@ -298,6 +300,9 @@ struct TcParams {
   const float* z_in[2];
   float* dump_h[2];    // [n_rays*S, W]   relu(pts_linears[D-1])
   float* dump_s0[2];   // [n_rays*S, W/2] relu(semantic_linear.0)
+  // MODE 3 (replay for the all-parameter backward): every hidden layer and the views hidden layer as well
+  float* dump_all[2][kMaxStages];   // [layer][n_rays*S, W]  relu(pts_linears[layer]); entries may be null
+  float* dump_hv[2];                // [n_rays*S, W/2] relu(views_linears.0)
 };
 constexpr int kTraceTiles = 16, kTraceStamps = 12;  // [tile][stage][stamp]; 5..8: a_ready[j] seen by the MMA lane, 9..11: worker 0 hands over slab 0..2
 
@@ -423,7 +428,9 @@ __host__ __device__ inline int build_ctab(const TcProg& pg, bool exact, uint32_t
 struct MmaState {
   RingPos pos;
   uint32_t gs, gpar, apar;
+  uint32_t fmt = 0;      // OR-ed into the instruction descriptor: 0 = fp16 operands, kIdescBf16 = bf16 operands (row GEMM)
 };
+constexpr uint32_t kIdescBf16 = (1u << 7) | (1u << 10);
 
 // All stages of one tile.  Called by the ELECTED LANE ONLY (the caller holds the elect block around the whole kernel loop).
 // Issue-side latency matters (tools/umma_queue.cu): the ring position is tracked incrementally, and the mbarrier wait for the
@@ -460,7 +467,7 @@ __device__ __forceinline__ void mma_tile(const uint32_t* __restrict__ tab, int n
       tc_fence_after();
       if (trace) trace[st * kTraceStamps + 5 + asrc] = clock64();
     }
-    const uint32_t idesc = make_idesc_f16((int)((w >> 3) & 63u) << 3);
+    const uint32_t idesc = make_idesc_f16((int)((w >> 3) & 63u) << 3) | ms.fmt;
     const uint32_t a_hi = acol + asrc * 64;
     // full[pos.slot] of THIS chunk was already waited for (inside the previous chunk, or before the first tile)
     const uint32_t b = ring + ms.pos.slot * kSlotBytes;
@@ -552,7 +559,7 @@ __device__ __forceinline__ void encode_half(const float x[3], int L, int enc, bo
 // (+relu) feeds the fp32 head accumulators (head weights are pre-divided by 16) and/or becomes the next A operand.
 constexpr int kCW = 16;   // epilogue chunk width in columns (one tcgen05.ld) = one K-step of the next layer
 constexpr int kSW = 16;   // arithmetic sub-block of a chunk
-template <int KIND, bool EXACT, bool DUMP>
+template <int KIND, bool EXACT, bool DUMP, bool DALL = false>
 __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
                                         const float* __restrict__ hw, int sem_dim, float (&hacc)[4], float (&hodd)[4],
                                         float* __restrict__ gout, float& vmax) {
@@ -606,7 +613,7 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
           hodd[s] = fmaf(hw[kHeadWS2 + s * kHalfMax + c0 + j + 1], x1, hodd[s]);
         }
     }
-    if (DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_SEM_WIDE) && gout) {
+    if (((DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_SEM_WIDE)) || (DALL && (KIND == EPI_HIDDEN || KIND == EPI_RGB))) && gout) {
       // saved activations: 16-byte stores (rows are W resp. W/2 floats, c0 + j a multiple of 4 on the odd pair)
       if (j & 2) *reinterpret_cast<float4*>(gout + c0 + j - 2) = make_float4(dq0, dq1, x0 * (1.f / kActScale), x1 * (1.f / kActScale));
       else { dq0 = x0 * (1.f / kActScale); dq1 = x1 * (1.f / kActScale); }
@@ -629,13 +636,13 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
   }
 }
 
-template <int KIND, bool EXACT, bool DUMP>
+template <int KIND, bool EXACT, bool DUMP, bool DALL = false>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
                                           const float* __restrict__ hw, int sem_dim, float (&hacc)[4], float (&hodd)[4],
                                           float* __restrict__ gout, float& vmax) {
 #pragma unroll
   for (int sb = 0; sb < kCW / kSW; ++sb)
-    epi_sub<KIND, EXACT, DUMP>(&v[kSW * sb], tm_lane, c0 + kSW * sb, inv16, bias, hw, sem_dim, hacc, hodd, gout, vmax);
+    epi_sub<KIND, EXACT, DUMP, DALL>(&v[kSW * sb], tm_lane, c0 + kSW * sb, inv16, bias, hw, sem_dim, hacc, hodd, gout, vmax);
 }
 __device__ __forceinline__ void tmem_ldc(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 __device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[16]) { tmem_wait_ld_fence16(r); }
@@ -646,7 +653,7 @@ __device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[16]) { tmem_wait_ld_
 // hand the slab to the MMA warp once their part is stored, so the next stage's MMAs start after a fraction of the epilogue
 // instead of all of it.  Slab 0 is handed over in two halves (K-steps 0-1 after the first chunk of every warp, 2-3 after the
 // second): a_ready[0], a_ready[1]; slab j >= 1 uses a_ready[1+j].
-template <int KIND, bool EXACT, bool DUMP>
+template <int KIND, bool EXACT, bool DUMP, bool DALL = false>
 __device__ __forceinline__ void epi_kind(int cb, int ce, int hf, uint32_t tm_lane, float inv16, const float* bias, const float* hw,
                                          int sem_dim, float* hacc, float* gout, float& vmax, uint32_t a_ready0, long long* trs = nullptr) {
   constexpr bool SLAB = (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA);
@@ -662,12 +669,12 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, int hf, uint32_t tm_lan
   tmem_wait_ldc(va);
   for (int i = 0; i < cnt; i += 2) {
     if (i + 1 < cnt) tmem_ldc(tm_lane + col(i + 1), vb);
-    epi_chunk<KIND, EXACT, DUMP>(va, tm_lane, col(i), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
+    epi_chunk<KIND, EXACT, DUMP, DALL>(va, tm_lane, col(i), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
     if (SLAB && i == 0) { hand_over(0u); if (trs) trs[9] = clock64(); }
     if (i + 1 < cnt) {
       tmem_wait_ldc(vb);
       if (i + 2 < cnt) tmem_ldc(tm_lane + col(i + 2), va);
-      epi_chunk<KIND, EXACT, DUMP>(vb, tm_lane, col(i + 1), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
+      epi_chunk<KIND, EXACT, DUMP, DALL>(vb, tm_lane, col(i + 1), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
       if (SLAB) {                       // my chunks of slab i/2 are stored
         hand_over(1u + (uint32_t)(i >> 1));
         if (trs && (i >> 1) < 2) trs[10 + (i >> 1)] = clock64();
@@ -684,11 +691,11 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, int hf, uint32_t tm_lan
   }
 }
 
-template <bool EXACT, bool DUMP = false>
+template <bool EXACT, bool DUMP = false, bool DALL = false>
 __device__ __forceinline__ void epilogue(int kind, int cb, int ce, int hf, uint32_t tm_lane, float inv16, const float* bias,
                                          const float* hw, int sem_dim, float* hacc, float* gout, float& vmax, uint32_t a_ready0,
                                          long long* trs = nullptr) {
-#define NSOS_EPI(K) epi_kind<K, EXACT, DUMP>(cb, ce, hf, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax, a_ready0, trs)
+#define NSOS_EPI(K) epi_kind<K, EXACT, DUMP, DALL>(cb, ce, hf, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax, a_ready0, trs)
   switch (kind) {
     case EPI_HIDDEN: NSOS_EPI(EPI_HIDDEN); break;
     case EPI_HIDDEN_SIGMA: NSOS_EPI(EPI_HIDDEN_SIGMA); break;
@@ -725,10 +732,11 @@ __device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int wa
 }
 
 // MODE 0: forward.  MODE 1: forward that also saves h_last / s_hid per point (training).  MODE 2: replay at given sample
-// depths (backward recompute: no sampling, no compositing) with the same saves.
+// depths (backward recompute: no sampling, no compositing) with the same saves.  MODE 3: replay that saves EVERY hidden layer and
+// the views hidden layer (recompute of the all-parameter backward).
 template <bool EXACT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant__ TcParams P) {
-  constexpr bool REPLAY = (MODE == 2), DUMP = (MODE >= 1);
+  constexpr bool REPLAY = (MODE >= 2), DUMP = (MODE >= 1), DALL = (MODE == 3);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   Smem sm;
@@ -930,9 +938,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               const size_t pt = (size_t)ray * S + i;
               if (Sg.epi == EPI_HIDDEN_SIGMA && P.dump_h[pass]) gout = P.dump_h[pass] + pt * pg.W;
               if (sem_part && P.dump_s0[pass]) gout = P.dump_s0[pass] + pt * pg.H2;
+              if (DALL) {
+                if (Sg.epi == EPI_HIDDEN && P.dump_all[pass][st]) gout = P.dump_all[pass][st] + pt * pg.W;
+                if (rgb_part && P.dump_hv[pass]) gout = P.dump_hv[pass] + pt * pg.H2;
+              }
             }
             const int kind = merged ? (hf ? EPI_RGB : EPI_SEM) : Sg.epi;
-            epilogue<EXACT, DUMP>(kind, cb, ce, hf, tm_d + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout, vmax, a_ready0,
+            epilogue<EXACT, DUMP, DALL>(kind, cb, ce, hf, tm_d + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout, vmax, a_ready0,
                                   tr ? tr + st * kTraceStamps : nullptr);
             if (Sg.epi == EPI_HIDDEN_SIGMA && hf == 1) sm.hpart[row * 8] = hacc[0];   // sigma share of the upper column half
             if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
@@ -1120,6 +1132,140 @@ __global__ void __launch_bounds__(kThreads, 1) k_selftest(const __grid_constant_
   if (warp == kMmaWarp) tmem_dealloc(tm, kTmemCols);
 }
 
+// ---- row GEMM: C[P,N] (=|+=) epi(A[P,K] . B[K,N]) for the all-parameter backward (dgrad products, feature_linear) ----------
+// The same pipeline as a one-stage tile of the render kernel: the eight worker warps read 128 rows of A (fp32, global),
+// split every value into bf16 hi + lo (fp32 range: gradients sit far below the fp16 range) and store them as the TMEM A
+// operand; B (a weight matrix or its transpose, <= 256 x 256) is packed once per call into bf16 hi/lo SWIZZLE_128B slabs and
+// streamed through the bulk-copy ring; 3 MMAs per product (hi.hi + lo.hi + hi.lo, fp32 accumulate); the epilogue applies
+// bias / ReLU / ReLU-mask / accumulate and writes fp32 rows.  Persistent CTAs over 128-row tiles.
+struct RowGemmParams {
+  TcProg prog;
+  uint32_t ctab[kCtabMax];
+  int nch;
+  const uint8_t* packed;      // slab image; producer_tile reads from packed + kAuxBytes
+  const float* A; long long lda; int K;      // K in {64,128,192,256}
+  float* C; long long ldc; int N;            // N multiple of 32, <= 256
+  const float* mask; long long mask_ld;      // keep where mask(m,n) > 0
+  const float* bias;
+  int accumulate, relu;
+  long long P;
+  int nslots;
+};
+// B(k,n) = B[k*b_rs + n*b_cs]  ->  per 64-wide K slab: bf16 hi plane [N x 64] then lo plane, K-major SWIZZLE_128B
+__global__ void k_pack_b_bf16(const float* __restrict__ B, long long b_rs, long long b_cs, int K, int N, uint8_t* __restrict__ out) {
+  const int j = blockIdx.x;                                   // K slab
+  uint8_t* hi = out + (size_t)j * 2 * N * 128;
+  uint8_t* lo = hi + (size_t)N * 128;
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < N * 64; e += gridDim.y * blockDim.x) {
+    const int n = e >> 6, k = e & 63, kk = 64 * j + k;
+    const float w = kk < K ? B[(long long)kk * b_rs + (long long)n * b_cs] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const size_t byte = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(hi + byte) = h;
+    *reinterpret_cast<__nv_bfloat16*>(lo + byte) = l;
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+__global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__ RowGemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Smem sm;
+  carve_smem(base, P.nslots, 2, 2, 8, &sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  init_pipeline(sm, P.nslots, warp, 1);
+  const uint32_t tm = *sm.tmem_ptr;
+  const long long ntiles = (P.P + 127) / 128;
+  const long long my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;      // >= 1 (grid <= ntiles)
+  if (warp >= kProducerWarp + kNumProducers) {
+  } else if (warp >= kProducerWarp) {
+    uint32_t chunk = 0;
+    for (long long it = 0; it < my_tiles; ++it) producer_tile(P.prog, P.packed, true, sm, P.nslots, chunk, 0, 1, warp - kProducerWarp);
+  } else if (warp == kMmaWarp) {
+    for (int i = lane; i < kCtabMax; i += 32) sm.ctab[i] = P.ctab[i];
+    __syncwarp();
+    if (elect_one()) {
+      MmaState ms{RingPos{0u, 0u}, 0u, 0u, 0u, kIdescBf16};
+      mbar_wait(smem_u32(&sm.full[0]), 0u, 299);
+      tc_fence_after();
+      for (long long it = 0; it < my_tiles; ++it) mma_tile(sm.ctab, P.nch, sm, (uint32_t)P.nslots, tm, ms, 1, it == my_tiles - 1);
+    }
+    __syncwarp();
+  } else {
+    const int q4 = warp & 3, hf = warp >> 2, row = q4 * 32 + lane;
+    const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
+    const int nka = P.K / 16, nkc = P.N / 16;            // 16-column chunks of A (K) and of C (N)
+    uint32_t it_acc = 0;
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long r = ((long long)blockIdx.x + it * gridDim.x) * 128 + row;
+      const bool valid = r < P.P;
+      const uint32_t dbuf = (uint32_t)(it & 1) * kBufCols, abuf = dbuf ^ kBufCols;
+      // ---- A rows -> bf16 hi/lo -> TMEM (K-step c: hi pairs at columns 16c.., lo pairs at 16c+8..)
+      const float* arow = P.A + r * P.lda;
+      for (int c = hf * (nka / 2); c < (hf + 1) * (nka / 2); ++c) {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t4 = valid ? __ldg(reinterpret_cast<const float4*>(arow + 16 * c) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
+          hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lo[j >> 1] = pack_bf16x2(v[j] - __bfloat162float(h0), v[j + 1] - __bfloat162float(h1));
+        }
+        tmem_st8(tm_lane + abuf + 16 * c, hi);
+        tmem_st8(tm_lane + abuf + 16 * c + kALo, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(smem_u32(sm.g_ready));
+      for (int j = 0; j < kMaxASlabs; ++j) mbar_arrive(smem_u32(&sm.a_ready[j]));
+      mbar_wait(smem_u32(sm.acc_full), it_acc & 1u, 600);
+      ++it_acc;
+      tc_fence_after();
+      // ---- epilogue: D -> (+bias) (relu) (mask) (+C) -> global
+      float* crow = P.C + r * P.ldc;
+      const float* mrow = P.mask ? P.mask + r * P.mask_ld : nullptr;
+      for (int c = hf * (nkc / 2); c < (hf + 1) * (nkc / 2); ++c) {
+        uint32_t vr[16];
+        tmem_ld16(tm_lane + dbuf + 16 * c, vr);
+        tmem_wait_ld_fence16(vr);
+        if (!valid) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float x[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            x[i] = __uint_as_float(vr[4 * q + i]);
+            if (P.bias) x[i] += __ldg(&P.bias[16 * c + 4 * q + i]);
+            if (P.relu) x[i] = fmaxf(x[i], 0.f);
+          }
+          if (mrow) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + 16 * c) + q);
+            if (!(m4.x > 0.f)) x[0] = 0.f;
+            if (!(m4.y > 0.f)) x[1] = 0.f;
+            if (!(m4.z > 0.f)) x[2] = 0.f;
+            if (!(m4.w > 0.f)) x[3] = 0.f;
+          }
+          float4* dst = reinterpret_cast<float4*>(crow + 16 * c) + q;
+          if (P.accumulate) { const float4 o = *dst; x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
+          *dst = make_float4(x[0], x[1], x[2], x[3]);
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(1, kWorkers);          // every worker is done with D(it) before anyone refills that buffer as A(it+1)
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tm, kTmemCols);
+}
+
 int run_pack(const PackPlan& plan, const NetGeom* g, const float* params, void* packed, cudaStream_t st) {
   TcAux* aux = reinterpret_cast<TcAux*>(packed);
   uint8_t* img = reinterpret_cast<uint8_t*>(packed);
@@ -1167,6 +1313,8 @@ struct ReplayIO {
   const float* z_in[2];
   float* dump_h[2];
   float* dump_s0[2];
+  float* const* dump_all[2] = {nullptr, nullptr};   // [layer] per pass (all-parameter backward) or null
+  float* dump_hv[2] = {nullptr, nullptr};
 };
 
 // common launcher of k_render_tc: forward (replay == nullptr) or backward recompute on given sample depths
@@ -1196,7 +1344,10 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
   P.perturb = cfg.perturb; P.noise_std = cfg.raw_noise_std; P.white_bkgd = cfg.white_bkgd; P.exact = exact; P.fine = fine;
   P.C = gc.C; P.sem_dim = gc.sem_dim; P.C6 = 6 + gc.sem_dim; P.ML = 2 * P.C6 + 1;
   if (replay) {
-    for (int i = 0; i < 2; ++i) { P.z_in[i] = replay->z_in[i]; P.dump_h[i] = replay->dump_h[i]; P.dump_s0[i] = replay->dump_s0[i]; }
+    for (int i = 0; i < 2; ++i) {
+      P.z_in[i] = replay->z_in[i]; P.dump_h[i] = replay->dump_h[i]; P.dump_s0[i] = replay->dump_s0[i]; P.dump_hv[i] = replay->dump_hv[i];
+      if (replay->dump_all[i]) for (int l = 0; l < kMaxStages; ++l) P.dump_all[i][l] = replay->dump_all[i][l];
+    }
   } else if (fine) {
     P.dump_h[0] = out.h_last0; P.dump_s0[0] = out.s_hid0; P.dump_h[1] = out.h_last; P.dump_s0[1] = out.s_hid;
   } else {
@@ -1244,7 +1395,9 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
     if (e != cudaSuccess) return e;
     return cudaLaunchKernelEx(&lc, kern, P);
   };
-  if (replay) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 2>) : launch(k_render_tc<false, 2>));
+  const bool replay_all = replay && (replay->dump_all[0] || replay->dump_all[1]);
+  if (replay_all) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 3>) : launch(k_render_tc<false, 3>));
+  else if (replay) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 2>) : launch(k_render_tc<false, 2>));
   else if (dump) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 1>) : launch(k_render_tc<false, 1>));
   else NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 0>) : launch(k_render_tc<false, 0>));
   NSOS_CHECK_CUDA(cudaGetLastError());
@@ -1274,6 +1427,68 @@ int tc_render_replay(const NsosRenderCfg& cfg, const void* packed_c, const void*
   memset(&out, 0, sizeof(out));
   const bool fine = cfg.n_importance > 0;
   if (fine) { out.raw0 = raw0; out.raw = raw1; } else { out.raw = raw0; }
+  return tc_launch(cfg, packed_c, packed_f, rays_o, rays_d, nullptr, nullptr, nullptr, 0, out, &io, nullptr, 0, n_rays, st);
+}
+
+// C[P,N] (=|+=) epi(A[P,K] . B),  B(k,n) = B[k*b_rs + n*b_cs].  scratch: >= tc_rowgemm_scratch_bytes(K, N).
+size_t tc_rowgemm_scratch_bytes(int K, int N) { return (size_t)((K + 63) / 64) * 2 * N * 128 + 1024; }
+bool tc_rowgemm_supported(int K, int N, int64_t lda, int64_t ldc, int64_t mask_ld) {
+  return K >= 64 && K <= 256 && K % 32 == 0 && N >= 32 && N <= 256 && N % 32 == 0 && lda % 4 == 0 && ldc % 4 == 0 && mask_ld % 4 == 0;
+}
+int tc_rowgemm(const float* A, int64_t lda, int K, const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int N,
+               const float* mask, int64_t mask_ld, const float* bias, int relu, int accumulate, int64_t P, void* scratch,
+               size_t scratch_bytes, cudaStream_t st) {
+  NSOS_REQUIRE(tc_rowgemm_supported(K, N, lda, ldc, mask ? mask_ld : 0), NSOS_ERR_UNSUPPORTED, "tc_rowgemm: unsupported shape K=%d N=%d", K, N);
+  NSOS_REQUIRE(scratch && scratch_bytes >= tc_rowgemm_scratch_bytes(K, N), NSOS_ERR_WORKSPACE, "tc_rowgemm: scratch too small");
+  if (P <= 0) return NSOS_OK;
+  RowGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int nsl = (K + 63) / 64;
+  p.prog.nst = 1; p.prog.W = N;
+  TcStage& S = p.prog.st[0];
+  S.n = N; S.epi = EPI_RAW; S.nslab = nsl;
+  for (int j = 0; j < nsl; ++j) { S.sn[j] = N; S.asrc[j] = j; }
+  p.nch = build_ctab(p.prog, true, p.ctab);
+  uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch) + 1023) / 1024 * 1024);
+  k_pack_b_bf16<<<dim3(nsl, 8), 256, 0, st>>>(B, b_rs, b_cs, K, N, img);
+  p.packed = img - kAuxBytes;          // producer_tile skips the aux header
+  p.A = A; p.lda = lda; p.K = nsl * 64; p.C = C; p.ldc = ldc; p.N = N; p.mask = mask; p.mask_ld = mask_ld; p.bias = bias;
+  p.accumulate = accumulate; p.relu = relu; p.P = P; p.nslots = 5;
+  // a K that is not a multiple of 64 (e.g. 96) is zero-padded in B; A columns beyond K must not be read: require K % 64 == 0 there
+  NSOS_REQUIRE(K % 64 == 0, NSOS_ERR_UNSUPPORTED, "tc_rowgemm: K must be a multiple of 64");
+  int dev = 0, sms = 0;
+  NSOS_CHECK_CUDA(cudaGetDevice(&dev));
+  NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long ntiles = (P + 127) / 128;
+  const int grid = (int)std::min<long long>(ntiles, sms);
+  const size_t need = carve_smem(nullptr, p.nslots, 2, 2, 8, nullptr) + 1024;
+  NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_rowgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  k_rowgemm<<<grid, kThreads, need, st>>>(p);
+  NSOS_CHECK_CUDA(cudaGetLastError());
+  return NSOS_OK;
+}
+
+// Recompute of the all-parameter backward: both nets at the saved sample depths, every hidden layer saved.
+// h_all[pass][layer] -> [n_rays*S, W] (layer < D), hv / s0 [n_rays*S, W/2], raw [n_rays*S, C].  Entries of pass 1 are ignored
+// without a fine pass.
+int tc_render_replay_all(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
+                         const float* z0, const float* z1, float* const raw[2], float* const* const h_all[2], float* const hv[2],
+                         float* const s0[2], int64_t n_rays, cudaStream_t st) {
+  NetGeom gc, gf;
+  NSOS_REQUIRE(make_geom(cfg.coarse, gc), NSOS_ERR_UNSUPPORTED, "invalid coarse net descriptor");
+  const bool fine = cfg.n_importance > 0;
+  if (fine) NSOS_REQUIRE(make_geom(cfg.fine, gf), NSOS_ERR_UNSUPPORTED, "invalid fine net descriptor"); else gf = gc;
+  ReplayIO io;
+  io.z_in[0] = z0; io.z_in[1] = z1;
+  for (int p = 0; p < 2; ++p) {
+    const NetGeom& g = p ? gf : gc;
+    io.dump_all[p] = h_all[p];
+    io.dump_h[p] = h_all[p] ? h_all[p][g.D - 1] : nullptr;       // the last trunk layer goes through the EPI_HIDDEN_SIGMA save
+    io.dump_s0[p] = s0[p]; io.dump_hv[p] = hv[p];
+  }
+  NsosRenderOut out;
+  memset(&out, 0, sizeof(out));
+  if (fine) { out.raw0 = raw[0]; out.raw = raw[1]; } else { out.raw = raw[0]; }
   return tc_launch(cfg, packed_c, packed_f, rays_o, rays_d, nullptr, nullptr, nullptr, 0, out, &io, nullptr, 0, n_rays, st);
 }
 

@@ -268,6 +268,152 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_sem_wgrad(const __grid_consta
   if (warp == kWgMmaWarp) tmem_dealloc(tm, kWgTmemCols);
 }
 
+
+// ---- general weight gradient: dW[Mo, Ki] += dY[P, Mo]^T . X[P, Ki]  (the all-parameter backward, trainer.py:201 with every parameter
+// trainable).  Same transposing fill and bf16 hi/lo contraction over points as k_sem_wgrad, for any layer:
+//   A  [128 x 64 pts] = dY[:, m0:m0+128]^T (one 128-row block of dW per blockIdx.y)
+//   B  [320 x 64 pts] = [main (256 wide, e.g. the previous layer's activations) ; aux (<= 64 wide, e.g. gamma(x))]^T
+// D[:, 0:256] accumulates the `main` columns of dW, D[:, 256:320] the `aux` columns, for the whole life of the CTA.
+struct WgGenParams {
+  const float* dY; long long ldy; int Mo;
+  const float* main; long long ld_main; int main_col;      // may be null
+  const float* aux; long long ld_aux; int aux_w, aux_col;  // may be null; aux_w <= 64
+  float* dW; long long ldw;
+  long long P;
+};
+struct WgGenSmem {
+  uint8_t *a[2], *b[2];
+  uint64_t *ready, *done;
+  uint32_t* tmem_ptr;
+};
+__host__ __device__ inline size_t wgg_carve(uint8_t* base, WgGenSmem* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; size_t o = off; off += bytes; return o; };
+  size_t oa[2], ob[2];
+  for (int p = 0; p < 2; ++p) oa[p] = take(kRowsA * 128, 1024);
+  for (int p = 0; p < 2; ++p) ob[p] = take(kRowsB * 128, 1024);
+  size_t obar = take(16, 8), otp = take(16, 16);
+  if (s) {
+    for (int p = 0; p < 2; ++p) { s->a[p] = base + oa[p]; s->b[p] = base + ob[p]; }
+    s->ready = (uint64_t*)(base + obar); s->done = s->ready + 1; s->tmem_ptr = (uint32_t*)(base + otp);
+  }
+  return off;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen(const __grid_constant__ WgGenParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  WgGenSmem sm;
+  wgg_carve(base, &sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+  const int m0 = blockIdx.y * 128;
+  const long long nslabs = (P.P + kSlabPts - 1) / kSlabPts;
+  const long long my_slabs = (nslabs - blockIdx.x + gridDim.x - 1) / gridDim.x;     // >= 1 (grid.x <= nslabs)
+  const bool has_main = P.main != nullptr, has_aux = P.aux != nullptr;
+  if (t == 0) {
+    mbar_init(smem_u32(sm.ready), kWgWorkers);
+    mbar_init(smem_u32(sm.done), 1);
+    fence_mbar_init();
+  }
+  if (warp == kWgMmaWarp) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *sm.tmem_ptr;
+
+  if (warp == kWgMmaWarp) {
+    const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])};
+    const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64);
+    for (long long it = 0; it < my_slabs; ++it) {
+      mbar_wait(smem_u32(sm.ready), (uint32_t)(it & 1), 730);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;     // hi.hi, lo.hi, hi.lo
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (it > 0 || pass > 0 || ks > 0) ? 1u : 0u;
+            const uint64_t da = make_sw128_desc(a[pa] + ks * 32);
+            if (has_main) umma_ss(tm + kColD1, da, make_sw128_desc(b[pb] + ks * 32), id256, acc);
+            if (has_aux) umma_ss(tm + kColD1b, da, make_sw128_desc(b[pb] + 256 * 128 + ks * 32), id64, acc);
+          }
+        }
+        umma_commit(smem_u32(sm.done));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int pgp = warp & 1, q = warp >> 1;            // point group (32 points), feature quarter
+    const int pl = 32 * pgp + lane, wd = pl >> 1;
+    for (long long it = 0; it < my_slabs; ++it) {
+      const long long slab = blockIdx.x + it * gridDim.x;
+      const long long p = slab * kSlabPts + pl;
+      const bool valid = p < P.P;
+      float hv[4][8];                                   // rolling window over this thread's 64 `main` values
+      const float* hrow = has_main ? P.main + p * P.ld_main + q * 64 : nullptr;
+      if (has_main) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) load8(hrow + 8 * g8, valid, hv[g8]);
+      }
+      float gv[4][8];                                   // this thread's 32 dY values (units m0 + q*32 ..)
+      {
+        const float* grow = P.dY + p * P.ldy + m0 + q * 32;
+        const bool gval = valid && (m0 + q * 32 < P.Mo);
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) load8(grow + 8 * g8, gval, gv[g8]);
+      }
+      if (it > 0) { mbar_wait(smem_u32(sm.done), (uint32_t)((it - 1) & 1), 740); tc_fence_after(); }
+      if (has_main) {
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8) {
+          put8(sm.b[0], sm.b[1], q * 64 + 8 * g8, hv[g8 & 3], lane, wd);
+          if (g8 + 4 < 8) load8(hrow + 8 * (g8 + 4), valid, hv[g8 & 3]);
+        }
+      }
+      if (has_aux) {
+        // aux rows (ld_aux may be odd-sized: scalar loads), zero beyond aux_w
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const int e0 = q * 16 + 8 * g8;
+          float ev[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ev[i] = (valid && e0 + i < P.aux_w) ? __ldg(&P.aux[p * P.ld_aux + e0 + i]) : 0.f;
+          put8(sm.b[0], sm.b[1], 256 + e0, ev, lane, wd);
+        }
+      }
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) put8(sm.a[0], sm.a[1], q * 32 + 8 * g8, gv[g8], lane, wd);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(smem_u32(sm.ready));
+    }
+    // ---- epilogue: TMEM partial sums -> global gradients (atomics; every CTA contributes)
+    mbar_wait(smem_u32(sm.done), (uint32_t)((my_slabs - 1) & 1), 750);
+    tc_fence_after();
+    const int q4 = warp & 3, hf = warp >> 2;
+    const int u = m0 + q4 * 32 + lane;
+    const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
+    for (int c = hf * 10; c < hf * 10 + 10; ++c) {
+      if (c < 16 ? !has_main : !has_aux) continue;
+      uint32_t r[16];
+      tmem_ld16(tm_lane + kColD1 + c * 16, r);
+      tmem_wait_ld_fence16(r);
+      if (u >= P.Mo) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int f = c * 16 + j;
+        const float x = __uint_as_float(r[j]);
+        if (f < 256) atomicAdd(&P.dW[(size_t)u * P.ldw + P.main_col + f], x);
+        else if (f - 256 < P.aux_w) atomicAdd(&P.dW[(size_t)u * P.ldw + P.aux_col + (f - 256)], x);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWgMmaWarp) tmem_dealloc(tm, kWgTmemCols);
+}
+
 }  // namespace
 
 bool tc_sem_wgrad_supported(const NetGeom& g) {
@@ -297,4 +443,32 @@ int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* 
   return NSOS_OK;
 }
 
+}  // namespace nsos
+
+namespace nsos {
+// dW[Mo, .] += dY[P, Mo]^T . [main (256 wide) | aux (aux_w <= 64 wide)]:  columns main_col.. / aux_col.. of dW (row pitch ldw).
+bool tc_wgrad_gen_supported(int Mo, int64_t ldy, int main_w, int64_t ld_main, int aux_w) {
+  return (Mo == 128 || Mo == 256) && ldy % 4 == 0 && (main_w == 0 || (main_w == 256 && ld_main % 4 == 0)) && aux_w >= 0 && aux_w <= 64 &&
+         (main_w > 0 || aux_w > 0);
+}
+int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_t ld_main, int main_col, const float* aux, int64_t ld_aux,
+                 int aux_w, int aux_col, float* dW, int64_t ldw, int64_t P, cudaStream_t st) {
+  NSOS_REQUIRE(tc_wgrad_gen_supported(Mo, ldy, main ? 256 : 0, ld_main, aux ? aux_w : 0), NSOS_ERR_UNSUPPORTED, "tc_wgrad_gen: unsupported shape");
+  if (P <= 0) return NSOS_OK;
+  WgGenParams p;
+  memset(&p, 0, sizeof(p));
+  p.dY = dY; p.ldy = ldy; p.Mo = Mo; p.main = main; p.ld_main = ld_main; p.main_col = main_col;
+  p.aux = aux; p.ld_aux = ld_aux; p.aux_w = aux ? aux_w : 0; p.aux_col = aux_col; p.dW = dW; p.ldw = ldw; p.P = P;
+  int dev = 0, sms = 0;
+  NSOS_CHECK_CUDA(cudaGetDevice(&dev));
+  NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long nslabs = (P + kSlabPts - 1) / kSlabPts;
+  const int mb = Mo / 128;
+  const int gx = (int)std::min<long long>(nslabs, std::max(1, sms / mb));
+  const size_t need = wgg_carve(nullptr, nullptr) + 1024;
+  NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  k_wgrad_gen<<<dim3(gx, mb), kWgThreads, need, st>>>(p);
+  NSOS_CHECK_CUDA(cudaGetLastError());
+  return NSOS_OK;
+}
 }  // namespace nsos

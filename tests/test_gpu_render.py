@@ -552,3 +552,60 @@ def test_wide_encodings_fail_loudly():
                 net(rays, (1.0, 2.0))
         with pytest.raises(_lib.NsosError):
             net.nerf(torch.rand(5, 3, device=DEV), viewdirs=torch.rand(5, 3, device=DEV))
+
+
+@pytest.mark.parametrize("K,N,P,trans,opts", [(256, 256, 1000, True, "mask"), (128, 256, 300, True, "acc"), (256, 256, 64, False, "bias_relu"),
+                                              (64, 128, 129, False, "")])
+def test_rowgemm_building_block(K, N, P, trans, opts):
+    """tcgen05 row GEMM of the all-parameter backward (bf16 hi/lo, 3 MMAs per product) vs fp64."""
+    _lib, _ = _imports()
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(K + N + P)
+    a = (torch.randn(P, K, generator=g) * torch.logspace(-6, 0, K)[None]).to(DEV)          # gradient-like dynamic range
+    w = (torch.randn(K, N, generator=g) * 0.2).to(DEV)                                      # B(k,n)
+    bt = w.t().contiguous() if trans else w                                                  # stored [N,K] (k contiguous) or [K,N]
+    b_rs, b_cs = (1, K) if trans else (N, 1)
+    c = torch.randn(P, N, generator=g).to(DEV)
+    c0 = c.clone()
+    mask = torch.randn(P, N, generator=g).to(DEV) if "mask" in opts else None
+    bias = torch.randn(N, generator=g).to(DEV) if "bias" in opts else None
+    scratch = torch.zeros(2 * K * N * 2 + 4096, dtype=torch.uint8, device=DEV)
+    _lib.check(L.nsos_selftest_rowgemm(_lib.ptr(a), K, K, _lib.ptr(bt), b_rs, b_cs, _lib.ptr(c), N, N, _lib.ptr(mask), N, _lib.ptr(bias),
+                                       int("relu" in opts), int("acc" in opts), P, _lib.ptr(scratch), scratch.numel(), None), "rowgemm")
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double()
+    if bias is not None:
+        ref = ref + bias.double()
+    if "relu" in opts:
+        ref = ref.clamp_min(0)
+    if mask is not None:
+        ref = torch.where(mask > 0, ref, torch.zeros_like(ref))
+    if "acc" in opts:
+        ref = ref + c0.double()
+    err = (c.double() - ref).abs().max().item()
+    assert err <= 3e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("Mo,main,aux_w,P", [(256, True, 0, 5000), (256, True, 63, 777), (256, False, 63, 130), (128, True, 0, 64)])
+def test_wgrad_building_block(Mo, main, aux_w, P):
+    """tcgen05 weight-gradient kernel (contraction over points, both operands transposed on the fly) vs fp64."""
+    _lib, _ = _imports()
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(Mo + aux_w + P)
+    dy = (torch.randn(P, Mo, generator=g) * torch.logspace(-5, 0, Mo)[None]).to(DEV)
+    x = torch.relu(torch.randn(P, 256, generator=g)).to(DEV) if main else None
+    e = torch.randn(P, 64, generator=g).to(DEV) if aux_w else None
+    ldw = (aux_w if aux_w else 0) + (256 if main else 0) + 5
+    dw = torch.randn(Mo, ldw, generator=g).to(DEV)
+    dw0 = dw.clone()
+    aux_col, main_col = 2, 2 + aux_w
+    _lib.check(L.nsos_selftest_wgrad(_lib.ptr(dy), Mo, Mo, _lib.ptr(x), 256, main_col, _lib.ptr(e), 64, aux_w, aux_col, _lib.ptr(dw), ldw, P, None),
+               "wgrad")
+    torch.cuda.synchronize()
+    ref = dw0.double()
+    if main:
+        ref[:, main_col:main_col + 256] += dy.double().t() @ x.double()
+    if aux_w:
+        ref[:, aux_col:aux_col + aux_w] += dy.double().t() @ e.double()[:, :aux_w]
+    err = (dw.double() - ref).abs().max().item()
+    assert err <= 3e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
