@@ -105,7 +105,7 @@ def lib() -> C.CDLL:
         "nsos_app_corr_loss_sharded": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, P(LossShard), vp, sz, vp]),
         "nsos_adam_multi": (C.c_int, [P(AdamTensor), i32, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]),
         "nsos_selftest_rowgemm": (C.c_int, [vp, i64, i32, vp, i64, i64, vp, i64, i32, vp, i64, vp, C.c_int, C.c_int, i64, vp, sz, vp]),
-        "nsos_selftest_wgrad": (C.c_int, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, vp, i64, i64, vp]),
+        "nsos_selftest_wgrad": (C.c_int, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, vp, i64, vp, i64, vp]),
         "nsos_selftest_umma": (C.c_int, [vp, vp, vp, i32, i32, C.c_int, C.c_int, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():

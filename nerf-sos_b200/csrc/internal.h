@@ -47,7 +47,7 @@ int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* 
                  const float* g_raw, int64_t P, cudaStream_t st);
 bool tc_wgrad_gen_supported(int Mo, int64_t ldy, int main_w, int64_t ld_main, int aux_w);
 int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_t ld_main, int main_col, const float* aux, int64_t ld_aux,
-                 int aux_w, int aux_col, float* dW, int64_t ldw, int64_t P, cudaStream_t st);
+                 int aux_w, int aux_col, float* dW, int64_t ldw, float* db, int64_t P, cudaStream_t st);
 int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,
                 cudaStream_t st);
 

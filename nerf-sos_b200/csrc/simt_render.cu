@@ -156,6 +156,51 @@ __global__ void k_relu_mask(float* __restrict__ G, const float* __restrict__ H, 
 
 inline dim3 grid1(int64_t n, int bs = 256) { return dim3((unsigned)((n + bs - 1) / bs)); }
 
+// ---- narrow products of the head backward (the 1-, 3- and sem_dim-wide outputs): memory-bound fp32 kernels -----------------
+// dX[p, k] (=|+=) [mask(p,k) > 0] * sum_{n<N} dY[p*ldy + n] * W[n*ldw + k],  N <= 4, K % 4 == 0
+__global__ void k_small_dgrad(const float* __restrict__ dY, int64_t ldy, int N, const float* __restrict__ W, int ldw, int K,
+                              float* __restrict__ dX, int64_t ldx, const float* __restrict__ mask, int accumulate, int64_t P) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k4n = K / 4;
+  if (idx >= P * k4n) return;
+  const int64_t p = idx / k4n;
+  const int k = (int)(idx % k4n) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n = 0; n < N; ++n) {
+    const float g = __ldg(&dY[p * ldy + n]);
+    const float* w = W + (int64_t)n * ldw + k;
+    acc.x = fmaf(g, __ldg(w), acc.x); acc.y = fmaf(g, __ldg(w + 1), acc.y); acc.z = fmaf(g, __ldg(w + 2), acc.z); acc.w = fmaf(g, __ldg(w + 3), acc.w);
+  }
+  float4* dst = reinterpret_cast<float4*>(dX + p * ldx + k);
+  if (mask) {
+    const float4 m = *reinterpret_cast<const float4*>(mask + p * ldx + k);
+    if (!(m.x > 0.f)) acc.x = 0.f;
+    if (!(m.y > 0.f)) acc.y = 0.f;
+    if (!(m.z > 0.f)) acc.z = 0.f;
+    if (!(m.w > 0.f)) acc.w = 0.f;
+  }
+  if (accumulate) { const float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+  *dst = acc;
+}
+// dW[n*ldw + k] += sum_p dY[p*ldy + n] * X[p*ldx + k]  (N <= 4, K <= blockDim.x);  db[n] += sum_p dY[p*ldy + n]
+__global__ void __launch_bounds__(256) k_small_wgrad(const float* __restrict__ dY, int64_t ldy, int N, const float* __restrict__ X, int64_t ldx,
+                                                     int K, float* __restrict__ dW, int ldw, float* __restrict__ db, int64_t P) {
+  const int k = threadIdx.x;
+  const int64_t per = (P + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = (int64_t)blockIdx.x * per, p1 = min(P, p0 + per);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
+  for (int64_t p = p0; p < p1; ++p) {
+    const float x = (k < K) ? X[p * ldx + k] : 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      if (n < N) acc[n] = fmaf(__ldg(&dY[p * ldy + n]), x, acc[n]);
+    if (db && k < N) bsum += __ldg(&dY[p * ldy + k]);
+  }
+  if (k < K)
+    for (int n = 0; n < N; ++n) atomicAdd(&dW[(int64_t)n * ldw + k], acc[n]);
+  if (db && k < N) atomicAdd(&db[k], bsum);
+}
+
 // ---- tensor-core dispatch for the large GEMMs of the all-parameter backward ------------------------
 // NSOS_MODE_TC_*: products with a 64..256-wide contraction and a 32..256-wide output run on tcgen05 (tc_rowgemm / tc_wgrad_gen:
 // bf16 hi/lo operands, 3 MMAs per product, fp32 accumulate); everything narrow (the 1-, 3- and sem_dim-wide heads, the per-ray
@@ -226,8 +271,15 @@ int mlp_forward(const NetGeom& g, const float* prm, const float* enc, const floa
 }
 
 // dW[N,K] += dY[P,N]^T . X[P,K]  (X possibly two sources)   -- split-K over P with atomics
+// db != nullptr: also the bias gradient db[N] += column sums of dY (in the same tensor-core launch when possible)
+int bgrad(const float* dY, int64_t ldy, int N, float* db, int64_t P, cudaStream_t st);
 int wgrad(const float* dY, int64_t ldy, int N, const float* X1, int64_t ldx1, int K1, const float* X2, int64_t ldx2, int K2,
-          int x2_rowdiv, float* dW, int64_t P, cudaStream_t st, const TcCtx* tc = nullptr) {
+          int x2_rowdiv, float* dW, int64_t P, cudaStream_t st, const TcCtx* tc = nullptr, float* db = nullptr) {
+  if (N <= 4 && X1 && !X2 && K1 <= 256) {          // narrow head: one memory-bound pass over X
+    k_small_wgrad<<<(unsigned)std::min<int64_t>(1184, (P + 255) / 256), 256, 0, st>>>(dY, ldy, N, X1, ldx1, K1, dW, K1, db, P);
+    NSOS_CHECK_CUDA(cudaGetLastError());
+    return NSOS_OK;
+  }
   // tensor cores: the 256-wide source is `main`, a <= 64-wide source of per-point rows is `aux` (gamma(x)); one launch for both
   bool done[2] = {false, false};
   if (tc && tc->on && (N == 128 || N == 256) && ldy % 4 == 0) {
@@ -240,13 +292,16 @@ int wgrad(const float* dY, int64_t ldy, int N, const float* X1, int64_t ldx1, in
       else if (K[part] <= 64 && ia < 0) ia = part;
     }
     if (im >= 0 || ia >= 0) {
+      float* db_tc = (ia < 0 || K[ia] <= 63) ? db : nullptr;
       int rc = tc_wgrad_gen(dY, ldy, N, im >= 0 ? X[im] : nullptr, im >= 0 ? ld[im] : 0, im >= 0 ? col[im] : 0, ia >= 0 ? X[ia] : nullptr,
-                            ia >= 0 ? ld[ia] : 0, ia >= 0 ? K[ia] : 0, ia >= 0 ? col[ia] : 0, dW, K1 + K2, P, st);
+                            ia >= 0 ? ld[ia] : 0, ia >= 0 ? K[ia] : 0, ia >= 0 ? col[ia] : 0, dW, K1 + K2, db_tc, P, st);
       if (rc) return rc;
       if (im >= 0) done[im] = true;
       if (ia >= 0) done[ia] = true;
+      if (db_tc) db = nullptr;
     }
   }
+  if (db) { int rc = bgrad(dY, ldy, N, db, P, st); if (rc) return rc; }
   // as a GEMM: M=N (rows of dW), N=K (cols), K=P.  A(m,k)=dY[k*ldy+m]; B(k,n)=X[k*ldx+n]
   for (int part = 0; part < 2; ++part) {
     const float* X = part ? X2 : X1; int64_t ldx = part ? ldx2 : ldx1; int Kp = part ? K2 : K1;
@@ -269,6 +324,11 @@ int bgrad(const float* dY, int64_t ldy, int N, float* db, int64_t P, cudaStream_
 // dX[P,K] (=|+=) dY[P,N] . W[N, k0:k0+K]   with optional relu mask from H
 int dgrad(const float* dY, int64_t ldy, int N, const float* Wt, int ldw, int k0, int K, float* dX, int64_t ldx, const float* mask,
           int accumulate, int64_t P, cudaStream_t st, const TcCtx* tc = nullptr) {
+  if (N <= 4 && K % 4 == 0 && ldx % 4 == 0) {        // narrow head: elementwise outer product
+    k_small_dgrad<<<grid1(P * (K / 4)), 256, 0, st>>>(dY, ldy, N, Wt + k0, ldw, K, dX, ldx, mask, accumulate, P);
+    NSOS_CHECK_CUDA(cudaGetLastError());
+    return NSOS_OK;
+  }
   GemmArgs g{};
   g.A1 = dY; g.a1_rs = ldy; g.a1_cs = 1; g.K1 = N; g.a1_rowdiv = 1; g.a2_rowdiv = 1;
   g.B = Wt + k0; g.b_rs = ldw; g.b_cs = 1; g.b_rowdiv = 1;   // B(k=n_out, n=k_in) = W[n_out*ldw + k0 + k_in]
@@ -293,19 +353,19 @@ int mlp_backward(const NetGeom& g, const float* prm, float* grads, const float* 
   int rc;
   if (!g.use_viewdirs) {
     if (!trunk) return NSOS_OK;
-    if ((rc = wgrad(w.g_raw, C, 4, hl, W, W, nullptr, 0, 0, 1, grads + g.w_out, P, st, &w.tc))) return rc;
-    if ((rc = bgrad(w.g_raw, C, 4, grads + g.b_out, P, st))) return rc;
+    if ((rc = wgrad(w.g_raw, C, 4, hl, W, W, nullptr, 0, 0, 1, grads + g.w_out, P, st, &w.tc, grads + g.b_out))) return rc;
+    
     if ((rc = dgrad(w.g_raw, C, 4, prm + g.w_out, W, 0, W, w.G[0], W, hl, 0, P, st, &w.tc))) return rc;
   } else {
     bool have_G = false;
     if (g.use_sem) {
       // sem = W_s2 . s0 + b ; s0 = relu(W_s0 . [h, enc] + b)
-      if ((rc = wgrad(w.g_raw + 4, C, g.sem_dim, b.s0, H, H, nullptr, 0, 0, 1, grads + g.w_s2, P, st, &w.tc))) return rc;
-      if ((rc = bgrad(w.g_raw + 4, C, g.sem_dim, grads + g.b_s2, P, st))) return rc;
+      if ((rc = wgrad(w.g_raw + 4, C, g.sem_dim, b.s0, H, H, nullptr, 0, 0, 1, grads + g.w_s2, P, st, &w.tc, grads + g.b_s2))) return rc;
+      
       if ((rc = dgrad(w.g_raw + 4, C, g.sem_dim, prm + g.w_s2, H, 0, H, w.g_half, H, b.s0, 0, P, st, &w.tc))) return rc;
       if ((rc = wgrad(w.g_half, H, H, hl, W, W, g.sem_coord ? enc : nullptr, kEncLd, g.sem_coord ? g.enc : 0, 1,
-                      grads + g.w_s0, P, st, &w.tc))) return rc;
-      if ((rc = bgrad(w.g_half, H, H, grads + g.b_s0, P, st))) return rc;
+                      grads + g.w_s0, P, st, &w.tc, grads + g.b_s0))) return rc;
+      
       if (trunk) {
         if ((rc = dgrad(w.g_half, H, H, prm + g.w_s0, g.sem_in, 0, W, w.G[0], W, nullptr, 0, P, st, &w.tc))) return rc;
         have_G = true;
@@ -313,18 +373,18 @@ int mlp_backward(const NetGeom& g, const float* prm, float* grads, const float* 
     }
     if (!trunk) return NSOS_OK;
     // rgb = W_rgb . hv + b ; hv = relu(W_v . [feat, encv] + b) ; feat = W_f . h + b
-    if ((rc = wgrad(w.g_raw, C, 3, b.hv, H, H, nullptr, 0, 0, 1, grads + g.w_rgb, P, st, &w.tc))) return rc;
-    if ((rc = bgrad(w.g_raw, C, 3, grads + g.b_rgb, P, st))) return rc;
+    if ((rc = wgrad(w.g_raw, C, 3, b.hv, H, H, nullptr, 0, 0, 1, grads + g.w_rgb, P, st, &w.tc, grads + g.b_rgb))) return rc;
+    
     if ((rc = dgrad(w.g_raw, C, 3, prm + g.w_rgb, H, 0, H, w.g_half, H, b.hv, 0, P, st, &w.tc))) return rc;
-    if ((rc = wgrad(w.g_half, H, H, b.feat, W, W, encv, kEncVLd, g.encv, S, grads + g.w_views, P, st, &w.tc))) return rc;
-    if ((rc = bgrad(w.g_half, H, H, grads + g.b_views, P, st))) return rc;
+    if ((rc = wgrad(w.g_half, H, H, b.feat, W, W, encv, kEncVLd, g.encv, S, grads + g.w_views, P, st, &w.tc, grads + g.b_views))) return rc;
+    
     if ((rc = dgrad(w.g_half, H, H, prm + g.w_views, W + g.encv, 0, W, w.g_feat, W, nullptr, 0, P, st, &w.tc))) return rc;
-    if ((rc = wgrad(w.g_feat, W, W, hl, W, W, nullptr, 0, 0, 1, grads + g.w_feat, P, st, &w.tc))) return rc;
-    if ((rc = bgrad(w.g_feat, W, W, grads + g.b_feat, P, st))) return rc;
+    if ((rc = wgrad(w.g_feat, W, W, hl, W, W, nullptr, 0, 0, 1, grads + g.w_feat, P, st, &w.tc, grads + g.b_feat))) return rc;
+    
     if ((rc = dgrad(w.g_feat, W, W, prm + g.w_feat, W, 0, W, w.G[0], W, nullptr, have_G ? 1 : 0, P, st, &w.tc))) return rc;
     // alpha = w_a . h + b
-    if ((rc = wgrad(w.g_raw + 3, C, 1, hl, W, W, nullptr, 0, 0, 1, grads + g.w_alpha, P, st, &w.tc))) return rc;
-    if ((rc = bgrad(w.g_raw + 3, C, 1, grads + g.b_alpha, P, st))) return rc;
+    if ((rc = wgrad(w.g_raw + 3, C, 1, hl, W, W, nullptr, 0, 0, 1, grads + g.w_alpha, P, st, &w.tc, grads + g.b_alpha))) return rc;
+    
     if ((rc = dgrad(w.g_raw + 3, C, 1, prm + g.w_alpha, W, 0, W, w.G[0], W, nullptr, 1, P, st, &w.tc))) return rc;
     k_relu_mask<<<grid1(P * W), 256, 0, st>>>(w.G[0], hl, P * W);
     NSOS_CHECK_CUDA(cudaGetLastError());
@@ -334,10 +394,10 @@ int mlp_backward(const NetGeom& g, const float* prm, float* grads, const float* 
   for (int i = g.D - 1; i >= 0; --i) {
     const float* dpre = w.G[cur];
     const float* hin = (i > 0) ? b.h[i - 1] : nullptr;
-    if (i == 0) { if ((rc = wgrad(dpre, W, W, enc, kEncLd, g.enc, nullptr, 0, 0, 1, grads + g.w_pts[i], P, st, &w.tc))) return rc; }
-    else if (g.in_pts[i] == W) { if ((rc = wgrad(dpre, W, W, hin, W, W, nullptr, 0, 0, 1, grads + g.w_pts[i], P, st, &w.tc))) return rc; }
-    else { if ((rc = wgrad(dpre, W, W, enc, kEncLd, g.enc, hin, W, W, 1, grads + g.w_pts[i], P, st, &w.tc))) return rc; }
-    if ((rc = bgrad(dpre, W, W, grads + g.b_pts[i], P, st))) return rc;
+    if (i == 0) { if ((rc = wgrad(dpre, W, W, enc, kEncLd, g.enc, nullptr, 0, 0, 1, grads + g.w_pts[i], P, st, &w.tc, grads + g.b_pts[i]))) return rc; }
+    else if (g.in_pts[i] == W) { if ((rc = wgrad(dpre, W, W, hin, W, W, nullptr, 0, 0, 1, grads + g.w_pts[i], P, st, &w.tc, grads + g.b_pts[i]))) return rc; }
+    else { if ((rc = wgrad(dpre, W, W, enc, kEncLd, g.enc, hin, W, W, 1, grads + g.w_pts[i], P, st, &w.tc, grads + g.b_pts[i]))) return rc; }
+    
     if (i > 0) {
       int k0 = (g.in_pts[i] == W) ? 0 : g.enc;   // h part of [enc, h]
       if ((rc = dgrad(dpre, W, W, prm + g.w_pts[i], g.in_pts[i], k0, W, w.G[cur ^ 1], W, hin, 0, P, st, &w.tc))) return rc;

@@ -279,6 +279,7 @@ struct WgGenParams {
   const float* main; long long ld_main; int main_col;      // may be null
   const float* aux; long long ld_aux; int aux_w, aux_col;  // may be null; aux_w <= 64
   float* dW; long long ldw;
+  float* db;                 // optional: db[Mo] += sum_p dY[p, :]  (a constant-one feature in aux row 63; needs aux_w <= 63)
   long long P;
 };
 struct WgGenSmem {
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen(const __grid_consta
   const int m0 = blockIdx.y * 128;
   const long long nslabs = (P.P + kSlabPts - 1) / kSlabPts;
   const long long my_slabs = (nslabs - blockIdx.x + gridDim.x - 1) / gridDim.x;     // >= 1 (grid.x <= nslabs)
-  const bool has_main = P.main != nullptr, has_aux = P.aux != nullptr;
+  const bool has_main = P.main != nullptr, has_aux = P.aux != nullptr || P.db != nullptr;     // the bias column lives in the aux block
   if (t == 0) {
     mbar_init(smem_u32(sm.ready), kWgWorkers);
     mbar_init(smem_u32(sm.done), 1);
@@ -378,7 +379,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen(const __grid_consta
           const int e0 = q * 16 + 8 * g8;
           float ev[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) ev[i] = (valid && e0 + i < P.aux_w) ? __ldg(&P.aux[p * P.ld_aux + e0 + i]) : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            ev[i] = (valid && P.aux && e0 + i < P.aux_w) ? __ldg(&P.aux[p * P.ld_aux + e0 + i]) : 0.f;
+            if (P.db && e0 + i == 63) ev[i] = valid ? 1.f : 0.f;
+          }
           put8(sm.b[0], sm.b[1], 256 + e0, ev, lane, wd);
         }
       }
@@ -406,6 +410,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen(const __grid_consta
         const float x = __uint_as_float(r[j]);
         if (f < 256) atomicAdd(&P.dW[(size_t)u * P.ldw + P.main_col + f], x);
         else if (f - 256 < P.aux_w) atomicAdd(&P.dW[(size_t)u * P.ldw + P.aux_col + (f - 256)], x);
+        else if (f == 319 && P.db) atomicAdd(&P.db[u], x);
       }
     }
   }
@@ -452,13 +457,15 @@ bool tc_wgrad_gen_supported(int Mo, int64_t ldy, int main_w, int64_t ld_main, in
          (main_w > 0 || aux_w > 0);
 }
 int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_t ld_main, int main_col, const float* aux, int64_t ld_aux,
-                 int aux_w, int aux_col, float* dW, int64_t ldw, int64_t P, cudaStream_t st) {
+                 int aux_w, int aux_col, float* dW, int64_t ldw, float* db, int64_t P, cudaStream_t st) {
   NSOS_REQUIRE(tc_wgrad_gen_supported(Mo, ldy, main ? 256 : 0, ld_main, aux ? aux_w : 0), NSOS_ERR_UNSUPPORTED, "tc_wgrad_gen: unsupported shape");
   if (P <= 0) return NSOS_OK;
   WgGenParams p;
   memset(&p, 0, sizeof(p));
   p.dY = dY; p.ldy = ldy; p.Mo = Mo; p.main = main; p.ld_main = ld_main; p.main_col = main_col;
   p.aux = aux; p.ld_aux = ld_aux; p.aux_w = aux ? aux_w : 0; p.aux_col = aux_col; p.dW = dW; p.ldw = ldw; p.P = P;
+  p.db = (p.aux_w <= 63) ? db : nullptr;
+  NSOS_REQUIRE(!db || p.db, NSOS_ERR_UNSUPPORTED, "tc_wgrad_gen: the bias column needs aux_w <= 63");
   int dev = 0, sms = 0;
   NSOS_CHECK_CUDA(cudaGetDevice(&dev));
   NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -599,9 +599,13 @@ def test_wgrad_building_block(Mo, main, aux_w, P):
     dw = torch.randn(Mo, ldw, generator=g).to(DEV)
     dw0 = dw.clone()
     aux_col, main_col = 2, 2 + aux_w
-    _lib.check(L.nsos_selftest_wgrad(_lib.ptr(dy), Mo, Mo, _lib.ptr(x), 256, main_col, _lib.ptr(e), 64, aux_w, aux_col, _lib.ptr(dw), ldw, P, None),
-               "wgrad")
+    db = torch.randn(Mo, generator=g).to(DEV)
+    db0 = db.clone()
+    _lib.check(L.nsos_selftest_wgrad(_lib.ptr(dy), Mo, Mo, _lib.ptr(x), 256, main_col, _lib.ptr(e), 64, aux_w, aux_col, _lib.ptr(dw), ldw,
+                                     _lib.ptr(db), P, None), "wgrad")
     torch.cuda.synchronize()
+    refb = db0.double() + dy.double().sum(0)                               # bias gradient from the constant-one feature
+    assert (db.double() - refb).abs().max().item() <= 3e-5 * refb.abs().max().item()
     ref = dw0.double()
     if main:
         ref[:, main_col:main_col + 256] += dy.double().t() @ x.double()
