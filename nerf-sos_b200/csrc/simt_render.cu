@@ -419,6 +419,12 @@ struct Carver {
 
 int64_t fwd_chunk_rays(int64_t n_rays) { return n_rays < 8192 ? n_rays : 8192; }
 int64_t bwd_chunk_rays(int64_t n_rays) { return n_rays < 2048 ? n_rays : 2048; }
+// tensor-core all-parameter backward: 11 KB of saved activations / gradients per sample point -> 23 GB per 8192 rays x 256 points
+int64_t bwd_all_chunk_rays(int64_t n_rays) {
+  const char* e = getenv("NSOS_BWD_CHUNK");
+  const int64_t c = e ? atoll(e) : 8192;
+  return n_rays < c ? n_rays : (c < 64 ? 64 : c);
+}
 
 struct FwdWs {
   float *z0, *z1, *enc, *encv, *dnorm, *raw, *w0, *hA, *hB, *feat, *hv, *s0;
@@ -613,7 +619,7 @@ size_t simt_render_bwd_workspace_bytes(const NsosRenderCfg& cfg, int64_t n_rays,
   if (!make_geom(cfg.coarse, gc)) return 0;
   if (cfg.n_importance > 0) { if (!make_geom(cfg.fine, gf)) return 0; } else gf = gc;
   if (trunk && (cfg.mode == NSOS_MODE_TC_EXACT || cfg.mode == NSOS_MODE_TC_FAST))        // either all-parameter path may run
-    return std::max(carve_bwd_all(cfg, gc, gf, bwd_chunk_rays(n_rays), nullptr, nullptr),
+    return std::max(carve_bwd_all(cfg, gc, gf, bwd_all_chunk_rays(n_rays), nullptr, nullptr),
                     carve_bwd(cfg, gc, gf, bwd_chunk_rays(n_rays), nullptr, nullptr));
   if (bwd_uses_tc(cfg, trunk, gc, gf)) return carve_bwd_tc(cfg, gc, gf, bwd_tc_chunk_rays(n_rays), nullptr, nullptr);
   return carve_bwd(cfg, gc, gf, bwd_chunk_rays(n_rays), nullptr, nullptr);
@@ -693,7 +699,7 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
     return NSOS_OK;
   }
   if (bwd_all_uses_tc(cfg, trunk, gc, gf, packed_c, packed_f)) {
-    const int64_t R = bwd_chunk_rays(n_rays);
+    const int64_t R = bwd_all_chunk_rays(n_rays);
     BwdAllWs w;
     size_t need = carve_bwd_all(cfg, gc, gf, R, (char*)workspace, &w);
     NSOS_REQUIRE(workspace_bytes >= need, NSOS_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
