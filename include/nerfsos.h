@@ -143,8 +143,8 @@ int nsos_render_fwd(const NsosRenderCfg* cfg, const float* params_coarse, const 
                     int64_t n_rays, void* stream);
 
 /* Backward of nsos_render_fwd (replaces autograd through the modules above, trainer.py:201).
- * g_maps [N, 2*C6+1] holds d(loss)/d(maps) (disp and z_std columns are ignored: no shipped loss
- * differentiates them).  z_vals0/z_vals are the sample positions saved by the forward call (the
+ * g_maps [N, 2*C6+1] holds d(loss)/d(maps) (rgb, disp, acc, depth, semantics of both passes; the z_std column is
+ * ignored: the importance samples are detached).  z_vals0/z_vals are the sample positions saved by the forward call (the
  * importance samples are detached, sampler.py:159, so the two passes are independent); the randoms /
  * seed must equal the forward call's.  Gradients are ACCUMULATED into grads_* (flat layout of
  * nsos_param_layout); trunk_grads=0 computes only semantic_linear.{0,2} (--fix_backbone,

@@ -105,7 +105,7 @@ __device__ inline void warp_composite(const RayPass& p, int lane, float* maps_ou
 }
 
 // Backward of warp_composite.  g_maps: upstream grads in the maps layout
-// (disp ignored).  g_raw_out: [S, C] (overwritten).
+// (rgb, disp, acc, depth, semantics).  g_raw_out: [S, C] (overwritten).
 __device__ inline void warp_composite_bwd(const RayPass& p, int lane, const float* g_maps, float* g_raw_out) {
   const int n = (p.S + 31) >> 5;
   const int i0 = lane * n;
@@ -135,16 +135,24 @@ __device__ inline void warp_composite_bwd(const RayPass& p, int lane, const floa
   float T0 = __shfl_up_sync(0xffffffffu, incl, 1);
   if (lane == 0) T0 = 1.f;
   // acc decides whether depth carries gradient (masked overwrite, renderer.py:72)
-  float T = T0, accl = 0.f;
+  float T = T0, accl = 0.f, depl = 0.f;
 #pragma unroll
   for (int j = 0; j < kMaxChunk; ++j) {
     int i = i0 + j;
-    if (j < n && i < p.S) { accl += a[j] * T; T *= (1.f - a[j] + 1e-10f); }
+    if (j < n && i < p.S) { accl += a[j] * T; depl = fmaf(a[j] * T, p.z[i], depl); T *= (1.f - a[j] + 1e-10f); }
   }
   float acc = warp_sum(accl);
+  const float dep = warp_sum(depl);
   float gr0 = g_maps[0], gr1 = g_maps[1], gr2 = g_maps[2];
   float g_acc = g_maps[4];
   float g_dep = (acc <= 1e-10f) ? 0.f : g_maps[5];
+  // disp = 1 / max(1e-10, depth / acc) (renderer.py:74): gradient where neither the depth overwrite nor the max clamps
+  const float g_disp = g_maps[3];
+  if (g_disp != 0.f && acc > 1e-10f && dep / acc > 1e-10f) {
+    const float disp = acc / dep;
+    g_dep = fmaf(-g_disp, disp * disp / acc, g_dep);                 // d disp / d depth = -acc / depth^2
+    g_acc = fmaf(g_disp, disp * disp * dep / (acc * acc), g_acc);    // d disp / d acc   =  1 / depth
+  }
   float gs[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) gs[c] = (c < p.sem_dim) ? g_maps[6 + c] : 0.f;

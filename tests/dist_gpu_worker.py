@@ -50,14 +50,14 @@ class Loader:
     dataset = DS()
 
 
-def make_net(dev):
+def make_net(dev, all_params=False):
     sd = load_golden("flower_weights")["sd"]
     net = NeRFNet(N_samples=64, N_importance=128, use_semantics=True, sem_with_coord=True, sem_dim=2, perturb=1.0,
                   raw_noise_std=1.0, mode="exact")
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     net = net.to(dev)
     for n, p in net.named_parameters():
-        p.requires_grad_("semantic_linear" in n)                      # --fix_backbone
+        p.requires_grad_(all_params or "semantic_linear" in n)        # --fix_backbone unless all_params (stage-1 training)
     return net
 
 
@@ -85,8 +85,8 @@ def main():
     rays_p = rays[:, :N].permute(1, 0, 2).reshape(B, Ps * Ps, 2, 3)    # [B, P*P, 2, 3] as PatchBatchCollater yields
     gt = torch.rand(B, Ps * Ps, 3, generator=gen).to(dev)
 
-    def run(lo, hi, group):
-        net = make_net(dev)
+    def run(lo, hi, group, all_params=False):
+        net = make_net(dev, all_params)
         from nerfsos_b200.engines.optim import FusedAdam
         opt = FusedAdam([p for p in net.parameters() if p.requires_grad], lr=5e-4)
         losses = [None, None, CorrelationLoss(a), GeoCorrelationLoss(a)]
@@ -110,6 +110,15 @@ def main():
     rel_g = (g_dp - g_1).abs().max().item() / g_1.abs().max().item()
     print(f"rank {rank}: loss dp={l_dp:.8f} single={l_1:.8f} rel={rel_l:.2e}; grad rel err {rel_g:.2e}", flush=True)
     assert rel_l <= 1e-6 and rel_g <= 1e-5, (rel_l, rel_g)
+    # ---- 3. the same with EVERY parameter trainable: the 5.1 MB gradient all-reduce of north_star, tensor-core backward
+    l_dp, g_dp = run(lo, hi, None, all_params=True)
+    P.world = lambda group=None: (0, 1)
+    l_1, g_1 = run(0, B, None, all_params=True)
+    P.world = orig
+    rel_l = abs(l_dp - l_1) / max(1e-12, abs(l_1))
+    rel_g = (g_dp - g_1).abs().max().item() / g_1.abs().max().item()
+    print(f"rank {rank}: all parameters ({g_1.numel()} gradients): loss rel={rel_l:.2e}; grad rel err {rel_g:.2e}", flush=True)
+    assert g_1.numel() == 1274124 and rel_l <= 1e-6 and rel_g <= 1e-4, (rel_l, rel_g)
     dist.barrier()
     if rank == 0:
         print("DIST_OK", flush=True)

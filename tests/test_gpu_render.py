@@ -613,3 +613,33 @@ def test_wgrad_building_block(Mo, main, aux_w, P):
         ref[:, aux_col:aux_col + aux_w] += dy.double().t() @ e.double()[:, :aux_w]
     err = (dw.double() - ref).abs().max().item()
     assert err <= 3e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+def test_disp_depth_acc_gradients_vs_torch_autograd():
+    """Losses on the disparity / depth / acc maps train in the reference (renderer.py:69-74 are differentiable); the compositing
+    backward carries all three.  Coarse pass, all parameters, fp32 path vs torch autograd through the op-for-op port."""
+    from oracle import torch_port as TP
+    g = load_golden("flower_eval_256")
+    rays = torch.from_numpy(g["rays"][:, :32])
+    net = flower_net("simt").eval()
+    for p in net.parameters():
+        p.requires_grad_(True)
+    gen = torch.Generator().manual_seed(9)
+    c = {k: torch.randn(32, 1, generator=gen) for k in ("disp", "depth", "acc")}
+    out = net(rays.to(DEV), (1.2, 12.0), N_importance=0)
+    loss = sum((out[k] * c[k].to(DEV)).sum() for k in c)
+    loss.backward()
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in load_golden("flower_weights")["sd"].items()}
+    o, d = rays[0], rays[1]
+    t = torch.linspace(0., 1., 64)
+    z = (1.2 * (1. - t) + 12.0 * t).expand(32, 64)
+    raw = TP._query(sd, "nerf.mlp", o[:, None] + d[:, None] * z[..., None], d / torch.norm(d, dim=-1, keepdim=True), 8, True, True, 1 << 20)
+    ref = TP._composite(raw, z, d, True)
+    lref = sum((ref[k] * c[k]).sum() for k in c)
+    assert abs(loss.item() - lref.item()) <= 1e-4 * max(1.0, abs(lref.item()))
+    lref.backward()
+    for n, p in net.named_parameters():
+        if n.startswith("nerf.") and "semantic" not in n:
+            r = sd[n].grad.numpy()
+            err = np.abs(p.grad.cpu().numpy() - r).max()
+            assert err <= 1e-3 * max(np.abs(r).max(), 1e-8), (n, err, np.abs(r).max())
