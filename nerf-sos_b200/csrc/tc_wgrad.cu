@@ -30,7 +30,8 @@ namespace nsos {
 namespace {
 using namespace ptx;
 
-constexpr int kWgWorkers = 256, kWgThreads = 288, kWgMmaWarp = 8;
+constexpr int kWgWorkers = 256, kWgThreads = 288, kWgMmaWarp = 8;   // k_wgrad_gen: 8 fill warps + an issuer warp
+constexpr int kSemThreads = 256;   // k_sem_wgrad: 8 warps (255 registers each: 28 loads in flight per thread); warp 0 also issues the MMAs
 constexpr int kSlabPts = 64;
 constexpr int kRowsA = 128, kRowsB = 320, kRowsB2 = 16;
 constexpr int kColD1 = 0, kColD1b = 256, kColD2 = 320;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, bool valid,
   }
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) k_sem_wgrad(const __grid_constant__ WgParams P) {
+__global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_constant__ WgParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   WgSmem sm;
@@ -118,43 +119,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_sem_wgrad(const __grid_consta
     mbar_init(smem_u32(sm.done), 1);
     fence_mbar_init();
   }
-  if (warp == kWgMmaWarp) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
   // B2 rows >= 8 are never written by the fill: zero the whole small tile once;  W2 -> smem
-  for (int i = t; i < kRowsB2 * 128 / 4; i += kWgThreads) {
+  for (int i = t; i < kRowsB2 * 128 / 4; i += kSemThreads) {
     reinterpret_cast<uint32_t*>(sm.b2[0])[i] = 0u;
     reinterpret_cast<uint32_t*>(sm.b2[1])[i] = 0u;
   }
-  for (int i = t; i < 4 * 128; i += kWgThreads) sm.w2[i] = (i / 128 < P.sem_dim) ? __ldg(&P.w_s2[i]) : 0.f;
+  for (int i = t; i < 4 * 128; i += kSemThreads) sm.w2[i] = (i / 128 < P.sem_dim) ? __ldg(&P.w_s2[i]) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *sm.tmem_ptr;
 
-  if (warp == kWgMmaWarp) {
-    const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, a2[2] = {smem_u32(sm.a2[0]), smem_u32(sm.a2[1])};
-    const uint32_t b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])}, b2[2] = {smem_u32(sm.b2[0]), smem_u32(sm.b2[1])};
-    const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64), id16 = make_idesc_bf16(16);
-    for (long long it = 0; it < my_slabs; ++it) {
-      mbar_wait(smem_u32(sm.ready), (uint32_t)(it & 1), 700);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;     // hi.hi, lo.hi, hi.lo
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t acc = (it > 0 || pass > 0 || ks > 0) ? 1u : 0u;
-            const uint64_t da = make_sw128_desc(a[pa] + ks * 32), db = make_sw128_desc(b[pb] + ks * 32);
-            umma_ss(tm + kColD1, da, db, id256, acc);
-            umma_ss(tm + kColD1b, da, make_sw128_desc(b[pb] + 256 * 128 + ks * 32), id64, acc);
-            umma_ss(tm + kColD2, make_sw128_desc(a2[pa] + ks * 32), make_sw128_desc(b2[pb] + ks * 32), id16, acc);
-          }
-        }
-        umma_commit(smem_u32(sm.done));
-      }
-      __syncwarp();
-    }
-  } else {
+  const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, a2[2] = {smem_u32(sm.a2[0]), smem_u32(sm.a2[1])};
+  const uint32_t b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])}, b2[2] = {smem_u32(sm.b2[0]), smem_u32(sm.b2[1])};
+  const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64), id16 = make_idesc_bf16(16);
+  {
     const int pgp = warp & 1, q = warp >> 1;            // point group (32 points), feature quarter
     const int pl = 32 * pgp + lane, wd = pl >> 1;
     float gb2_acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -166,29 +146,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_sem_wgrad(const __grid_consta
       float gs[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid)
         for (int c = 0; c < 4; ++c) if (c < P.sem_dim) gs[c] = __ldg(&P.g_raw[p * P.C + 4 + c]);
-      // This thread's share of the slab is 64 h values, 16 gamma values and 32 s0 values of one point.  All of h is
-      // requested through a rolling window of 8 independent 16-byte loads per thread (32 KB in flight per SM, plus gamma / s0): the kernel streams 15 GB per
-      // training step and one or two loads in flight per thread left it at 23 % of the HBM roofline
-      // (profiles/r01_ncu_full_k_sem_wgrad_summary.txt).  The loads also overlap the tensor pipe working on the previous slab.
-      float hv[4][8];                                   // rolling window: 4 groups of 8 values (8 x 16 B in flight per thread)
+      // This thread's share of the slab is 64 h values, 16 gamma values and 32 s0 values of one point.
+      // All of this thread's share of the slab is requested up front: 28 independent 16-byte loads per thread (112 KB in flight
+      // per SM) before anything is converted.  Round 1 kept a rolling window of 8 (32 KB per SM), which left the kernel at 23-32 %
+      // of the HBM roofline: latency-bound at 9 warps per SM.  The loads also overlap the tensor pipe working on the previous slab.
+      float hv[8][8], ev[2][8], sv[4][8];
       const float* hrow = P.h + p * 256 + q * 64;
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) load8(hrow + 8 * g8, valid, hv[g8]);
+      for (int g8 = 0; g8 < 8; ++g8) load8(hrow + 8 * g8, valid, hv[g8]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) load8(P.enc + p * P.enc_ld + q * 16 + 8 * k, valid && P.sem_coord, ev[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) load8(P.s0 + p * 128 + q * 32 + 8 * k, valid, sv[k]);
       if (it > 0) { mbar_wait(smem_u32(sm.done), (uint32_t)((it - 1) & 1), 710); tc_fence_after(); }
-      float ev[2][8], sv[4][8];
-      // ---- B rows 0..255: h (gamma and s0 are requested while h is being converted)
+      // ---- B rows 0..255: h
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) {
-        put8(sm.b[0], sm.b[1], q * 64 + 8 * g8, hv[g8 & 3], lane, wd);
-        if (g8 + 4 < 8) load8(hrow + 8 * (g8 + 4), valid, hv[g8 & 3]);
-        // the window drains from g8 = 4 on: its registers take the gamma and s0 requests
-        if (g8 == 4) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k) load8(P.enc + p * P.enc_ld + q * 16 + 8 * k, valid && P.sem_coord, ev[k]);
-        }
-        if (g8 == 5) { load8(P.s0 + p * 128 + q * 32, valid, sv[0]); load8(P.s0 + p * 128 + q * 32 + 8, valid, sv[1]); }
-        if (g8 == 6) { load8(P.s0 + p * 128 + q * 32 + 16, valid, sv[2]); load8(P.s0 + p * 128 + q * 32 + 24, valid, sv[3]); }
-      }
+      for (int g8 = 0; g8 < 8; ++g8) put8(sm.b[0], sm.b[1], q * 64 + 8 * g8, hv[g8], lane, wd);
       // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0)
 #pragma unroll
       for (int g8 = 0; g8 < 2; ++g8) {
@@ -225,6 +198,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_sem_wgrad(const __grid_consta
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(sm.ready));
+      if (warp == 0) {                                   // the slab's tiles are complete once all 256 threads have arrived
+        mbar_wait(smem_u32(sm.ready), (uint32_t)(it & 1), 700);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;     // hi.hi, lo.hi, hi.lo
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = (it > 0 || pass > 0 || ks > 0) ? 1u : 0u;
+              const uint64_t da = make_sw128_desc(a[pa] + ks * 32), db = make_sw128_desc(b[pb] + ks * 32);
+              umma_ss(tm + kColD1, da, db, id256, acc);
+              umma_ss(tm + kColD1b, da, make_sw128_desc(b[pb] + 256 * 128 + ks * 32), id64, acc);
+              umma_ss(tm + kColD2, make_sw128_desc(a2[pa] + ks * 32), make_sw128_desc(b2[pb] + ks * 32), id16, acc);
+            }
+          }
+          umma_commit(smem_u32(sm.done));
+        }
+        __syncwarp();
+      }
     }
     // ---- epilogue: TMEM partial sums -> global gradients (atomics; every CTA contributes)
     mbar_wait(smem_u32(sm.done), (uint32_t)((my_slabs - 1) & 1), 720);
@@ -265,7 +258,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_sem_wgrad(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kWgMmaWarp) tmem_dealloc(tm, kWgTmemCols);
+  if (warp == 0) tmem_dealloc(tm, kWgTmemCols);
 }
 
 
@@ -443,7 +436,7 @@ int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* 
   const int grid = (int)std::min<long long>(nslabs, sms);
   const size_t need = wg_carve(nullptr, nullptr) + 1024;
   NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_sem_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-  k_sem_wgrad<<<grid, kWgThreads, need, st>>>(p);
+  k_sem_wgrad<<<grid, kSemThreads, need, st>>>(p);
   NSOS_CHECK_CUDA(cudaGetLastError());
   return NSOS_OK;
 }
