@@ -104,6 +104,8 @@ typedef struct NsosRenderOut {
   float* s_hid0;     /* [N, Sc, W/2]                 */
   float* h_last;     /* [N, Sc+K, W]                 */
   float* s_hid;      /* [N, Sc+K, W/2]               */
+  float* enc0;       /* [N, Sc, 64]   gamma(x) of the coarse points (63 columns + one zero), only needed with sem_with_coord:   */
+  float* enc;        /* [N, Sc+K, 64] saves the backward pass a separate positional-encoding kernel                             */
   /* Optional sticky status word (caller zero-initialises, reads and clears it; never reset by the library).
    * bit 0: NSOS_MODE_TC_EXACT/FAST only -- a hidden activation exceeded the fp16 range of the activation planes
    *        (|a| > 4094): the rgb / semantics maps of the affected rays are NaN.  Render such nets with NSOS_MODE_SIMT_FP32. */

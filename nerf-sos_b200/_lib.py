@@ -36,7 +36,7 @@ class Randoms(C.Structure):
 
 class RenderOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
-                                          "z_samples", "inds", "h_last0", "s_hid0", "h_last", "s_hid", "status")]
+                                          "z_samples", "inds", "h_last0", "s_hid0", "h_last", "s_hid", "enc0", "enc", "status")]
 
 
 class AdamTensor(C.Structure):

@@ -641,10 +641,11 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
   if (bwd_uses_tc(cfg, trunk, gc, gf)) {
     // activations saved by the forward call make the trunk replay unnecessary
     const float* sv_raw[2] = {nullptr, nullptr}; const float* sv_h[2] = {nullptr, nullptr}; const float* sv_s[2] = {nullptr, nullptr};
+    const float* sv_e[2] = {nullptr, nullptr};
     if (saved) {
-      if (fine) { sv_raw[0] = saved->raw0; sv_h[0] = saved->h_last0; sv_s[0] = saved->s_hid0;
-                  sv_raw[1] = saved->raw; sv_h[1] = saved->h_last; sv_s[1] = saved->s_hid; }
-      else { sv_raw[0] = saved->raw; sv_h[0] = saved->h_last; sv_s[0] = saved->s_hid; }
+      if (fine) { sv_raw[0] = saved->raw0; sv_h[0] = saved->h_last0; sv_s[0] = saved->s_hid0; sv_e[0] = saved->enc0;
+                  sv_raw[1] = saved->raw; sv_h[1] = saved->h_last; sv_s[1] = saved->s_hid; sv_e[1] = saved->enc; }
+      else { sv_raw[0] = saved->raw; sv_h[0] = saved->h_last; sv_s[0] = saved->s_hid; sv_e[0] = saved->enc; }
     }
     const bool have_saved = sv_raw[0] && sv_h[0] && sv_s[0] && (!fine || (sv_raw[1] && sv_h[1] && sv_s[1]));
     if (!have_saved)
@@ -680,18 +681,20 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
         const float* noise = is_fine ? rn.noise1 : rn.noise0;
         const int moff = (fine && !is_fine) ? C6 : 0;
         const int64_t P = n * S;
-        k_encode_pts<<<grid1(P), 256, 0, st>>>(ro, rd, z, w.enc, P, S, g.Lp);
+        // gamma(x): saved by the training forward (same 64-float row pitch), else recomputed here
+        const float* enc_p = (have_saved && sv_e[pass]) ? sv_e[pass] + r0 * S * kEncLd : w.enc;
+        if (enc_p == w.enc && g.sem_coord) k_encode_pts<<<grid1(P), 256, 0, st>>>(ro, rd, z, w.enc, P, S, g.Lp);
         k_composite_bwd<<<grid1(n * 32, 128), 128, 0, st>>>(raw_p[pass], z, w.dnorm, noise ? noise + r0 * S : nullptr, cfg.raw_noise_std,
                                                              seed, r0, is_fine ? RNG_NOISE1 : RNG_NOISE0, S, g.C, g.sem_dim,
                                                              cfg.white_bkgd, g_maps + r0 * ML, ML, moff, w.g_raw, n);
         NSOS_CHECK_CUDA(cudaGetLastError());
         if (tc_sem_wgrad_supported(g) && !getenv("NSOS_WGRAD_SIMT")) {
-          rc = tc_sem_wgrad(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, h_p[pass], w.enc, kEncLd, s_p[pass], w.g_raw, P, st);
+          rc = tc_sem_wgrad(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, h_p[pass], enc_p, kEncLd, s_p[pass], w.g_raw, P, st);
         } else {
           MlpBufs b{};
           b.h[g.D - 1] = const_cast<float*>(h_p[pass]); b.s0 = const_cast<float*>(s_p[pass]);
           BwdBufs bw{w.g_raw, {nullptr, nullptr}, w.g_half, nullptr, TcCtx{}};
-          rc = mlp_backward(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, w.enc, w.encv, S, P, b, bw, 0, st);
+          rc = mlp_backward(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, enc_p, w.encv, S, P, b, bw, 0, st);
         }
         if (rc) return rc;
       }

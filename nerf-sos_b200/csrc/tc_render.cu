@@ -303,6 +303,7 @@ struct TcParams {
   // MODE 3 (replay for the all-parameter backward): every hidden layer and the views hidden layer as well
   float* dump_all[2][kMaxStages];   // [layer][n_rays*S, W]  relu(pts_linears[layer]); entries may be null
   float* dump_hv[2];                // [n_rays*S, W/2] relu(views_linears.0)
+  float* dump_enc[2];               // [n_rays*S, 64]  gamma(x) (training forward: the semantic-head weight gradients read it)
 };
 constexpr int kTraceTiles = 16, kTraceStamps = 12;  // [tile][stage][stamp]; 5..8: a_ready[j] seen by the MMA lane, 9..11: worker 0 hands over slab 0..2
 
@@ -900,6 +901,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             float e[32];
             if (hf == 0) encode_half<0>(x, pg.Lp, pg.enc, rowvalid, e); else encode_half<1>(x, pg.Lp, pg.enc, rowvalid, e);
             store_halfrow_sw128(sm.g_hi, sm.g_lo, row, hf, e, EXACT);
+            if (DUMP && P.dump_enc[pass] && rowvalid && rp[9] > 0.f) {       // e = 16 * gamma(x): exact power-of-two rescale
+              float4* ge = reinterpret_cast<float4*>(P.dump_enc[pass] + ((size_t)ray * S + i) * 64 + 32 * hf);
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4)
+                ge[c4] = make_float4(e[4 * c4] * (1.f / kActScale), e[4 * c4 + 1] * (1.f / kActScale), e[4 * c4 + 2] * (1.f / kActScale),
+                                     e[4 * c4 + 3] * (1.f / kActScale));
+            }
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -1350,8 +1358,9 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
     }
   } else if (fine) {
     P.dump_h[0] = out.h_last0; P.dump_s0[0] = out.s_hid0; P.dump_h[1] = out.h_last; P.dump_s0[1] = out.s_hid;
+    P.dump_enc[0] = out.enc0; P.dump_enc[1] = out.enc;
   } else {
-    P.dump_h[0] = out.h_last; P.dump_s0[0] = out.s_hid;
+    P.dump_h[0] = out.h_last; P.dump_s0[0] = out.s_hid; P.dump_enc[0] = out.enc;
   }
   const bool dump = !replay && (P.dump_h[0] || P.dump_h[1] || P.dump_s0[0] || P.dump_s0[1]);
   if (!replay && getenv("NSOS_TRACE") && workspace && workspace_bytes >= tc_render_workspace_bytes(cfg, n_rays)) {

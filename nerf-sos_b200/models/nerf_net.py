@@ -77,9 +77,13 @@ class _RenderFn(torch.autograd.Function):
             Wd = net.nerf.mlp.W
             acts["h_last"] = torch.empty(N, S_last, Wd, **f32)
             acts["s_hid"] = torch.empty(N, S_last, Wd // 2, **f32)
+            if net.nerf.mlp.sem_with_coord:                 # gamma(x) per point: saves the backward its own encoding pass
+                acts["enc"] = torch.empty(N, S_last, 64, **f32)
             if fine:
                 acts["h_last0"] = torch.empty(N, Sc, Wd, **f32)
                 acts["s_hid0"] = torch.empty(N, Sc, Wd // 2, **f32)
+                if net.nerf.mlp.sem_with_coord:
+                    acts["enc0"] = torch.empty(N, Sc, 64, **f32)
         if want["raw"] or acts:
             out["raw"] = torch.empty(N, S_last, Cr, **f32)
             if fine:
@@ -94,7 +98,7 @@ class _RenderFn(torch.autograd.Function):
             out["inds"] = torch.empty(N, K, dtype=torch.int64, device=dev)
         ro = _lib.RenderOut(*[_lib.ptr(out.get(k)) for k in ("maps", "weights0", "weights", "raw0", "raw", "z_vals0", "z_vals",
                                                              "z_samples", "inds")],
-                            *[_lib.ptr(acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")], _lib.ptr(net._status(dev)))
+                            *[_lib.ptr(acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid", "enc0", "enc")], _lib.ptr(net._status(dev)))
         rs = _lib.Randoms(*[_lib.ptr(rnd.get(k)) for k in ("t_rand", "noise0", "u", "noise1", "z_samples")])
         flat_c, flat_f = want.get("flat") or (net.nerf.flat_params(), net.nerf_fine.flat_params())
         pk_c = net.nerf.packed(cfg.mode, force=net.training, flat=flat_c)
@@ -154,7 +158,7 @@ class _RenderFn(torch.autograd.Function):
         saved = None
         if ctx.acts and not trunk:
             saved = C.byref(_lib.RenderOut(None, None, None, _lib.ptr(ctx.acts.get("raw0")), _lib.ptr(ctx.acts.get("raw")), None, None,
-                                           None, None, *[_lib.ptr(ctx.acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid")], None))
+                                           None, None, *[_lib.ptr(ctx.acts.get(k)) for k in ("h_last0", "s_hid0", "h_last", "s_hid", "enc0", "enc")], None))
         with torch.cuda.device(dev):
             _lib.check(L.nsos_render_bwd(cfg, _lib.ptr(flat_c), _lib.ptr(flat_f), _lib.ptr(pk_c), _lib.ptr(pk_f), _lib.ptr(rays_o),
                                          _lib.ptr(rays_d), _lib.ptr(z0),
