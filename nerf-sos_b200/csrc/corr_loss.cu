@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(kT) k_geo_pairs(const float* __restrict__ xyz,
     __syncthreads();
     for (int k = 0; k < 3; ++k) sx[k][threadIdx.x] = (j < M) ? xyz[((size_t)other * 3 + k) * M + j] : 0.f;
     for (int k = 0; k < C; ++k) sc[k][threadIdx.x] = (j < M) ? w.chat[((size_t)other * C + k) * M + j] : 0.f;
-    if (SECOND) srm[threadIdx.x] = (j < M) ? w.rowmean[((size_t)h * B + n) * M + j] : 0.f;
+    // row means of the streamed pixels: pass 3 needs them (its pixel is the SECOND operand), and so does the self term of pass 2,
+    // which folds its own pass 3 in: for the self pair fd and cd are symmetric, so d/d(chat_i) as second operand is the same sum
+    // with t(q,i) = fd - rowmean[q] + ... in place of t(i,q)
+    if (SECOND || h == 1) srm[threadIdx.x] = (j < M) ? w.rowmean[((size_t)h * B + n) * M + j] : 0.f;
     __syncthreads();
     int lim = min(kT, M - j0);
 #pragma unroll 4
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(kT) k_geo_pairs(const float* __restrict__ xyz,
       float cd = fminf(kMaxCorr, raw);
       float t = fd - (SECOND ? srm[jj] : my_rm) + om - shift;          // fd_c - shift
       if (!SECOND) loss -= cd * t;                                      // -clamp(cd,0)*(fd_c-shift), cd > 0 always
+      if (!SECOND && h == 1) t += fd - srm[jj] + om - shift;            // self term: + the role of this pixel as second operand
       if (want_grad && raw <= kMaxCorr) {                               // masked assignment blocks the gradient (:411)
         float a = t * cd * cd;                                          // d(-cd*t)/ds = t*cd^2
 #pragma unroll
@@ -308,7 +312,8 @@ int geo_corr_loss(const float* xyz, const float* code, const int64_t* neg_idx, c
   const float coef0 = (float)(neg_w / denom), coef1 = (float)(self_w / denom);
   if (nq > 0) k_geo_pairs<false><<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, g_code != nullptr, q0);
   if (g_code) {
-    if (nq > 0) k_geo_pairs<true><<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, 1, q0);
+    // pass 3 only for the negative pairs (blockIdx.z = 0): the self pairs were folded into pass 2
+    if (nq > 0) k_geo_pairs<true><<<dim3(grid.x, grid.y, 1), kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, 1, q0);
     k_normalize_bwd<<<nb, 256, 0, st>>>(w.chat, w.invn, w.g_chat, g_code, B, C, M);
   }
   k_finish_loss<<<1, 32, 0, st>>>(w.acc, loss, neg_w / denom, self_w / denom);
