@@ -43,7 +43,7 @@ namespace {
 using namespace ptx;
 
 constexpr int kSlotBytes = 32768;      // one weight slab plane: N(<=256) rows x 64 fp16
-constexpr int kMaxSlots = 6;
+constexpr int kMaxSlots = 6, kDefaultSlots = 3;
 constexpr int kWorkers = 256;          // 8 row-worker warps: warp w -> TMEM lane quarter w%4, column half w/4
 constexpr int kMmaWarp = 8, kProducerWarp = 9;   // producer warps: kProducerWarp .. kProducerWarp + kNumProducers - 1
 constexpr int kNumProducers = 2;                // one thread can issue only ~1 bulk copy per 680 cycles (tools/bulk_rate.cu)
@@ -1369,7 +1369,9 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
   }
   const int smem_max = max_optin_smem();
   NSOS_REQUIRE(smem_max >= 200 * 1024, NSOS_ERR_DEVICE, "device offers only %d B of opt-in shared memory", smem_max);
-  int nslots = kMaxSlots;
+  // ring depth: three 32 KB slots sustain the MMA rate; deeper rings measured 1-2 % slower (profiles/r02_notes.md).  NSOS_NSLOTS overrides (experiments)
+  int nslots = kDefaultSlots;
+  if (const char* e = getenv("NSOS_NSLOTS")) nslots = std::max(2, std::min(kMaxSlots, atoi(e)));
   size_t need = 0;
   for (; nslots >= 2; --nslots) {
     need = carve_smem(nullptr, nslots, Sc, P.Sf, P.C, nullptr) + 1024;
