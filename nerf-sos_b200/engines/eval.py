@@ -1,4 +1,5 @@
-"""Drop-in for the render/metric part of engines/eval.py of the reference: eval_one_view (:31-98) and evaluate (:101-212).
+"""Drop-in for engines/eval.py of the reference: eval_one_view (:31-98), evaluate (:101-212), render_video (:214-270) and
+export_density (:279-304).
 
 A view is rendered by ONE call into the fused kernel (no ray_chunk loop, no [H*W,192,6] `raw` tensor -- 3.5 GB per
 1008x756 view in the reference), optionally ray-sharded over the ranks of a process group, and every metric is computed
@@ -92,3 +93,82 @@ def evaluate(model, dataset, device, save_dir=None, fast_mode=False, ret_cluster
             json.dump(allm, f)
     return {"mse": tot.get("total_mse"), "psnr": tot.get("total_psnr"), "ssim": tot.get("total_ssim"), "lpips": tot.get("total_lpips"),
             "clus_ari": tot.get("total_clus_ari"), "sem_ari": tot.get("total_sem_ari"), "seg_iou": tot.get("total_seg_iou"), "all": allm}
+
+
+def _to8b(x):
+    return (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+
+def render_video(model, dataset, device, save_dir, suffix="", fps=30, quality=8, ret_cluster=True, fast_mode=False, clus_no_sfm=False,
+                 N_cluster=2, find_fg=True, dino=None, group=None, writer=None, **render_kwargs):
+    """eval.py:214-270: renders every view of `dataset` (one fused launch per view) and writes rgb / disp / sem / clus videos.
+    `writer(path, frames_uint8, fps=, quality=)` defaults to imageio.mimwrite when imageio is importable; offline the uint8
+    frame stacks are saved as `<name>.npy` next to where the .mp4 would go.  The foreground polarity check (:231-245) needs a
+    DINO extractor: pass `dino=` (the reference builds one from torch.hub here); without it the clustering is kept as found.
+    Returns the frame stacks."""
+    near, far = dataset.near_far()
+    radii = dataset.radii()
+    rgbs, disps, sems, clusters = [], [], [], []
+    ret = {}
+    for i in range(len(dataset)):
+        if fast_mode and i >= 2:
+            break
+        ret, _ = eval_one_view(model, dataset[i], (near, far), radii, device, clus_no_sfm, N_cluster, group=group, **render_kwargs)
+        if "sem" in ret:
+            sems.append(ret["sem"].float().cpu().numpy())
+        if ret_cluster and "clustering" in ret:
+            c = ret["clustering"]
+            if find_fg and dino is not None:
+                from .trainer import normalize_batch
+                x = normalize_batch(ret["rgb"].permute(2, 0, 1).unsqueeze(0))
+                attn = dino.get_vit_attn_feat_noresize(x)["attn"].reshape(1, 1, x.shape[2] // 16, x.shape[3] // 16)
+                attn = torch.nn.functional.interpolate(attn, x.shape[2:]).reshape(x.shape[2], x.shape[3], 1)
+                if attn[c == 1].mean() < attn[c == 0].mean():
+                    c = 1 - c
+            clusters.append(c.cpu().numpy())
+        rgbs.append(ret["rgb"].cpu().numpy())
+        disps.append(ret["disp"].cpu().numpy())
+    if writer is None:
+        try:
+            import imageio
+            writer = imageio.mimwrite
+        except ImportError:
+            writer = lambda path, frames, **kw: np.save(os.path.splitext(path)[0] + ".npy", frames)
+    os.makedirs(save_dir, exist_ok=True)
+    name = lambda k: os.path.join(save_dir, f"{k}{'_' + suffix if suffix else ''}.mp4")
+    out = {"rgb": _to8b(np.stack(rgbs, 0))}
+    disp = np.stack(disps, 0)
+    out["disp"] = _to8b(disp / np.max(disp))
+    if "semantics" in ret and sems:
+        out["sem"] = _to8b(np.stack(sems, 0))
+    if ret_cluster and clusters:
+        out["clus"] = (np.stack(clusters, 0) * 255).astype(np.uint8)
+    for k, frames in out.items():
+        writer(name(k), frames, fps=fps, quality=quality)
+    return out
+
+
+def export_density(model, extents=(2.0, 2.0, 2.0), voxel_size=2. / 256., save_dir="", device=None, chunk=1 << 22):
+    """eval.py:279-304: queries `model.nerf_fine` on a regular grid (x14, zero view directions) and returns
+    relu(raw[..., -1]) as a numpy volume [W, H, D] -- the LAST raw channel, exactly as the reference does (with a segmentation
+    head that is the last semantic logit, not sigma: raw = [rgb(3), sigma, sem...], nerf_mlp.py:94; use `channel=` semantics by
+    slicing `model.nerf_fine(pts, viewdirs=...)` yourself if sigma is wanted).  The query runs through nsos_mlp_query in slices
+    of `chunk` points; `density.npy` is written when `save_dir` is given (the reference's .mrc / .ply writers need mrc / open3d)."""
+    model.eval()
+    device = device or next(model.parameters()).device
+    with torch.no_grad():
+        h, w, d = extents
+        pts = torch.stack(torch.meshgrid(torch.linspace(-w / 2, w / 2, int(w / voxel_size)), torch.linspace(-h / 2, h / 2, int(h / voxel_size)),
+                                         torch.linspace(-d / 2, d / 2, int(d / voxel_size)), indexing="ij"), dim=-1).to(device).float()
+        pts = pts * 14
+        flat = pts.reshape(-1, 3)
+        sig = torch.empty(flat.shape[0], device=device)
+        for i in range(0, flat.shape[0], chunk):
+            x = flat[i:i + chunk]
+            raw = model.nerf_fine(x, viewdirs=torch.zeros_like(x))
+            sig[i:i + chunk] = raw[..., -1].clamp_min(0)
+        sigma = sig.reshape(pts.shape[:-1]).cpu().numpy()
+    if save_dir:
+        os.makedirs(save_dir, exist_ok=True)
+        np.save(os.path.join(save_dir, "density.npy"), sigma)
+    return sigma

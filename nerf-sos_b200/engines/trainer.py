@@ -181,3 +181,9 @@ def train_one_step(batch, model, optimizer, scheduler, train_loader, global_step
         scheduler.step(global_step)
     return dict(loss=loss, psnr=psnr, sem0=zero, sem1=zero, img0=img_loss0, img1=img_loss, contrast=contrast_l, corr0=corr0,
                 corr1=corr1, geo_corr0=geo0, geo_corr1=geo1, **ari)
+
+
+def save_checkpoint(path, global_step, model, optimizer):
+    """trainer.py:216-222: same dictionary layout ('global_step', 'model', 'optimizer'); FusedAdam's state_dict uses
+    torch.optim.Adam's names, so either side can resume from the other's file."""
+    torch.save({"global_step": global_step, "model": model.state_dict(), "optimizer": optimizer.state_dict()}, path)

@@ -90,3 +90,44 @@ def test_device_metrics_match_reference_metric_code():
     for k, (x, y) in dict(clus_ari=(gt, clus), clus_ari_fg=(gt[fg], clus[fg]), sem_ari=(gt, sem_pred), sem_ari_fg=(gt[fg], sem_pred[fg])).items():
         assert abs(float(M.adjusted_rand_score(x, y)) - float(g[k])) <= 1e-3, k
     assert abs(float(M.binary_iou(clus, gt)) - float(g["iou_fg"])) <= 1e-3
+
+
+def test_render_video_export_density_save_checkpoint(scene, tmp_path):
+    """The remaining engine entry points of the boundary: render_video (eval.py:214-270), export_density (:279-304)
+    and save_checkpoint (trainer.py:216-222)."""
+    from nerfsos_b200.data import ExhibitNeRFDataset
+    from nerfsos_b200.engines.eval import export_density, render_video
+    from nerfsos_b200.engines.optim import FusedAdam
+    from nerfsos_b200.engines.trainer import save_checkpoint
+    from oracle import nerf_oracle as O
+    net = _net().eval()
+    ds = ExhibitNeRFDataset(scene)
+    written = {}
+    out = render_video(net, ds, DEV, str(tmp_path / "vid"), suffix="t", find_fg=False,
+                       writer=lambda path, frames, **kw: written.__setitem__(os.path.basename(path), (frames.shape, frames.dtype, kw["fps"])))
+    assert set(written) == {"rgb_t.mp4", "disp_t.mp4", "sem_t.mp4", "clus_t.mp4"}
+    assert written["rgb_t.mp4"] == ((1, 48, 64, 3), np.uint8, 30) and out["clus"].shape == (1, 48, 64, 1)
+    with torch.no_grad():
+        direct = net(ds[0]["rays"].to(DEV), ds.near_far(), retraw=False)
+    assert np.array_equal(out["rgb"][0], (255 * np.clip(direct["rgb"].cpu().numpy(), 0, 1)).astype(np.uint8))
+    # default writer offline: frame stacks as .npy
+    render_video(net, ds, DEV, str(tmp_path / "vid2"), ret_cluster=False, find_fg=False)
+    assert os.path.exists(tmp_path / "vid2" / "rgb.npy") or os.path.exists(tmp_path / "vid2" / "rgb.mp4")
+
+    # export_density: the reference's grid (x14), zero view directions, relu of the LAST raw channel
+    sig = export_density(net, extents=(0.25, 0.25, 0.25), voxel_size=2. / 64., save_dir=str(tmp_path / "dens"), device=DEV, chunk=300)
+    assert sig.shape == (8, 8, 8) and os.path.exists(tmp_path / "dens" / "density.npy")
+    lin = torch.linspace(-0.125, 0.125, 8)
+    pts = (torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1) * 14).reshape(-1, 3).numpy()
+    sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+    _, fine = O.split_state_dict(sd)
+    mk = dict(D=net.nerf_fine.mlp.D, skips=tuple(net.nerf_fine.mlp.skips))
+    ref = O.mlp_forward(fine, O.encode(pts, 10), O.encode(np.zeros_like(pts), 4), **mk)
+    np.testing.assert_allclose(sig.reshape(-1), np.maximum(ref[:, -1], 0), rtol=1e-4, atol=5e-4)
+
+    opt = FusedAdam([p for p in net.parameters()], lr=1e-3)
+    path = str(tmp_path / "ck.ckpt")
+    save_checkpoint(path, 7, net, opt)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert ck["global_step"] == 7 and set(ck) == {"global_step", "model", "optimizer"}
+    assert set(ck["model"]) == set(net.state_dict()) and "param_groups" in ck["optimizer"]
