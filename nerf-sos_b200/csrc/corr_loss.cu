@@ -14,6 +14,9 @@
 // FP32 + MUFU issue rate, not by HBM or tensor cores.
 #include "internal.h"
 
+#include <algorithm>
+#include <type_traits>
+
 namespace nsos {
 namespace {
 
@@ -24,13 +27,37 @@ constexpr float kMaxCorr = 15.f, kEpsCorr = 5e-2f;
 struct GeoWs {
   float* chat;      // [B,C,M] normalised code
   float* invn;      // [B,M]   1/max(|code|,eps)  (0 where the norm is clamped: no gradient through eps)
-  float* rowmean;   // [2,B,M]
+  float* rowmean;   // [js][2,B,M] partial row means, one per split of the streamed pixels (summed in a fixed order by the readers)
+  int js;           // number of partials
   float* g_chat;    // [B,C,M]
   double* acc;      // [0..1] sum of rowmeans per helper, [2..3] loss sums per helper
   float* oldmean;   // [2]
 };
 
 __device__ __forceinline__ float inv_l1(float s) { return fminf(kMaxCorr, 1.f / (s + kEpsCorr)); }   // image.py:404-413
+
+// The pair kernels have one thread per pixel of a patch and stream the M pixels of the other patch: B*M*2 = 65 k threads for the
+// shipped batch, 256 blocks for 148 SMs (1.7 waves of 8 warps per SM -- latency-bound at a sixth of the issue rate).  The streamed
+// range is therefore split `js` ways over more blocks (partial sums meet in the atomics that were there already; row means are
+// kept as `js` partials and summed in a fixed order where they are read, so the result does not depend on block scheduling).
+constexpr int kGeoJsMax = 8, kGeoBlocksTarget = 1024;     // ~7 resident 256-thread blocks on each of the 148 SMs
+__host__ inline int geo_jsplit(int blocks, int M) {
+  const int ntile = (M + kT - 1) / kT;
+  int js = 1;
+  while (js < kGeoJsMax && blocks * js < kGeoBlocksTarget && js * 2 <= ntile) js *= 2;
+  return js;
+}
+// [j_begin, j_end) of split jp
+__device__ __forceinline__ void geo_jrange(int M, int js, int jp, int& jb, int& je) {
+  const int ntile = (M + kT - 1) / kT, per = (ntile + js - 1) / js;
+  jb = min(M, jp * per * kT);
+  je = min(M, (jp + 1) * per * kT);
+}
+__device__ __forceinline__ float geo_rowmean_at(const GeoWs& w, int h, int B, int M, int n, int i) {
+  float r = 0.f;
+  for (int k = 0; k < w.js; ++k) r += w.rowmean[(((size_t)k * 2 + h) * B + n) * M + i];
+  return r;
+}
 
 // F.normalize(code, dim=1, eps=1e-10) (image.py:300-301)
 __global__ void k_normalize(const float* __restrict__ code, float* __restrict__ chat, float* __restrict__ invn, int B, int C, int M) {
@@ -50,22 +77,25 @@ __global__ void __launch_bounds__(kT) k_geo_rowmean(const float* __restrict__ xy
   __shared__ float sx[3][kT];
   const int n = q0 + blockIdx.y, h = blockIdx.z;
   const int nb = (h == 0) ? (int)neg[n] : n;
-  const int p = blockIdx.x * kT + threadIdx.x;
+  const int nbi = (M + kT - 1) / kT, jp = blockIdx.x / nbi;
+  const int p = (blockIdx.x % nbi) * kT + threadIdx.x;
   const bool act = p < M;
+  int jb, je;
+  geo_jrange(M, w.js, jp, jb, je);
   float x0 = 0, x1 = 0, x2 = 0;
   if (act) { x0 = xyz[((size_t)n * 3 + 0) * M + p]; x1 = xyz[((size_t)n * 3 + 1) * M + p]; x2 = xyz[((size_t)n * 3 + 2) * M + p]; }
   float sum = 0.f;
-  for (int q0 = 0; q0 < M; q0 += kT) {
+  for (int q0 = jb; q0 < je; q0 += kT) {
     int q = q0 + threadIdx.x;
     __syncthreads();
     for (int c = 0; c < 3; ++c) sx[c][threadIdx.x] = (q < M) ? xyz[((size_t)nb * 3 + c) * M + q] : 0.f;
     __syncthreads();
-    int lim = min(kT, M - q0);
+    int lim = min(kT, je - q0);
 #pragma unroll 8
     for (int j = 0; j < lim; ++j) sum += inv_l1(fabsf(x0 - sx[0][j]) + fabsf(x1 - sx[1][j]) + fabsf(x2 - sx[2][j]));
   }
   float rm = sum / (float)M;
-  if (act) w.rowmean[((size_t)h * B + n) * M + p] = rm;
+  if (act) w.rowmean[(((size_t)jp * 2 + h) * B + n) * M + p] = rm;        // this split's share of the mean
   // block partial of the sum of row means -> old_mean
   float v = act ? rm : 0.f;
 #pragma unroll
@@ -84,9 +114,10 @@ __global__ void k_export_sums(const double* acc, double* sums) {
 
 // pass 2 (SECOND=false): thread per p of the first patch, loop over q of the second: loss + grad wrt chat[n,:,p]
 // pass 3 (SECOND=true):  thread per q of the second patch, loop over p of the first: grad wrt chat[nb,:,q]
-template <bool SECOND>
+// CT = compile-time channel count (1..4, the shipped sem_dim is 2), or kCMax for the guarded generic loop
+template <bool SECOND, int CT>
 __global__ void __launch_bounds__(kT) k_geo_pairs(const float* __restrict__ xyz, const int64_t* __restrict__ neg, GeoWs w, int B, int C, int M,
-                                                  float shift0, float shift1, float coef0, float coef1, int want_grad, int q0) {
+                                                  float shift0, float shift1, float coef0, float coef1, int want_grad, int q0, int js) {
   __shared__ float sx[3][kT];
   __shared__ float sc[kCMax][kT];
   __shared__ float srm[kT];
@@ -96,36 +127,42 @@ __global__ void __launch_bounds__(kT) k_geo_pairs(const float* __restrict__ xyz,
   const float coef = h ? coef1 : coef0;                  // weight_h / (B*M*M)
   const float om = w.oldmean[h];
   const int me = SECOND ? nb : n, other = SECOND ? n : nb;   // patch this thread's pixel / the streamed pixels belong to
-  const int i = blockIdx.x * kT + threadIdx.x;
+  const int nbi = (M + kT - 1) / kT, jp = blockIdx.x / nbi;
+  const int i = (blockIdx.x % nbi) * kT + threadIdx.x;
   const bool act = i < M;
-  float x[3] = {0, 0, 0}, c[kCMax], g[kCMax];
+  int jb, je;
+  geo_jrange(M, js, jp, jb, je);
+  float x[3] = {0, 0, 0}, c[CT], g[CT];
 #pragma unroll
-  for (int k = 0; k < kCMax; ++k) { c[k] = 0.f; g[k] = 0.f; }
+  for (int k = 0; k < CT; ++k) { c[k] = 0.f; g[k] = 0.f; }
   float my_rm = 0.f;
   if (act) {
+#pragma unroll
     for (int k = 0; k < 3; ++k) x[k] = xyz[((size_t)me * 3 + k) * M + i];
-    for (int k = 0; k < C; ++k) c[k] = w.chat[((size_t)me * C + k) * M + i];
-    if (!SECOND) my_rm = w.rowmean[((size_t)h * B + n) * M + i];
+#pragma unroll
+    for (int k = 0; k < CT; ++k) if (k < C) c[k] = w.chat[((size_t)me * C + k) * M + i];
+    if (!SECOND) my_rm = geo_rowmean_at(w, h, B, M, n, i);
   }
   float loss = 0.f;
-  for (int j0 = 0; j0 < M; j0 += kT) {
+  for (int j0 = jb; j0 < je; j0 += kT) {
     int j = j0 + threadIdx.x;
     __syncthreads();
     for (int k = 0; k < 3; ++k) sx[k][threadIdx.x] = (j < M) ? xyz[((size_t)other * 3 + k) * M + j] : 0.f;
-    for (int k = 0; k < C; ++k) sc[k][threadIdx.x] = (j < M) ? w.chat[((size_t)other * C + k) * M + j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < CT; ++k) if (k < C) sc[k][threadIdx.x] = (j < M) ? w.chat[((size_t)other * C + k) * M + j] : 0.f;
     // row means of the streamed pixels: pass 3 needs them (its pixel is the SECOND operand), and so does the self term of pass 2,
     // which folds its own pass 3 in: for the self pair fd and cd are symmetric, so d/d(chat_i) as second operand is the same sum
     // with t(q,i) = fd - rowmean[q] + ... in place of t(i,q)
-    if (SECOND || h == 1) srm[threadIdx.x] = (j < M) ? w.rowmean[((size_t)h * B + n) * M + j] : 0.f;
+    if (SECOND || h == 1) srm[threadIdx.x] = (j < M) ? geo_rowmean_at(w, h, B, M, n, j) : 0.f;
     __syncthreads();
-    int lim = min(kT, M - j0);
+    int lim = min(kT, je - j0);
 #pragma unroll 4
     for (int jj = 0; jj < lim; ++jj) {
       float fd = inv_l1(fabsf(x[0] - sx[0][jj]) + fabsf(x[1] - sx[1][jj]) + fabsf(x[2] - sx[2][jj]));
       float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < kCMax; ++k)
-        if (k < C) s += fabsf(c[k] - sc[k][jj]);
+      for (int k = 0; k < CT; ++k)
+        if (CT < kCMax || k < C) s += fabsf(c[k] - sc[k][jj]);
       float raw = 1.f / (s + kEpsCorr);
       float cd = fminf(kMaxCorr, raw);
       float t = fd - (SECOND ? srm[jj] : my_rm) + om - shift;          // fd_c - shift
@@ -134,8 +171,8 @@ __global__ void __launch_bounds__(kT) k_geo_pairs(const float* __restrict__ xyz,
       if (want_grad && raw <= kMaxCorr) {                               // masked assignment blocks the gradient (:411)
         float a = t * cd * cd;                                          // d(-cd*t)/ds = t*cd^2
 #pragma unroll
-        for (int k = 0; k < kCMax; ++k)
-          if (k < C) {
+        for (int k = 0; k < CT; ++k)
+          if (CT < kCMax || k < C) {
             float d = c[k] - sc[k][jj];
             float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);      // d|u|/du, 0 at 0 like torch.abs
             g[k] += a * sg;                                             // same sign for both roles: d = mine - other
@@ -143,8 +180,10 @@ __global__ void __launch_bounds__(kT) k_geo_pairs(const float* __restrict__ xyz,
       }
     }
   }
-  if (want_grad && act)
-    for (int k = 0; k < C; ++k) atomicAdd(&w.g_chat[((size_t)me * C + k) * M + i], g[k] * coef);
+  if (want_grad && act) {
+#pragma unroll
+    for (int k = 0; k < CT; ++k) if (k < C) atomicAdd(&w.g_chat[((size_t)me * C + k) * M + i], g[k] * coef);
+  }
   if (!SECOND) {
     float v = act ? loss : 0.f;
 #pragma unroll
@@ -175,7 +214,7 @@ __global__ void k_normalize_bwd(const float* __restrict__ chat, const float* __r
 size_t carve_geo(char* base, int B, int C, int M, GeoWs* w) {
   size_t off = 0;
   auto take = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
-  size_t o1 = take(sizeof(float) * B * C * M), o2 = take(sizeof(float) * B * M), o3 = take(sizeof(float) * 2 * B * M),
+  size_t o1 = take(sizeof(float) * B * C * M), o2 = take(sizeof(float) * B * M), o3 = take(sizeof(float) * kGeoJsMax * 2 * B * M),
          o4 = take(sizeof(float) * B * C * M), o5 = take(sizeof(double) * 4), o6 = take(sizeof(float) * 2);
   if (w && base) {
     w->chat = (float*)(base + o1); w->invn = (float*)(base + o2); w->rowmean = (float*)(base + o3);
@@ -297,7 +336,11 @@ int geo_corr_loss(const float* xyz, const float* code, const int64_t* neg_idx, c
   NSOS_REQUIRE(workspace && workspace_bytes >= need, NSOS_ERR_WORKSPACE, "geo_corr_loss: workspace too small (%zu < %zu)", workspace_bytes, need);
   const float self_shift = params[0], self_w = params[1], neg_shift = params[2], neg_w = params[3];   // HOST array
   const int nb = (B * M + 255) / 256;
-  dim3 grid((M + kT - 1) / kT, nq, 2);
+  const int nbi = (M + kT - 1) / kT;
+  // splits of the streamed pixel range (the same in phases 1 and 2: the row-mean partials stay in the workspace between them)
+  const int js = geo_jsplit(nbi * std::max(nq, 1) * 2, M), js3 = geo_jsplit(nbi * std::max(nq, 1), M);
+  w.js = js;
+  dim3 grid(nbi * js, nq, 2);
   if (phase != 2) {
     NSOS_CHECK_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 4, st));
     k_normalize<<<nb, 256, 0, st>>>(code, w.chat, w.invn, B, C, M);
@@ -310,10 +353,20 @@ int geo_corr_loss(const float* xyz, const float* code, const int64_t* neg_idx, c
   const double denom = (double)Bt * M * M;
   // helper 0 = negative pair (neg_shift, neg_weight), helper 1 = self pair (image.py:476-482)
   const float coef0 = (float)(neg_w / denom), coef1 = (float)(self_w / denom);
-  if (nq > 0) k_geo_pairs<false><<<grid, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, g_code != nullptr, q0);
+  auto pairs = [&](auto second, dim3 gr, int want, int jsplit) {
+    constexpr bool S2 = decltype(second)::value;
+    switch (C) {
+      case 1: k_geo_pairs<S2, 1><<<gr, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, want, q0, jsplit); break;
+      case 2: k_geo_pairs<S2, 2><<<gr, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, want, q0, jsplit); break;
+      case 3: k_geo_pairs<S2, 3><<<gr, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, want, q0, jsplit); break;
+      case 4: k_geo_pairs<S2, 4><<<gr, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, want, q0, jsplit); break;
+      default: k_geo_pairs<S2, kCMax><<<gr, kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, want, q0, jsplit); break;
+    }
+  };
+  if (nq > 0) pairs(std::false_type{}, grid, g_code != nullptr, js);
   if (g_code) {
     // pass 3 only for the negative pairs (blockIdx.z = 0): the self pairs were folded into pass 2
-    if (nq > 0) k_geo_pairs<true><<<dim3(grid.x, grid.y, 1), kT, 0, st>>>(xyz, neg_idx, w, B, C, M, neg_shift, self_shift, coef0, coef1, 1, q0);
+    if (nq > 0) pairs(std::true_type{}, dim3(nbi * js3, nq, 1), 1, js3);
     k_normalize_bwd<<<nb, 256, 0, st>>>(w.chat, w.invn, w.g_chat, g_code, B, C, M);
   }
   k_finish_loss<<<1, 32, 0, st>>>(w.acc, loss, neg_w / denom, self_w / denom);
@@ -351,7 +404,7 @@ int app_corr_loss(const float* feats, const float* nfeats, const float* code, co
   }
   NSOS_REQUIRE(loss, NSOS_ERR_BAD_ARG, "app_corr_loss: loss pointer missing");
   NSOS_CHECK_CUDA(cudaMemsetAsync(w.g_chat, 0, sizeof(float) * 2 * B * C * S, st));
-  k_oldmean<<<1, 32, 0, st>>>(GeoWs{nullptr, nullptr, nullptr, nullptr, w.acc, w.oldmean}, phase == 2 ? sh->sums : w.acc, (double)Bt * S);
+  k_oldmean<<<1, 32, 0, st>>>(GeoWs{nullptr, nullptr, nullptr, 1, nullptr, w.acc, w.oldmean}, phase == 2 ? sh->sums : w.acc, (double)Bt * S);
   const double denom = (double)Bt * S * S;
   const float coef0 = (float)(neg_w / denom), coef1 = (float)(self_w / denom);
   k_app_pairs<<<dim3(B, 2), 256, 0, st>>>(w, B, C, S, neg_shift, self_shift, coef0, coef1, want);
