@@ -99,13 +99,17 @@ typedef struct NsosRenderOut {
   float* z_samples;  /* [N, K] (unsorted, as drawn)  */
   int64_t* inds;     /* [N, K] searchsorted indices  */
   /* Optional activations saved for nsos_render_bwd (tcgen05 modes, W=256; ignored by NSOS_MODE_SIMT_FP32):
-   * last trunk activation relu(pts_linears[D-1]) and semantic hidden layer relu(semantic_linear.0), per point. */
-  float* h_last0;    /* [N, Sc, W]                   */
-  float* s_hid0;     /* [N, Sc, W/2]                 */
-  float* h_last;     /* [N, Sc+K, W]                 */
-  float* s_hid;      /* [N, Sc+K, W/2]               */
-  float* enc0;       /* [N, Sc, 64]   gamma(x) of the coarse points (63 columns + one zero), only needed with sem_with_coord:   */
-  float* enc;        /* [N, Sc+K, 64] saves the backward pass a separate positional-encoding kernel                             */
+   * last trunk activation relu(pts_linears[D-1]) and semantic hidden layer relu(semantic_linear.0), per point.
+   * OPAQUE to the caller: hand the same pointers back to nsos_render_bwd.  The library writes them in the layout its
+   * weight-gradient kernel contracts over -- groups of 32 consecutive points, feature-major inside a group: element
+   * (pt, f) of an F-wide array at ((pt >> 5) * F + f) * 32 + (pt & 31) -- so every buffer must hold
+   * ceil(points / 32) * 32 * F floats (points = N*Sc resp. N*(Sc+K)). */
+  float* h_last0;    /* N*Sc points,     F = W       */
+  float* s_hid0;     /* N*Sc points,     F = W/2     */
+  float* h_last;     /* N*(Sc+K) points, F = W       */
+  float* s_hid;      /* N*(Sc+K) points, F = W/2     */
+  float* enc0;       /* N*Sc points,     F = 64: gamma(x) of the coarse points (63 columns + one zero), only needed with sem_with_coord: */
+  float* enc;        /* N*(Sc+K) points, F = 64: saves the backward pass a separate positional-encoding kernel                          */
   /* Optional sticky status word (caller zero-initialises, reads and clears it; never reset by the library).
    * bit 0: NSOS_MODE_TC_EXACT/FAST only -- a hidden activation exceeded the fp16 range of the activation planes
    *        (|a| > 4094): the rgb / semantics maps of the affected rays are NaN.  Render such nets with NSOS_MODE_SIMT_FP32. */

@@ -43,8 +43,12 @@ int tc_rowgemm(const float* A, int64_t lda, int K, const float* B, int64_t b_rs,
                size_t scratch_bytes, cudaStream_t st);
 // tc_wgrad.cu (semantic-head weight gradients on tcgen05)
 bool tc_sem_wgrad_supported(const NetGeom& g);
-int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, const float* s0,
-                 const float* g_raw, int64_t P, cudaStream_t st);
+// true: the activations saved for the semantic-head backward (h_last, s_hid, gamma) use the blocked layout -- groups of 32
+// consecutive points, feature-major inside a group: (pt, f) of an F-wide tensor at ((pt >> 5) * F + f) * 32 + (pt & 31);
+// buffers hold ceil(points / 32) * 32 * F floats.  false: row-major [point][feature] (fp32 fallback of the weight gradients).
+bool sem_saves_blocked(const NetGeom& coarse, const NetGeom& fine);   // one answer for both nets of a render call
+int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, int enc_blocked,
+                 const float* s0, const float* g_raw, int64_t P, cudaStream_t st);
 bool tc_wgrad_gen_supported(int Mo, int64_t ldy, int main_w, int64_t ld_main, int aux_w);
 int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_t ld_main, int main_col, const float* aux, int64_t ld_aux,
                  int aux_w, int aux_col, float* dW, int64_t ldw, float* db, int64_t P, cudaStream_t st);

@@ -600,8 +600,9 @@ size_t carve_bwd_tc(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& 
   w.enc = c.take<float>(Pm * kEncLd); w.encv = c.take<float>(R * kEncVLd); w.dnorm = c.take<float>(R);
   w.raw[0] = c.take<float>(P0 * gc.C); w.raw[1] = c.take<float>(P1 * gf.C + 1);
   w.g_raw = c.take<float>(Pm * std::max(gc.C, gf.C));
-  w.h[0] = c.take<float>(P0 * gc.W); w.s0[0] = c.take<float>(P0 * (gc.W / 2));
-  w.h[1] = c.take<float>(P1 * gf.W + 1); w.s0[1] = c.take<float>(P1 * (gf.W / 2) + 1);
+  // (+32 points: the blocked layout of the replayed activations rounds the point count up to whole groups)
+  w.h[0] = c.take<float>((P0 + 32) * gc.W); w.s0[0] = c.take<float>((P0 + 32) * (gc.W / 2));
+  w.h[1] = c.take<float>((P1 + 32) * gf.W + 1); w.s0[1] = c.take<float>((P1 + 32) * (gf.W / 2) + 1);
   w.g_half = c.take<float>(Pm * (std::max(gc.W, gf.W) / 2 + 1));
   if (ws) *ws = w;
   return align_up(c.off, 256);
@@ -688,8 +689,9 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
                                                              seed, r0, is_fine ? RNG_NOISE1 : RNG_NOISE0, S, g.C, g.sem_dim,
                                                              cfg.white_bkgd, g_maps + r0 * ML, ML, moff, w.g_raw, n);
         NSOS_CHECK_CUDA(cudaGetLastError());
-        if (tc_sem_wgrad_supported(g) && !getenv("NSOS_WGRAD_SIMT")) {
-          rc = tc_sem_wgrad(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, h_p[pass], enc_p, kEncLd, s_p[pass], w.g_raw, P, st);
+        if (sem_saves_blocked(gc, gf)) {  // h / s0 (and a saved gamma) are in the blocked layout then
+          rc = tc_sem_wgrad(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, h_p[pass], enc_p, kEncLd, enc_p != w.enc, s_p[pass],
+                            w.g_raw, P, st);
         } else {
           MlpBufs b{};
           b.h[g.D - 1] = const_cast<float*>(h_p[pass]); b.s0 = const_cast<float*>(s_p[pass]);

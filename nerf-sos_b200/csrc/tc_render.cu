@@ -304,6 +304,11 @@ struct TcParams {
   float* dump_all[2][kMaxStages];   // [layer][n_rays*S, W]  relu(pts_linears[layer]); entries may be null
   float* dump_hv[2];                // [n_rays*S, W/2] relu(views_linears.0)
   float* dump_enc[2];               // [n_rays*S, 64]  gamma(x) (training forward: the semantic-head weight gradients read it)
+  // Layout of dump_h / dump_s0 / dump_enc per pass.  0: row-major [point][feature].  1: blocked -- groups of 32 consecutive points,
+  // feature-major inside a group: element (pt, f) of an F-wide tensor sits at ((pt >> 5) * F + f) * 32 + (pt & 31).  The 32 lanes of
+  // an epilogue warp hold 32 consecutive points, so one store instruction covers one 128-byte line (row-major: 32 lines), and
+  // kernel C (tc_wgrad.cu), which contracts over points, reads 32 points of a feature with one coalesced load.
+  int dump_blocked[2];
 };
 constexpr int kTraceTiles = 16, kTraceStamps = 12;  // [tile][stage][stamp]; 5..8: a_ready[j] seen by the MMA lane, 9..11: worker 0 hands over slab 0..2
 
@@ -560,7 +565,7 @@ __device__ __forceinline__ void encode_half(const float x[3], int L, int enc, bo
 // (+relu) feeds the fp32 head accumulators (head weights are pre-divided by 16) and/or becomes the next A operand.
 constexpr int kCW = 16;   // epilogue chunk width in columns (one tcgen05.ld) = one K-step of the next layer
 constexpr int kSW = 16;   // arithmetic sub-block of a chunk
-template <int KIND, bool EXACT, bool DUMP, bool DALL = false>
+template <int KIND, bool EXACT, bool DUMP, bool DALL = false, bool BLK = false>
 __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
                                         const float* __restrict__ hw, int sem_dim, float (&hacc)[4], float (&hodd)[4],
                                         float* __restrict__ gout, float& vmax) {
@@ -615,9 +620,14 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
         }
     }
     if (((DUMP && (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SEM || KIND == EPI_SEM_WIDE)) || (DALL && (KIND == EPI_HIDDEN || KIND == EPI_RGB))) && gout) {
-      // saved activations: 16-byte stores (rows are W resp. W/2 floats, c0 + j a multiple of 4 on the odd pair)
-      if (j & 2) *reinterpret_cast<float4*>(gout + c0 + j - 2) = make_float4(dq0, dq1, x0 * (1.f / kActScale), x1 * (1.f / kActScale));
-      else { dq0 = x0 * (1.f / kActScale); dq1 = x1 * (1.f / kActScale); }
+      if (BLK) {
+        // blocked layout (gout = this point's slot in its group of 32): one 128-byte line per warp store
+        gout[(size_t)(c0 + j) * 32] = x0 * (1.f / kActScale);
+        gout[(size_t)(c0 + j + 1) * 32] = x1 * (1.f / kActScale);
+      } else if (j & 2) {
+        // row-major: 16-byte stores (rows are W resp. W/2 floats, c0 + j a multiple of 4 on the odd pair)
+        *reinterpret_cast<float4*>(gout + c0 + j - 2) = make_float4(dq0, dq1, x0 * (1.f / kActScale), x1 * (1.f / kActScale));
+      } else { dq0 = x0 * (1.f / kActScale); dq1 = x1 * (1.f / kActScale); }
     }
     if (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA) {
       vmax = fmaxf(vmax, fmaxf(x0, x1));          // range guard: 16*a must stay below the fp16 maximum (checked once per tile)
@@ -637,13 +647,13 @@ __device__ __forceinline__ void epi_sub(const uint32_t* v, uint32_t tm_lane, int
   }
 }
 
-template <int KIND, bool EXACT, bool DUMP, bool DALL = false>
+template <int KIND, bool EXACT, bool DUMP, bool DALL = false, bool BLK = false>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[kCW], uint32_t tm_lane, int c0, float inv16, const float* __restrict__ bias,
                                           const float* __restrict__ hw, int sem_dim, float (&hacc)[4], float (&hodd)[4],
                                           float* __restrict__ gout, float& vmax) {
 #pragma unroll
   for (int sb = 0; sb < kCW / kSW; ++sb)
-    epi_sub<KIND, EXACT, DUMP, DALL>(&v[kSW * sb], tm_lane, c0 + kSW * sb, inv16, bias, hw, sem_dim, hacc, hodd, gout, vmax);
+    epi_sub<KIND, EXACT, DUMP, DALL, BLK>(&v[kSW * sb], tm_lane, c0 + kSW * sb, inv16, bias, hw, sem_dim, hacc, hodd, gout, vmax);
 }
 __device__ __forceinline__ void tmem_ldc(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 __device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[16]) { tmem_wait_ld_fence16(r); }
@@ -654,7 +664,7 @@ __device__ __forceinline__ void tmem_wait_ldc(uint32_t (&r)[16]) { tmem_wait_ld_
 // hand the slab to the MMA warp once their part is stored, so the next stage's MMAs start after a fraction of the epilogue
 // instead of all of it.  Slab 0 is handed over in two halves (K-steps 0-1 after the first chunk of every warp, 2-3 after the
 // second): a_ready[0], a_ready[1]; slab j >= 1 uses a_ready[1+j].
-template <int KIND, bool EXACT, bool DUMP, bool DALL = false>
+template <int KIND, bool EXACT, bool DUMP, bool DALL = false, bool BLK = false>
 __device__ __forceinline__ void epi_kind(int cb, int ce, int hf, uint32_t tm_lane, float inv16, const float* bias, const float* hw,
                                          int sem_dim, float* hacc, float* gout, float& vmax, uint32_t a_ready0, long long* trs = nullptr) {
   constexpr bool SLAB = (KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA);
@@ -670,12 +680,12 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, int hf, uint32_t tm_lan
   tmem_wait_ldc(va);
   for (int i = 0; i < cnt; i += 2) {
     if (i + 1 < cnt) tmem_ldc(tm_lane + col(i + 1), vb);
-    epi_chunk<KIND, EXACT, DUMP, DALL>(va, tm_lane, col(i), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
+    epi_chunk<KIND, EXACT, DUMP, DALL, BLK>(va, tm_lane, col(i), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
     if (SLAB && i == 0) { hand_over(0u); if (trs) trs[9] = clock64(); }
     if (i + 1 < cnt) {
       tmem_wait_ldc(vb);
       if (i + 2 < cnt) tmem_ldc(tm_lane + col(i + 2), va);
-      epi_chunk<KIND, EXACT, DUMP, DALL>(vb, tm_lane, col(i + 1), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
+      epi_chunk<KIND, EXACT, DUMP, DALL, BLK>(vb, tm_lane, col(i + 1), inv16, bias, hw, sem_dim, he, ho, gout, vmax);
       if (SLAB) {                       // my chunks of slab i/2 are stored
         hand_over(1u + (uint32_t)(i >> 1));
         if (trs && (i >> 1) < 2) trs[10 + (i >> 1)] = clock64();
@@ -692,11 +702,11 @@ __device__ __forceinline__ void epi_kind(int cb, int ce, int hf, uint32_t tm_lan
   }
 }
 
-template <bool EXACT, bool DUMP = false, bool DALL = false>
+template <bool EXACT, bool DUMP = false, bool DALL = false, bool BLK = false>
 __device__ __forceinline__ void epilogue(int kind, int cb, int ce, int hf, uint32_t tm_lane, float inv16, const float* bias,
                                          const float* hw, int sem_dim, float* hacc, float* gout, float& vmax, uint32_t a_ready0,
                                          long long* trs = nullptr) {
-#define NSOS_EPI(K) epi_kind<K, EXACT, DUMP, DALL>(cb, ce, hf, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax, a_ready0, trs)
+#define NSOS_EPI(K) epi_kind<K, EXACT, DUMP, DALL, BLK>(cb, ce, hf, tm_lane, inv16, bias, hw, sem_dim, hacc, gout, vmax, a_ready0, trs)
   switch (kind) {
     case EPI_HIDDEN: NSOS_EPI(EPI_HIDDEN); break;
     case EPI_HIDDEN_SIGMA: NSOS_EPI(EPI_HIDDEN_SIGMA); break;
@@ -735,9 +745,11 @@ __device__ __forceinline__ void init_pipeline(const Smem& sm, int nslots, int wa
 // MODE 0: forward.  MODE 1: forward that also saves h_last / s_hid per point (training).  MODE 2: replay at given sample
 // depths (backward recompute: no sampling, no compositing) with the same saves.  MODE 3: replay that saves EVERY hidden layer and
 // the views hidden layer (recompute of the all-parameter backward).
-template <bool EXACT, int MODE>
+// BLK (MODE 1 / 2): dump_h / dump_s0 / dump_enc in the blocked layout of TcParams::dump_blocked (both passes alike)
+template <bool EXACT, int MODE, bool BLK = false>
 __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant__ TcParams P) {
   constexpr bool REPLAY = (MODE >= 2), DUMP = (MODE >= 1), DALL = (MODE == 3);
+  static_assert(!BLK || (DUMP && !DALL), "the blocked layout belongs to the semantic-head saves");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   Smem sm;
@@ -902,11 +914,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             if (hf == 0) encode_half<0>(x, pg.Lp, pg.enc, rowvalid, e); else encode_half<1>(x, pg.Lp, pg.enc, rowvalid, e);
             store_halfrow_sw128(sm.g_hi, sm.g_lo, row, hf, e, EXACT);
             if (DUMP && P.dump_enc[pass] && rowvalid && rp[9] > 0.f) {       // e = 16 * gamma(x): exact power-of-two rescale
-              float4* ge = reinterpret_cast<float4*>(P.dump_enc[pass] + ((size_t)ray * S + i) * 64 + 32 * hf);
+              const size_t pt = (size_t)ray * S + i;
+              if (BLK) {
+                float* ge = P.dump_enc[pass] + ((pt >> 5) * 64 + 32 * hf) * 32 + (pt & 31);
 #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4)
-                ge[c4] = make_float4(e[4 * c4] * (1.f / kActScale), e[4 * c4 + 1] * (1.f / kActScale), e[4 * c4 + 2] * (1.f / kActScale),
-                                     e[4 * c4 + 3] * (1.f / kActScale));
+                for (int c = 0; c < 32; ++c) ge[c * 32] = e[c] * (1.f / kActScale);
+              } else {
+                float4* ge = reinterpret_cast<float4*>(P.dump_enc[pass] + pt * 64 + 32 * hf);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                  ge[c4] = make_float4(e[4 * c4] * (1.f / kActScale), e[4 * c4 + 1] * (1.f / kActScale), e[4 * c4 + 2] * (1.f / kActScale),
+                                       e[4 * c4 + 3] * (1.f / kActScale));
+              }
             }
           }
           fence_proxy_async_smem();
@@ -942,17 +961,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
             if (tr) tr[st * kTraceStamps + 1] = clock64();                 // accumulator ready
             float* ha = (Sg.epi == EPI_HIDDEN_SIGMA) ? &hacc[0] : sem_part ? &hacc[4] : &hacc[1];
             float* gout = nullptr;
+            constexpr bool blk = BLK;
             if (DUMP && rowvalid && rp[9] > 0.f) {
               const size_t pt = (size_t)ray * S + i;
-              if (Sg.epi == EPI_HIDDEN_SIGMA && P.dump_h[pass]) gout = P.dump_h[pass] + pt * pg.W;
-              if (sem_part && P.dump_s0[pass]) gout = P.dump_s0[pass] + pt * pg.H2;
+              if (Sg.epi == EPI_HIDDEN_SIGMA && P.dump_h[pass]) gout = P.dump_h[pass] + (blk ? (pt >> 5) * 32 * pg.W + (pt & 31) : pt * pg.W);
+              if (sem_part && P.dump_s0[pass]) gout = P.dump_s0[pass] + (blk ? (pt >> 5) * 32 * pg.H2 + (pt & 31) : pt * pg.H2);
               if (DALL) {
                 if (Sg.epi == EPI_HIDDEN && P.dump_all[pass][st]) gout = P.dump_all[pass][st] + pt * pg.W;
                 if (rgb_part && P.dump_hv[pass]) gout = P.dump_hv[pass] + pt * pg.H2;
               }
             }
             const int kind = merged ? (hf ? EPI_RGB : EPI_SEM) : Sg.epi;
-            epilogue<EXACT, DUMP, DALL>(kind, cb, ce, hf, tm_d + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout, vmax, a_ready0,
+            epilogue<EXACT, DUMP, DALL, BLK>(kind, cb, ce, hf, tm_d + ((merged && hf) ? (uint32_t)pg.H2 : 0u), inv16, bias, hw, P.sem_dim, ha, gout, vmax, a_ready0,
                                   tr ? tr + st * kTraceStamps : nullptr);
             if (Sg.epi == EPI_HIDDEN_SIGMA && hf == 1) sm.hpart[row * 8] = hacc[0];   // sigma share of the upper column half
             if (tr) tr[st * kTraceStamps + 2] = clock64();                 // epilogue done (this thread)
@@ -1363,6 +1383,11 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
     P.dump_h[0] = out.h_last; P.dump_s0[0] = out.s_hid; P.dump_enc[0] = out.enc;
   }
   const bool dump = !replay && (P.dump_h[0] || P.dump_h[1] || P.dump_s0[0] || P.dump_s0[1]);
+  // what the semantic-head weight-gradient kernel reads is written in its blocked layout (the all-parameter replay feeds row GEMMs)
+  if (!(replay && (replay->dump_all[0] || replay->dump_all[1]))) {
+    P.dump_blocked[0] = P.dump_blocked[1] = sem_saves_blocked(gc, gf) ? 1 : 0;
+  }
+  const bool blk = P.dump_blocked[0] != 0;
   if (!replay && getenv("NSOS_TRACE") && workspace && workspace_bytes >= tc_render_workspace_bytes(cfg, n_rays)) {
     P.trace = reinterpret_cast<long long*>(workspace);
     NSOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(long long) * kTraceTiles * 16 * kTraceStamps, st));
@@ -1408,7 +1433,9 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
   };
   const bool replay_all = replay && (replay->dump_all[0] || replay->dump_all[1]);
   if (replay_all) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 3>) : launch(k_render_tc<false, 3>));
+  else if (replay && blk) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 2, true>) : launch(k_render_tc<false, 2, true>));
   else if (replay) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 2>) : launch(k_render_tc<false, 2>));
+  else if (dump && blk) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 1, true>) : launch(k_render_tc<false, 1, true>));
   else if (dump) NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 1>) : launch(k_render_tc<false, 1>));
   else NSOS_CHECK_CUDA(exact ? launch(k_render_tc<true, 0>) : launch(k_render_tc<false, 0>));
   NSOS_CHECK_CUDA(cudaGetLastError());

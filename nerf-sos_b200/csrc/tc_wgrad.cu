@@ -31,7 +31,9 @@ namespace {
 using namespace ptx;
 
 constexpr int kWgWorkers = 256, kWgThreads = 288, kWgMmaWarp = 8;   // k_wgrad_gen: 8 fill warps + an issuer warp
-constexpr int kSemThreads = 256;   // k_sem_wgrad: 8 warps (255 registers each: 28 loads in flight per thread); warp 0 also issues the MMAs
+constexpr int kSemThreads = 256;   // k_sem_wgrad: 8 fill warps (two sets of 14 loads per lane, 255 registers); warp 0 also issues the MMAs
+                                   // (a ninth warp would cost every thread 87 registers: allocation is per 4 warps)
+constexpr int kHalfPts = 32;                       // points per fill / MMA unit: half of a 64-point tile
 constexpr int kSlabPts = 64;
 constexpr int kRowsA = 128, kRowsB = 320, kRowsB2 = 16;
 constexpr int kColD1 = 0, kColD1b = 256, kColD2 = 320;
@@ -42,12 +44,13 @@ struct WgParams {
   float *gW0, *gb0, *gW2, *gb2;
   long long P;
   int C, enc_dim, enc_ld, sem_dim, sem_coord, ld0;
+  int enc_blocked;   // gamma rows: blocked like h / s0 (saved by the training forward) or row-major with pitch enc_ld (k_encode_pts)
 };
 
 struct WgSmem {
   uint8_t *a[2], *a2[2], *b[2], *b2[2];   // [plane]: 0 = hi, 1 = lo
   float* w2;                              // [4][128]
-  uint64_t *ready, *done;
+  uint64_t *ready, *done;                 // [2] each: one pair per tile half
   uint32_t* tmem_ptr;
 };
 __host__ __device__ inline size_t wg_carve(uint8_t* base, WgSmem* s) {
@@ -58,10 +61,10 @@ __host__ __device__ inline size_t wg_carve(uint8_t* base, WgSmem* s) {
   for (int p = 0; p < 2; ++p) oa2[p] = take(kRowsA * 128, 1024);
   for (int p = 0; p < 2; ++p) ob[p] = take(kRowsB * 128, 1024);
   for (int p = 0; p < 2; ++p) ob2[p] = take(kRowsB2 * 128, 1024);
-  size_t ow = take(sizeof(float) * 4 * 128, 16), obar = take(16, 8), otp = take(16, 16);
+  size_t ow = take(sizeof(float) * 4 * 128, 16), obar = take(32, 8), otp = take(16, 16);
   if (s) {
     for (int p = 0; p < 2; ++p) { s->a[p] = base + oa[p]; s->a2[p] = base + oa2[p]; s->b[p] = base + ob[p]; s->b2[p] = base + ob2[p]; }
-    s->w2 = (float*)(base + ow); s->ready = (uint64_t*)(base + obar); s->done = s->ready + 1; s->tmem_ptr = (uint32_t*)(base + otp);
+    s->w2 = (float*)(base + ow); s->ready = (uint64_t*)(base + obar); s->done = s->ready + 2; s->tmem_ptr = (uint32_t*)(base + otp);
   }
   return off;
 }
@@ -106,17 +109,27 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, bool valid,
   }
 }
 
+// One point's share of a 32-point half slab as held by one lane of fill warp e: 32 h values, 8 gamma values, 16 s0 values
+// (14 independent 16-byte loads) and the point's semantic-logit gradients.
+struct SemLoads {
+  float hv[4][8], ev[8], sv[2][8], gs[4];
+  bool valid;
+};
+
+// Round 2: the 64-point tiles are filled and consumed as two 32-point halves (K-steps 0-1 / 2-3 of the same SWIZZLE_128B rows), each
+// with its own ready / done barrier pair: the eight fill warps convert half h+1 while the issuer warp's MMAs read half h, and every
+// lane keeps the loads of the NEXT half in flight (second register set) while it converts the current one.  Lane = point, warp =
+// feature eighth.  Before: one 64-point buffer, loads -> wait -> fill -> MMA in sequence, 2.0 TB/s.
 __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_constant__ WgParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   WgSmem sm;
   wg_carve(base, &sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
-  const long long nslabs = (P.P + kSlabPts - 1) / kSlabPts;
-  const long long my_slabs = (nslabs - blockIdx.x + gridDim.x - 1) / gridDim.x;     // >= 1 (grid <= nslabs)
+  const long long nhalf = (P.P + kHalfPts - 1) / kHalfPts;
+  const long long my_n = (nhalf - blockIdx.x + gridDim.x - 1) / gridDim.x;     // >= 1 (grid <= nhalf)
   if (t == 0) {
-    mbar_init(smem_u32(sm.ready), kWgWorkers);
-    mbar_init(smem_u32(sm.done), 1);
+    for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(&sm.ready[h]), kWgWorkers); mbar_init(smem_u32(&sm.done[h]), 1); }
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
@@ -126,6 +139,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
     reinterpret_cast<uint32_t*>(sm.b2[1])[i] = 0u;
   }
   for (int i = t; i < 4 * 128; i += kSemThreads) sm.w2[i] = (i / 128 < P.sem_dim) ? __ldg(&P.w_s2[i]) : 0.f;
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -134,93 +148,112 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
   const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, a2[2] = {smem_u32(sm.a2[0]), smem_u32(sm.a2[1])};
   const uint32_t b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])}, b2[2] = {smem_u32(sm.b2[0]), smem_u32(sm.b2[1])};
   const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64), id16 = make_idesc_bf16(16);
+  // 3 x 2 x 3 MMAs per half (hi.hi, lo.hi, hi.lo; M=128, N=256/64/16, K=16), issued by warp 0 once all 256 threads have arrived
+  auto issue = [&](int half, long long it) {
+    mbar_wait(smem_u32(&sm.ready[half]), (uint32_t)((it >> 1) & 1), 700 + half);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;     // hi.hi, lo.hi, hi.lo
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int ks = 2 * half + k2;
+          const uint32_t acc = (it > 0 || pass > 0 || k2 > 0) ? 1u : 0u;
+          const uint64_t da = make_sw128_desc(a[pa] + ks * 32), db = make_sw128_desc(b[pb] + ks * 32);
+          umma_ss(tm + kColD1, da, db, id256, acc);
+          umma_ss(tm + kColD1b, da, make_sw128_desc(b[pb] + 256 * 128 + ks * 32), id64, acc);
+          umma_ss(tm + kColD2, make_sw128_desc(a2[pa] + ks * 32), make_sw128_desc(b2[pb] + ks * 32), id16, acc);
+        }
+      }
+      umma_commit(smem_u32(&sm.done[half]));
+    }
+    __syncwarp();
+  };
   {
-    const int pgp = warp & 1, q = warp >> 1;            // point group (32 points), feature quarter
-    const int pl = 32 * pgp + lane, wd = pl >> 1;
+    // ================= fill warps =================
+    const int e = warp;                                  // feature eighth: h 32e.., gamma 8e.., s0 units 16e..
     float gb2_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long it = 0; it < my_slabs; ++it) {
-      const long long slab = blockIdx.x + it * gridDim.x;
-      const long long p = slab * kSlabPts + pl;
-      const bool valid = p < P.P;
-      // issue the first global loads before waiting for the tensor pipe to release the tiles
-      float gs[4] = {0.f, 0.f, 0.f, 0.f};
-      if (valid)
-        for (int c = 0; c < 4; ++c) if (c < P.sem_dim) gs[c] = __ldg(&P.g_raw[p * P.C + 4 + c]);
-      // This thread's share of the slab is 64 h values, 16 gamma values and 32 s0 values of one point.
-      // All of this thread's share of the slab is requested up front: 28 independent 16-byte loads per thread (112 KB in flight
-      // per SM) before anything is converted.  Round 1 kept a rolling window of 8 (32 KB per SM), which left the kernel at 23-32 %
-      // of the HBM roofline: latency-bound at 9 warps per SM.  The loads also overlap the tensor pipe working on the previous slab.
-      float hv[8][8], ev[2][8], sv[4][8];
-      const float* hrow = P.h + p * 256 + q * 64;
+    // h / s0 (and gamma when the forward pass saved it) arrive in the blocked layout (internal.h: sem_saves_blocked): the half is
+    // one group of 32 points, a feature's 32 values are one 128-byte line -> every load instruction of the warp is one line
+    auto load = [&](SemLoads& L, long long it) {
+      const long long grp = blockIdx.x + it * gridDim.x;
+      const long long p = grp * kHalfPts + lane;
+      L.valid = p < P.P;
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) load8(hrow + 8 * g8, valid, hv[g8]);
+      for (int c = 0; c < 4; ++c) L.gs[c] = (L.valid && c < P.sem_dim) ? __ldg(&P.g_raw[p * P.C + 4 + c]) : 0.f;
+      const float* hb = P.h + (grp * 256 + e * 32) * kHalfPts + lane;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) load8(P.enc + p * P.enc_ld + q * 16 + 8 * k, valid && P.sem_coord, ev[k]);
+      for (int g8 = 0; g8 < 4; ++g8)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) load8(P.s0 + p * 128 + q * 32 + 8 * k, valid, sv[k]);
-      if (it > 0) { mbar_wait(smem_u32(sm.done), (uint32_t)((it - 1) & 1), 710); tc_fence_after(); }
+        for (int i = 0; i < 8; ++i) L.hv[g8][i] = L.valid ? __ldg(hb + (8 * g8 + i) * kHalfPts) : 0.f;
+      if (P.enc_blocked) {
+        const float* eb = P.enc + (grp * P.enc_ld + e * 8) * kHalfPts + lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) L.ev[i] = (L.valid && P.sem_coord) ? __ldg(eb + i * kHalfPts) : 0.f;
+      } else {
+        load8(P.enc + p * P.enc_ld + e * 8, L.valid && P.sem_coord, L.ev);
+      }
+      const float* sb = P.s0 + (grp * 128 + e * 16) * kHalfPts + lane;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) L.sv[k][i] = L.valid ? __ldg(sb + (8 * k + i) * kHalfPts) : 0.f;
+    };
+    auto fill = [&](SemLoads& L, int half, long long it) {
+      // the MMAs that read this half two iterations ago have completed
+      if (it >= 2) { mbar_wait(smem_u32(&sm.done[half]), (uint32_t)(((it >> 1) - 1) & 1), 710 + half); tc_fence_after(); }
+      const int wd = (kHalfPts * half + lane) >> 1;      // 32-bit word (point pair) of the tile row
       // ---- B rows 0..255: h
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) put8(sm.b[0], sm.b[1], q * 64 + 8 * g8, hv[g8], lane, wd);
+      for (int g8 = 0; g8 < 4; ++g8) put8(sm.b[0], sm.b[1], e * 32 + 8 * g8, L.hv[g8], lane, wd);
       // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0)
-#pragma unroll
-      for (int g8 = 0; g8 < 2; ++g8) {
-        const int e0 = q * 16 + 8 * g8;
+      {
+        const int e0 = e * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (e0 + i >= P.enc_dim) ev[g8][i] = 0.f;
-          if (e0 + i == 63) ev[g8][i] = valid ? 1.f : 0.f;
+          if (e0 + i >= P.enc_dim) L.ev[i] = 0.f;
+          if (e0 + i == 63) L.ev[i] = L.valid ? 1.f : 0.f;
         }
-        put8(sm.b[0], sm.b[1], 256 + e0, ev[g8], lane, wd);
+        put8(sm.b[0], sm.b[1], 256 + e0, L.ev, lane, wd);
       }
-      // ---- A2 = s0^T and A = g_s0^T, units q*32..+31
+      // ---- A2 = s0^T and A = g_s0^T, units 16e..16e+15
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {
-        const int u0 = q * 32 + 8 * g8;
-        put8(sm.a2[0], sm.a2[1], u0, sv[g8], lane, wd);
+      for (int g8 = 0; g8 < 2; ++g8) {
+        const int u0 = e * 16 + 8 * g8;
+        put8(sm.a2[0], sm.a2[1], u0, L.sv[g8], lane, wd);
         float g[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float d = 0.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) d = fmaf(gs[c], sm.w2[c * 128 + u0 + i], d);     // zero rows beyond sem_dim
-          g[i] = sv[g8][i] > 0.f ? d : 0.f;
+          for (int c = 0; c < 4; ++c) d = fmaf(L.gs[c], sm.w2[c * 128 + u0 + i], d);     // zero rows beyond sem_dim
+          g[i] = L.sv[g8][i] > 0.f ? d : 0.f;
         }
         put8(sm.a[0], sm.a[1], u0, g, lane, wd);
       }
       // ---- B2 = g_sem^T (rows 0..7; rows >= sem_dim are zero)
-      if (q == 0) {
-        float g[8] = {gs[0], gs[1], gs[2], gs[3], 0.f, 0.f, 0.f, 0.f};
+      if (e == 7) {                                      // (warp 0 carries the MMA issue)
+        float g[8] = {L.gs[0], L.gs[1], L.gs[2], L.gs[3], 0.f, 0.f, 0.f, 0.f};
         put8(sm.b2[0], sm.b2[1], 0, g, lane, wd);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gb2_acc[c] += gs[c];
+        for (int c = 0; c < 4; ++c) gb2_acc[c] += L.gs[c];
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(smem_u32(sm.ready));
-      if (warp == 0) {                                   // the slab's tiles are complete once all 256 threads have arrived
-        mbar_wait(smem_u32(sm.ready), (uint32_t)(it & 1), 700);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;     // hi.hi, lo.hi, hi.lo
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t acc = (it > 0 || pass > 0 || ks > 0) ? 1u : 0u;
-              const uint64_t da = make_sw128_desc(a[pa] + ks * 32), db = make_sw128_desc(b[pb] + ks * 32);
-              umma_ss(tm + kColD1, da, db, id256, acc);
-              umma_ss(tm + kColD1b, da, make_sw128_desc(b[pb] + 256 * 128 + ks * 32), id64, acc);
-              umma_ss(tm + kColD2, make_sw128_desc(a2[pa] + ks * 32), make_sw128_desc(b2[pb] + ks * 32), id16, acc);
-            }
-          }
-          umma_commit(smem_u32(sm.done));
-        }
-        __syncwarp();
-      }
+      mbar_arrive(smem_u32(&sm.ready[half]));
+      if (warp == 0) issue(half, it);
+    };
+    SemLoads L0, L1;
+    load(L0, 0);
+    for (long long it = 0; it < my_n; it += 2) {
+      if (it + 1 < my_n) load(L1, it + 1);
+      fill(L0, 0, it);
+      if (it + 2 < my_n) load(L0, it + 2);
+      if (it + 1 < my_n) fill(L1, 1, it + 1);
     }
     // ---- epilogue: TMEM partial sums -> global gradients (atomics; every CTA contributes)
-    mbar_wait(smem_u32(sm.done), (uint32_t)((my_slabs - 1) & 1), 720);
+    mbar_wait(smem_u32(&sm.done[(my_n - 1) & 1]), (uint32_t)(((my_n - 1) >> 1) & 1), 720);     // the last commit covers every earlier MMA
     tc_fence_after();
     const int q4 = warp & 3, hf = warp >> 2;
     const int u = q4 * 32 + lane;
@@ -246,7 +279,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
       for (int c = 0; c < 4; ++c)
         if (c < P.sem_dim) atomicAdd(&P.gW2[c * 128 + u], __uint_as_float(r[c]));
     }
-    if (q == 0) {
+    if (e == 7) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float s = gb2_acc[c];
@@ -414,26 +447,30 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen(const __grid_consta
 
 }  // namespace
 
+bool sem_saves_blocked(const NetGeom& gc, const NetGeom& gf) {
+  return tc_sem_wgrad_supported(gc) && tc_sem_wgrad_supported(gf) && !getenv("NSOS_WGRAD_SIMT");
+}
 bool tc_sem_wgrad_supported(const NetGeom& g) {
   return g.use_viewdirs && g.use_sem && g.W == 256 && g.enc <= 63 && g.sem_dim >= 1 && g.sem_dim <= 4;
 }
 
-// h [P,256], enc [P,enc_ld] (gamma(x), only read with sem_with_coord), s0 [P,128] (post-ReLU), g_raw [P,C] (sem gradients in
-// columns 4..).  Accumulates into the flat gradient buffer `grads` (layout of nsos_param_layout).
-int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, const float* s0,
-                 const float* g_raw, int64_t P, cudaStream_t st) {
+// h (256 features) and s0 (128, post-ReLU) in the BLOCKED layout (sem_saves_blocked), starting at a multiple of 32 points;
+// enc = gamma(x), 64 features, only read with sem_with_coord: blocked (enc_blocked) or row-major [P,enc_ld]; g_raw [P,C] row-major
+// (sem gradients in columns 4..).  Accumulates into the flat gradient buffer `grads` (layout of nsos_param_layout).
+int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, int enc_blocked,
+                 const float* s0, const float* g_raw, int64_t P, cudaStream_t st) {
   NSOS_REQUIRE(tc_sem_wgrad_supported(g), NSOS_ERR_UNSUPPORTED, "semantic-head wgrad kernel needs W=256, sem_dim<=4");
   if (P <= 0) return NSOS_OK;
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.h = h; p.enc = enc; p.s0 = s0; p.g_raw = g_raw; p.w_s2 = prm + g.w_s2;
   p.gW0 = grads + g.w_s0; p.gb0 = grads + g.b_s0; p.gW2 = grads + g.w_s2; p.gb2 = grads + g.b_s2;
-  p.P = P; p.C = g.C; p.enc_dim = g.enc; p.enc_ld = enc_ld; p.sem_dim = g.sem_dim; p.sem_coord = g.sem_coord; p.ld0 = g.sem_in;
+  p.P = P; p.C = g.C; p.enc_dim = g.enc; p.enc_ld = enc_ld; p.enc_blocked = enc_blocked; p.sem_dim = g.sem_dim; p.sem_coord = g.sem_coord; p.ld0 = g.sem_in;
   int dev = 0, sms = 0;
   NSOS_CHECK_CUDA(cudaGetDevice(&dev));
   NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const long long nslabs = (P + kSlabPts - 1) / kSlabPts;
-  const int grid = (int)std::min<long long>(nslabs, sms);
+  const long long nhalf = (P + kHalfPts - 1) / kHalfPts;
+  const int grid = (int)std::min<long long>(nhalf, sms);
   const size_t need = wg_carve(nullptr, nullptr) + 1024;
   NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_sem_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   k_sem_wgrad<<<grid, kSemThreads, need, st>>>(p);

@@ -74,16 +74,19 @@ class _RenderFn(torch.autograd.Function):
         # the backward pass does not recompute the trunk (393 kB per ray at 64+192 samples; beyond the cap it replays)
         acts = {}
         if _save_acts(net, params, cfg, N * (Sc + (Sf if fine else 0)), want.get("grad", False)):
+            # opaque to Python: the library writes them in its blocked layout (groups of 32 points, csrc/internal.h
+            # sem_saves_blocked), hence the point count rounded up to whole groups
             Wd = net.nerf.mlp.W
-            acts["h_last"] = torch.empty(N, S_last, Wd, **f32)
-            acts["s_hid"] = torch.empty(N, S_last, Wd // 2, **f32)
+            pts = lambda S: (N * S + 31) // 32 * 32
+            acts["h_last"] = torch.empty(pts(S_last) * Wd, **f32)
+            acts["s_hid"] = torch.empty(pts(S_last) * (Wd // 2), **f32)
             if net.nerf.mlp.sem_with_coord:                 # gamma(x) per point: saves the backward its own encoding pass
-                acts["enc"] = torch.empty(N, S_last, 64, **f32)
+                acts["enc"] = torch.empty(pts(S_last) * 64, **f32)
             if fine:
-                acts["h_last0"] = torch.empty(N, Sc, Wd, **f32)
-                acts["s_hid0"] = torch.empty(N, Sc, Wd // 2, **f32)
+                acts["h_last0"] = torch.empty(pts(Sc) * Wd, **f32)
+                acts["s_hid0"] = torch.empty(pts(Sc) * (Wd // 2), **f32)
                 if net.nerf.mlp.sem_with_coord:
-                    acts["enc0"] = torch.empty(N, Sc, 64, **f32)
+                    acts["enc0"] = torch.empty(pts(Sc) * 64, **f32)
         if want["raw"] or acts:
             out["raw"] = torch.empty(N, S_last, Cr, **f32)
             if fine:
