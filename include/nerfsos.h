@@ -246,12 +246,15 @@ int nsos_selftest_umma(const float* a, const float* w, float* d, int32_t N, int3
  *   rowgemm: C[P,N] (=|+=) epi(A[P,K] . B), B(k,n) = b[k*b_rs + n*b_cs]   (dgrad through a layer: B = W; feature_linear: B = W^T)
  *            K multiple of 64 <= 256, N multiple of 32 <= 256; epi = +bias, ReLU, keep where mask > 0; scratch >= 2*K*N*2 + 2048 B
  *   wgrad:   dW[Mo,.] += dY[P,Mo]^T . [main (256 wide) | aux (<= 64 wide)]   (contraction over points; Mo = 128 or 256);
- *            db (optional, aux_w <= 63): db[Mo] += column sums of dY (bias gradient) from a constant-one feature in the same launch */
+ *            db (optional, aux_w <= 63): db[Mo] += column sums of dY (bias gradient) from a constant-one feature in the same launch;
+ *            scratch >= nsos_selftest_wgrad_scratch_bytes(): per-CTA partial sums, reduced by a second launch (no atomics) */
 int nsos_selftest_rowgemm(const float* a, int64_t lda, int32_t K, const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc,
                           int32_t N, const float* mask, int64_t mask_ld, const float* bias, int relu, int accumulate, int64_t P,
                           void* scratch, size_t scratch_bytes, void* stream);
 int nsos_selftest_wgrad(const float* dY, int64_t ldy, int32_t Mo, const float* main, int64_t ld_main, int32_t main_col, const float* aux,
-                        int64_t ld_aux, int32_t aux_w, int32_t aux_col, float* dW, int64_t ldw, float* db, int64_t P, void* stream);
+                        int64_t ld_aux, int32_t aux_w, int32_t aux_col, float* dW, int64_t ldw, float* db, int64_t P, void* scratch,
+                        size_t scratch_bytes, void* stream);
+size_t nsos_selftest_wgrad_scratch_bytes(void);
 
 #ifdef __cplusplus
 }

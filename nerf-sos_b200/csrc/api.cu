@@ -180,9 +180,13 @@ int nsos_selftest_rowgemm(const float* a, int64_t lda, int32_t K, const float* b
   return tc_rowgemm(a, lda, K, b, b_rs, b_cs, c, ldc, N, mask, mask_ld, bias, relu, accumulate, P, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 int nsos_selftest_wgrad(const float* dY, int64_t ldy, int32_t Mo, const float* main, int64_t ld_main, int32_t main_col, const float* aux,
-                        int64_t ld_aux, int32_t aux_w, int32_t aux_col, float* dW, int64_t ldw, float* db, int64_t P, void* stream) {
-  NSOS_REQUIRE(dY && dW && (main || aux), NSOS_ERR_BAD_ARG, "nsos_selftest_wgrad: null argument");
-  return tc_wgrad_gen(dY, ldy, Mo, main, ld_main, main_col, aux, ld_aux, aux_w, aux_col, dW, ldw, db, P, (cudaStream_t)stream);
+                        int64_t ld_aux, int32_t aux_w, int32_t aux_col, float* dW, int64_t ldw, float* db, int64_t P, void* scratch,
+                        size_t scratch_bytes, void* stream) {
+  NSOS_REQUIRE(dY && dW && (main || aux) && scratch, NSOS_ERR_BAD_ARG, "nsos_selftest_wgrad: null argument");
+  return tc_wgrad_gen(dY, ldy, Mo, main, ld_main, main_col, aux, ld_aux, aux_w, aux_col, dW, ldw, db, P, scratch, scratch_bytes,
+                      (cudaStream_t)stream);
+}
+size_t nsos_selftest_wgrad_scratch_bytes(void) { return tc_wgrad_part_bytes();
 }
 
 }  // extern "C"

@@ -47,11 +47,13 @@ bool tc_sem_wgrad_supported(const NetGeom& g);
 // consecutive points, feature-major inside a group: (pt, f) of an F-wide tensor at ((pt >> 5) * F + f) * 32 + (pt & 31);
 // buffers hold ceil(points / 32) * 32 * F floats.  false: row-major [point][feature] (fp32 fallback of the weight gradients).
 bool sem_saves_blocked(const NetGeom& coarse, const NetGeom& fine);   // one answer for both nets of a render call
+// both weight-gradient kernels leave per-CTA partial sums in `part` (>= tc_wgrad_part_bytes()) and reduce them in a second launch
+size_t tc_wgrad_part_bytes();
 int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, int enc_blocked,
-                 const float* s0, const float* g_raw, int64_t P, cudaStream_t st);
+                 const float* s0, const float* g_raw, int64_t P, void* part, size_t part_bytes, cudaStream_t st);
 bool tc_wgrad_gen_supported(int Mo, int64_t ldy, int main_w, int64_t ld_main, int aux_w);
 int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_t ld_main, int main_col, const float* aux, int64_t ld_aux,
-                 int aux_w, int aux_col, float* dW, int64_t ldw, float* db, int64_t P, cudaStream_t st);
+                 int aux_w, int aux_col, float* dW, int64_t ldw, float* db, int64_t P, void* part, size_t part_bytes, cudaStream_t st);
 int tc_selftest(const float* a, const float* w, float* d, int N, int K, int a_in_tmem, int mode, void* scratch, size_t scratch_bytes,
                 cudaStream_t st);
 

@@ -207,8 +207,10 @@ __global__ void __launch_bounds__(256) k_small_wgrad(const float* __restrict__ d
 // direction encoding) stays on the fp32 CUDA-core GEMM.
 struct TcCtx {
   bool on = false;
-  void* scratch = nullptr;
+  void* scratch = nullptr;       // packed B operand of tc_rowgemm
   size_t scratch_bytes = 0;
+  void* part = nullptr;          // per-CTA partial sums of the weight-gradient kernels (tc_wgrad_part_bytes())
+  size_t part_bytes = 0;
 };
 int gemm_dispatch(const GemmArgs& a, const TcCtx* tc, cudaStream_t st) {
   if (tc && tc->on && !a.A2 && a.a1_cs == 1 && a.a1_rowdiv <= 1 && a.b_rowdiv <= 1 && a.c_cs == 1 && a.split_k <= 1 && a.K1 % 64 == 0 &&
@@ -282,7 +284,7 @@ int wgrad(const float* dY, int64_t ldy, int N, const float* X1, int64_t ldx1, in
   }
   // tensor cores: the 256-wide source is `main`, a <= 64-wide source of per-point rows is `aux` (gamma(x)); one launch for both
   bool done[2] = {false, false};
-  if (tc && tc->on && (N == 128 || N == 256) && ldy % 4 == 0) {
+  if (tc && tc->on && tc->part && (N == 128 || N == 256) && ldy % 4 == 0) {
     const float* X[2] = {X1, X2}; const int64_t ld[2] = {ldx1, ldx2}; const int K[2] = {K1, K2}; const int col[2] = {0, K1};
     const int rd[2] = {1, x2_rowdiv};
     int im = -1, ia = -1;
@@ -294,7 +296,7 @@ int wgrad(const float* dY, int64_t ldy, int N, const float* X1, int64_t ldx1, in
     if (im >= 0 || ia >= 0) {
       float* db_tc = (ia < 0 || K[ia] <= 63) ? db : nullptr;
       int rc = tc_wgrad_gen(dY, ldy, N, im >= 0 ? X[im] : nullptr, im >= 0 ? ld[im] : 0, im >= 0 ? col[im] : 0, ia >= 0 ? X[ia] : nullptr,
-                            ia >= 0 ? ld[ia] : 0, ia >= 0 ? K[ia] : 0, ia >= 0 ? col[ia] : 0, dW, K1 + K2, db_tc, P, st);
+                            ia >= 0 ? ld[ia] : 0, ia >= 0 ? K[ia] : 0, ia >= 0 ? col[ia] : 0, dW, K1 + K2, db_tc, P, tc->part, tc->part_bytes, st);
       if (rc) return rc;
       if (im >= 0) done[im] = true;
       if (ia >= 0) done[ia] = true;
@@ -553,7 +555,7 @@ namespace {
 struct BwdAllWs {
   float *enc, *encv, *dnorm, *g_raw, *G0, *G1, *g_half, *g_feat, *feat;
   float *raw[2], *h[2][16], *hv[2], *s0[2];
-  uint8_t* scratch;
+  uint8_t *scratch, *part;     // rowgemm operand image; partial sums of the weight-gradient kernels
 };
 size_t carve_bwd_all(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& gf, int64_t R, char* base, BwdAllWs* ws) {
   const bool fine = cfg.n_importance > 0;
@@ -573,6 +575,7 @@ size_t carve_bwd_all(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom&
     w.hv[p] = c.take<float>(Pp[p] * (g.W / 2) + 1); w.s0[p] = c.take<float>(Pp[p] * (g.W / 2) + 1);
   }
   w.scratch = c.take<uint8_t>(kTcScratch);
+  w.part = c.take<uint8_t>(tc_wgrad_part_bytes());
   if (ws) *ws = w;
   return align_up(c.off, 256);
 }
@@ -590,6 +593,7 @@ namespace {
 int64_t bwd_tc_chunk_rays(int64_t n_rays) { return n_rays < 4096 ? n_rays : 4096; }
 struct BwdTcWs {
   float *enc, *encv, *dnorm, *raw[2], *g_raw, *h[2], *s0[2], *g_half;
+  uint8_t* part;      // partial sums of the weight-gradient kernel
 };
 size_t carve_bwd_tc(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& gf, int64_t R, char* base, BwdTcWs* ws) {
   const bool fine = cfg.n_importance > 0;
@@ -604,6 +608,7 @@ size_t carve_bwd_tc(const NsosRenderCfg& cfg, const NetGeom& gc, const NetGeom& 
   w.h[0] = c.take<float>((P0 + 32) * gc.W); w.s0[0] = c.take<float>((P0 + 32) * (gc.W / 2));
   w.h[1] = c.take<float>((P1 + 32) * gf.W + 1); w.s0[1] = c.take<float>((P1 + 32) * (gf.W / 2) + 1);
   w.g_half = c.take<float>(Pm * (std::max(gc.W, gf.W) / 2 + 1));
+  w.part = c.take<uint8_t>(tc_wgrad_part_bytes());
   if (ws) *ws = w;
   return align_up(c.off, 256);
 }
@@ -691,7 +696,7 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
         NSOS_CHECK_CUDA(cudaGetLastError());
         if (sem_saves_blocked(gc, gf)) {  // h / s0 (and a saved gamma) are in the blocked layout then
           rc = tc_sem_wgrad(g, is_fine ? pf : pc, is_fine ? grads_f : grads_c, h_p[pass], enc_p, kEncLd, enc_p != w.enc, s_p[pass],
-                            w.g_raw, P, st);
+                            w.g_raw, P, w.part, tc_wgrad_part_bytes(), st);
         } else {
           MlpBufs b{};
           b.h[g.D - 1] = const_cast<float*>(h_p[pass]); b.s0 = const_cast<float*>(s_p[pass]);
@@ -712,7 +717,7 @@ int simt_render_bwd(const NsosRenderCfg& cfg, const float* pc, const float* pf, 
     NsosRandoms rn{nullptr, nullptr, nullptr, nullptr, nullptr};
     if (rnd) rn = *rnd;
     TcCtx tcx;
-    tcx.on = true; tcx.scratch = w.scratch; tcx.scratch_bytes = kTcScratch;
+    tcx.on = true; tcx.scratch = w.scratch; tcx.scratch_bytes = kTcScratch; tcx.part = w.part; tcx.part_bytes = tc_wgrad_part_bytes();
     for (int64_t r0 = 0; r0 < n_rays; r0 += R) {
       const int64_t n = std::min(R, n_rays - r0);
       const float* ro = rays_o + r0 * 3; const float* rd = rays_d + r0 * 3;

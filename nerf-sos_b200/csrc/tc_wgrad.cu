@@ -39,9 +39,45 @@ constexpr int kRowsA = 128, kRowsB = 320, kRowsB2 = 16;
 constexpr int kColD1 = 0, kColD1b = 256, kColD2 = 320;
 constexpr uint32_t kWgTmemCols = 512;
 
+// ---- second stage of the weight gradients ----------------------------------------------------------------------
+// Every CTA of a weight-gradient kernel holds a [128 x 336] partial sum in TMEM.  Adding those to the gradient buffer with
+// atomics (round 1) cost more than the contraction: 148 CTAs x 41 k atomics on the same addresses per launch, 16 launches per
+// training step = 4.8 of the kernel's 7 ms.  The CTAs now store their partials column-major ([cta][col][128 rows]: a warp
+// store is one line) into scratch memory and k_wgrad_reduce adds them up in a fixed order -- coalesced, deterministic.
+constexpr int kPartCols = 336, kPartRows = 128, kPartMaxCtas = 160;
+constexpr size_t kPartFloatsPerCta = (size_t)kPartCols * kPartRows;
+struct WgSeg {          // columns [c0, c1) of the partial -> dst[row * rs + (col - c0) * cs], rows < nrows
+  int c0, c1, nrows;
+  float* dst;
+  long long rs, cs;
+};
+struct WgReduceParams {
+  const float* part;    // [ny][ncta][kPartCols][kPartRows]
+  int ncta;
+  WgSeg seg[2][4];      // [blockIdx.y]
+};
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const __grid_constant__ WgReduceParams R) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= kPartCols * kPartRows) return;
+  const int col = idx / kPartRows, row = idx % kPartRows, y = blockIdx.y;
+  const WgSeg* sg = nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (col >= R.seg[y][i].c0 && col < R.seg[y][i].c1 && row < R.seg[y][i].nrows) sg = &R.seg[y][i];
+  if (!sg) return;
+  const float* p = R.part + ((size_t)y * R.ncta * kPartCols + col) * kPartRows + row;
+  float s0 = 0.f, s1 = 0.f;
+  int b = 0;
+  for (; b + 1 < R.ncta; b += 2) { s0 += p[(size_t)b * kPartFloatsPerCta]; s1 += p[(size_t)(b + 1) * kPartFloatsPerCta]; }
+  if (b < R.ncta) s0 += p[(size_t)b * kPartFloatsPerCta];
+  float* d = sg->dst + row * sg->rs + (col - sg->c0) * sg->cs;
+  *d += s0 + s1;
+}
+
 struct WgParams {
   const float *h, *enc, *s0, *g_raw, *w_s2;
   float *gW0, *gb0, *gW2, *gb2;
+  float* part;       // [gridDim.x][kPartCols][128] partial sums of this launch (k_wgrad_reduce adds them to the gradients)
   long long P;
   int C, enc_dim, enc_ld, sem_dim, sem_coord, ld0;
   int enc_blocked;   // gamma rows: blocked like h / s0 (saved by the training forward) or row-major with pitch enc_ld (k_encode_pts)
@@ -109,12 +145,20 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, bool valid,
   }
 }
 
-// One point's share of a 32-point half slab as held by one lane of fill warp e: 32 h values, 8 gamma values, 16 s0 values
-// (14 independent 16-byte loads) and the point's semantic-logit gradients.
+// One lane's share of a 32-point half slab: TWO neighbouring points (2m, 2m+1; m = lane & 15) of the features
+// f = base + 2k + (lane >> 4): 16 h features, 4 gamma features, 8 s0 units of fill warp e (28 independent 8-byte loads), and the
+// two points' semantic-logit gradients.  A neighbouring pair is one 32-bit word of a K-major bf16 tile row: no shuffles.
 struct SemLoads {
-  float hv[4][8], ev[8], sv[2][8], gs[4];
-  bool valid;
+  float hx[16], hy[16], ex[4], ey[4], sx[8], sy[8];     // .x = point 2m, .y = point 2m+1
+  float gs0[4], gs1[4];
+  bool valid0, valid1;
 };
+// fp32 pair -> bf16x2 hi word (low half = first point) and bf16x2 word of the residuals
+__device__ __forceinline__ void split_pair_bf16(float2 v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
+  const float rx = v.x - __uint_as_float(hi << 16), ry = v.y - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
+}
 
 // Round 2: the 64-point tiles are filled and consumed as two 32-point halves (K-steps 0-1 / 2-3 of the same SWIZZLE_128B rows), each
 // with its own ready / done barrier pair: the eight fill warps convert half h+1 while the issuer warp's MMAs read half h, and every
@@ -175,69 +219,98 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
     const int e = warp;                                  // feature eighth: h 32e.., gamma 8e.., s0 units 16e..
     float gb2_acc[4] = {0.f, 0.f, 0.f, 0.f};
     // h / s0 (and gamma when the forward pass saved it) arrive in the blocked layout (internal.h: sem_saves_blocked): the half is
-    // one group of 32 points, a feature's 32 values are one 128-byte line -> every load instruction of the warp is one line
+    // one group of 32 points and a feature's 32 values are one 128-byte line.  Lanes 0-15 read point pairs of feature f, lanes
+    // 16-31 of feature f+1: every load instruction of the warp covers two whole lines.
+    const int m = lane & 15, fb = lane >> 4;             // point pair, feature parity
     auto load = [&](SemLoads& L, long long it) {
       const long long grp = blockIdx.x + it * gridDim.x;
-      const long long p = grp * kHalfPts + lane;
-      L.valid = p < P.P;
+      const long long p = grp * kHalfPts + 2 * m;
+      const bool v0 = p < P.P, v1 = p + 1 < P.P;
+      L.valid0 = v0; L.valid1 = v1;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) L.gs[c] = (L.valid && c < P.sem_dim) ? __ldg(&P.g_raw[p * P.C + 4 + c]) : 0.f;
-      const float* hb = P.h + (grp * 256 + e * 32) * kHalfPts + lane;
-#pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) L.hv[g8][i] = L.valid ? __ldg(hb + (8 * g8 + i) * kHalfPts) : 0.f;
-      if (P.enc_blocked) {
-        const float* eb = P.enc + (grp * P.enc_ld + e * 8) * kHalfPts + lane;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) L.ev[i] = (L.valid && P.sem_coord) ? __ldg(eb + i * kHalfPts) : 0.f;
-      } else {
-        load8(P.enc + p * P.enc_ld + e * 8, L.valid && P.sem_coord, L.ev);
+      for (int c = 0; c < 4; ++c) {
+        L.gs0[c] = (v0 && c < P.sem_dim) ? __ldg(&P.g_raw[p * P.C + 4 + c]) : 0.f;
+        L.gs1[c] = (v1 && c < P.sem_dim) ? __ldg(&P.g_raw[(p + 1) * P.C + 4 + c]) : 0.f;
       }
-      const float* sb = P.s0 + (grp * 128 + e * 16) * kHalfPts + lane;
+      // both points or none: groups are whole inside the buffers
+#define NSOS_LD2(X, Y, PTR)                                                              \
+  {                                                                                      \
+    const float2 v_ = v0 ? __ldg(reinterpret_cast<const float2*>(PTR)) : make_float2(0.f, 0.f); \
+    X = v_.x; Y = v1 ? v_.y : 0.f;                                                       \
+  }
+      const float* hb = P.h + (grp * 256 + e * 32 + fb) * kHalfPts + 2 * m;
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
+      for (int k = 0; k < 16; ++k) NSOS_LD2(L.hx[k], L.hy[k], hb + 2 * k * kHalfPts)
+      if (!P.sem_coord) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) L.sv[k][i] = L.valid ? __ldg(sb + (8 * k + i) * kHalfPts) : 0.f;
+        for (int k = 0; k < 4; ++k) { L.ex[k] = 0.f; L.ey[k] = 0.f; }
+      } else if (P.enc_blocked) {
+        const float* eb = P.enc + (grp * P.enc_ld + e * 8 + fb) * kHalfPts + 2 * m;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) NSOS_LD2(L.ex[k], L.ey[k], eb + 2 * k * kHalfPts)
+      } else {                                           // row-major gamma (k_encode_pts, replay path)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float* er = P.enc + p * P.enc_ld + e * 8 + fb + 2 * k;
+          L.ex[k] = v0 ? __ldg(er) : 0.f; L.ey[k] = v1 ? __ldg(er + P.enc_ld) : 0.f;
+        }
+      }
+      const float* sb = P.s0 + (grp * 128 + e * 16 + fb) * kHalfPts + 2 * m;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) NSOS_LD2(L.sx[k], L.sy[k], sb + 2 * k * kHalfPts)
+#undef NSOS_LD2
     };
+    // Tile row R = 8*r8 + 2*(k & 3) + fb of a K-major SWIZZLE_128B tile; this lane's word is point pair 16*half + m:
+    // byte offset = r8*1024 + (R & 7)*128 + (((4*half + (m >> 2)) ^ (R & 7)) << 4) + (m & 3)*4
     auto fill = [&](SemLoads& L, int half, long long it) {
       // the MMAs that read this half two iterations ago have completed
       if (it >= 2) { mbar_wait(smem_u32(&sm.done[half]), (uint32_t)(((it >> 1) - 1) & 1), 710 + half); tc_fence_after(); }
-      const int wd = (kHalfPts * half + lane) >> 1;      // 32-bit word (point pair) of the tile row
-      // ---- B rows 0..255: h
+      uint32_t off[4];                                   // per (k & 3): everything of the offset except r8*1024
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) put8(sm.b[0], sm.b[1], e * 32 + 8 * g8, L.hv[g8], lane, wd);
-      // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0)
-      {
-        const int e0 = e * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (e0 + i >= P.enc_dim) L.ev[i] = 0.f;
-          if (e0 + i == 63) L.ev[i] = L.valid ? 1.f : 0.f;
-        }
-        put8(sm.b[0], sm.b[1], 256 + e0, L.ev, lane, wd);
+      for (int j = 0; j < 4; ++j) {
+        const int r7 = 2 * j + fb;
+        off[j] = (uint32_t)(r7 * 128 + (((4 * half + (m >> 2)) ^ r7) << 4) + (m & 3) * 4);
       }
-      // ---- A2 = s0^T and A = g_s0^T, units 16e..16e+15
+      auto put = [&](uint8_t* hi_tile, uint8_t* lo_tile, int r8, int k, float x, float y) {
+        uint32_t hi, lo;
+        split_pair_bf16(make_float2(x, y), hi, lo);
+        *reinterpret_cast<uint32_t*>(hi_tile + (size_t)r8 * 1024 + off[k & 3]) = hi;
+        *reinterpret_cast<uint32_t*>(lo_tile + (size_t)r8 * 1024 + off[k & 3]) = lo;
+      };
+      // ---- B rows 0..255: h (feature 32e + 2k + fb)
 #pragma unroll
-      for (int g8 = 0; g8 < 2; ++g8) {
-        const int u0 = e * 16 + 8 * g8;
-        put8(sm.a2[0], sm.a2[1], u0, L.sv[g8], lane, wd);
-        float g[8];
+      for (int k = 0; k < 16; ++k) put(sm.b[0], sm.b[1], 4 * e + (k >> 2), k, L.hx[k], L.hy[k]);
+      // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0); feature 8e + 2k + fb
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float d = 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) d = fmaf(L.gs[c], sm.w2[c * 128 + u0 + i], d);     // zero rows beyond sem_dim
-          g[i] = L.sv[g8][i] > 0.f ? d : 0.f;
-        }
-        put8(sm.a[0], sm.a[1], u0, g, lane, wd);
+      for (int k = 0; k < 4; ++k) {
+        const int f = e * 8 + 2 * k + fb;
+        float x = L.ex[k], y = L.ey[k];
+        if (f >= P.enc_dim) { x = 0.f; y = 0.f; }
+        if (f == 63) { x = L.valid0 ? 1.f : 0.f; y = L.valid1 ? 1.f : 0.f; }
+        put(sm.b[0], sm.b[1], 32 + e, k, x, y);
       }
-      // ---- B2 = g_sem^T (rows 0..7; rows >= sem_dim are zero)
+      // ---- A2 = s0^T and A = g_s0^T, unit 16e + 2k + fb
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int u = e * 16 + 2 * k + fb;
+        put(sm.a2[0], sm.a2[1], 2 * e + (k >> 2), k, L.sx[k], L.sy[k]);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                    // zero rows beyond sem_dim
+          const float wv = sm.w2[c * 128 + u];
+          d0 = fmaf(L.gs0[c], wv, d0); d1 = fmaf(L.gs1[c], wv, d1);
+        }
+        put(sm.a[0], sm.a[1], 2 * e + (k >> 2), k, L.sx[k] > 0.f ? d0 : 0.f, L.sy[k] > 0.f ? d1 : 0.f);
+      }
+      // ---- B2 = g_sem^T (rows 0..3; rows >= sem_dim are zero, rows 4..15 were cleared once)
       if (e == 7) {                                      // (warp 0 carries the MMA issue)
-        float g[8] = {L.gs[0], L.gs[1], L.gs[2], L.gs[3], 0.f, 0.f, 0.f, 0.f};
-        put8(sm.b2[0], sm.b2[1], 0, g, lane, wd);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gb2_acc[c] += L.gs[c];
+        for (int k = 0; k < 2; ++k)                     // row c = 2k + fb
+          put(sm.b2[0], sm.b2[1], 0, k, fb ? L.gs0[2 * k + 1] : L.gs0[2 * k], fb ? L.gs1[2 * k + 1] : L.gs1[2 * k]);
+        if (fb == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) gb2_acc[c] += L.gs0[c] + L.gs1[c];
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -252,32 +325,27 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
       if (it + 2 < my_n) load(L0, it + 2);
       if (it + 1 < my_n) fill(L1, 1, it + 1);
     }
-    // ---- epilogue: TMEM partial sums -> global gradients (atomics; every CTA contributes)
+    // ---- epilogue: TMEM partial sums -> this CTA's slice of the scratch buffer, column-major (one line per warp store):
+    // cols 0..318 dW0, 319 db0, 320..323 dW2^T, 324..327 db2 (row 0)
     mbar_wait(smem_u32(&sm.done[(my_n - 1) & 1]), (uint32_t)(((my_n - 1) >> 1) & 1), 720);     // the last commit covers every earlier MMA
     tc_fence_after();
     const int q4 = warp & 3, hf = warp >> 2;
     const int u = q4 * 32 + lane;
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
-    const int nfeat = P.sem_coord ? 256 + P.enc_dim : 256;
+    float* part = P.part + (size_t)blockIdx.x * kPartFloatsPerCta + u;
     for (int c = hf * 10; c < hf * 10 + 10; ++c) {
       uint32_t r[16];
       tmem_ld16(tm_lane + kColD1 + c * 16, r);
       tmem_wait_ld_fence16(r);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int f = c * 16 + j;
-        const float x = __uint_as_float(r[j]);
-        if (f < nfeat) atomicAdd(&P.gW0[(size_t)u * P.ld0 + f], x);
-        else if (f == 319) atomicAdd(&P.gb0[u], x);
-      }
+      for (int j = 0; j < 16; ++j) part[(size_t)(c * 16 + j) * kPartRows] = __uint_as_float(r[j]);
     }
     if (hf == 1) {
       uint32_t r[16];
       tmem_ld16(tm_lane + kColD2, r);
       tmem_wait_ld_fence16(r);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < P.sem_dim) atomicAdd(&P.gW2[c * 128 + u], __uint_as_float(r[c]));
+      for (int c = 0; c < 4; ++c) part[(size_t)(320 + c) * kPartRows] = __uint_as_float(r[c]);
     }
     if (e == 7) {
 #pragma unroll
@@ -285,7 +353,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
         float s = gb2_acc[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && c < P.sem_dim) atomicAdd(&P.gb2[c], s);
+        if (lane == 0) P.part[(size_t)blockIdx.x * kPartFloatsPerCta + (size_t)(324 + c) * kPartRows] = s;
       }
     }
   }
@@ -306,6 +374,7 @@ struct WgGenParams {
   const float* aux; long long ld_aux; int aux_w, aux_col;  // may be null; aux_w <= 64
   float* dW; long long ldw;
   float* db;                 // optional: db[Mo] += sum_p dY[p, :]  (a constant-one feature in aux row 63; needs aux_w <= 63)
+  float* part;               // [gridDim.y][gridDim.x][kPartCols][128] partial sums (k_wgrad_reduce)
   long long P;
 };
 struct WgGenSmem {
@@ -418,26 +487,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen(const __grid_consta
       tc_fence_before();
       mbar_arrive(smem_u32(sm.ready));
     }
-    // ---- epilogue: TMEM partial sums -> global gradients (atomics; every CTA contributes)
+    // ---- epilogue: TMEM partial sums -> this CTA's slice of the scratch buffer (column-major; rows >= Mo - m0 are never read)
     mbar_wait(smem_u32(sm.done), (uint32_t)((my_slabs - 1) & 1), 750);
     tc_fence_after();
     const int q4 = warp & 3, hf = warp >> 2;
-    const int u = m0 + q4 * 32 + lane;
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
     for (int c = hf * 10; c < hf * 10 + 10; ++c) {
       if (c < 16 ? !has_main : !has_aux) continue;
       uint32_t r[16];
       tmem_ld16(tm_lane + kColD1 + c * 16, r);
       tmem_wait_ld_fence16(r);
-      if (u >= P.Mo) continue;
+      float* part = P.part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kPartFloatsPerCta + (q4 * 32 + lane);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int f = c * 16 + j;
-        const float x = __uint_as_float(r[j]);
-        if (f < 256) atomicAdd(&P.dW[(size_t)u * P.ldw + P.main_col + f], x);
-        else if (f - 256 < P.aux_w) atomicAdd(&P.dW[(size_t)u * P.ldw + P.aux_col + (f - 256)], x);
-        else if (f == 319 && P.db) atomicAdd(&P.db[u], x);
-      }
+      for (int j = 0; j < 16; ++j) part[(size_t)(c * 16 + j) * kPartRows] = __uint_as_float(r[j]);
     }
   }
   tc_fence_before();
@@ -457,9 +519,12 @@ bool tc_sem_wgrad_supported(const NetGeom& g) {
 // h (256 features) and s0 (128, post-ReLU) in the BLOCKED layout (sem_saves_blocked), starting at a multiple of 32 points;
 // enc = gamma(x), 64 features, only read with sem_with_coord: blocked (enc_blocked) or row-major [P,enc_ld]; g_raw [P,C] row-major
 // (sem gradients in columns 4..).  Accumulates into the flat gradient buffer `grads` (layout of nsos_param_layout).
+size_t tc_wgrad_part_bytes() { return sizeof(float) * kPartMaxCtas * kPartFloatsPerCta; }     // 27.5 MB
+
 int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* h, const float* enc, int enc_ld, int enc_blocked,
-                 const float* s0, const float* g_raw, int64_t P, cudaStream_t st) {
+                 const float* s0, const float* g_raw, int64_t P, void* part, size_t part_bytes, cudaStream_t st) {
   NSOS_REQUIRE(tc_sem_wgrad_supported(g), NSOS_ERR_UNSUPPORTED, "semantic-head wgrad kernel needs W=256, sem_dim<=4");
+  NSOS_REQUIRE(part && part_bytes >= tc_wgrad_part_bytes(), NSOS_ERR_WORKSPACE, "tc_sem_wgrad: partial-sum scratch too small");
   if (P <= 0) return NSOS_OK;
   WgParams p;
   memset(&p, 0, sizeof(p));
@@ -470,10 +535,20 @@ int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* 
   NSOS_CHECK_CUDA(cudaGetDevice(&dev));
   NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long nhalf = (P + kHalfPts - 1) / kHalfPts;
-  const int grid = (int)std::min<long long>(nhalf, sms);
+  const int grid = (int)std::min<long long>(nhalf, std::min(sms, kPartMaxCtas));
   const size_t need = wg_carve(nullptr, nullptr) + 1024;
+  p.part = (float*)part;
   NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_sem_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   k_sem_wgrad<<<grid, kSemThreads, need, st>>>(p);
+  WgReduceParams r;
+  memset(&r, 0, sizeof(r));
+  r.part = p.part; r.ncta = grid;
+  const int nfeat = g.sem_coord ? 256 + g.enc : 256;
+  r.seg[0][0] = WgSeg{0, nfeat, 128, p.gW0, (long long)p.ld0, 1};
+  r.seg[0][1] = WgSeg{319, 320, 128, p.gb0, 1, 0};
+  r.seg[0][2] = WgSeg{320, 320 + g.sem_dim, 128, p.gW2, 1, 128};
+  r.seg[0][3] = WgSeg{324, 324 + g.sem_dim, 1, p.gb2, 0, 1};
+  k_wgrad_reduce<<<dim3((kPartCols * kPartRows + 255) / 256, 1), 256, 0, st>>>(r);
   NSOS_CHECK_CUDA(cudaGetLastError());
   return NSOS_OK;
 }
@@ -487,8 +562,9 @@ bool tc_wgrad_gen_supported(int Mo, int64_t ldy, int main_w, int64_t ld_main, in
          (main_w > 0 || aux_w > 0);
 }
 int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_t ld_main, int main_col, const float* aux, int64_t ld_aux,
-                 int aux_w, int aux_col, float* dW, int64_t ldw, float* db, int64_t P, cudaStream_t st) {
+                 int aux_w, int aux_col, float* dW, int64_t ldw, float* db, int64_t P, void* part, size_t part_bytes, cudaStream_t st) {
   NSOS_REQUIRE(tc_wgrad_gen_supported(Mo, ldy, main ? 256 : 0, ld_main, aux ? aux_w : 0), NSOS_ERR_UNSUPPORTED, "tc_wgrad_gen: unsupported shape");
+  NSOS_REQUIRE(part && part_bytes >= tc_wgrad_part_bytes(), NSOS_ERR_WORKSPACE, "tc_wgrad_gen: partial-sum scratch too small");
   if (P <= 0) return NSOS_OK;
   WgGenParams p;
   memset(&p, 0, sizeof(p));
@@ -501,10 +577,23 @@ int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_
   NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long nslabs = (P + kSlabPts - 1) / kSlabPts;
   const int mb = Mo / 128;
-  const int gx = (int)std::min<long long>(nslabs, std::max(1, sms / mb));
+  const int gx = (int)std::min<long long>(nslabs, std::max(1, std::min(sms, kPartMaxCtas) / mb));
   const size_t need = wgg_carve(nullptr, nullptr) + 1024;
+  p.part = (float*)part;
+  NSOS_REQUIRE(mb >= 1 && mb <= 2, NSOS_ERR_UNSUPPORTED, "tc_wgrad_gen: at most 256 output rows");
   NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   k_wgrad_gen<<<dim3(gx, mb), kWgThreads, need, st>>>(p);
+  WgReduceParams r;
+  memset(&r, 0, sizeof(r));
+  r.part = p.part; r.ncta = gx;
+  for (int y = 0; y < mb; ++y) {
+    const int rows = std::min(128, Mo - 128 * y);
+    float* dwy = dW + (size_t)128 * y * ldw;
+    if (main) r.seg[y][0] = WgSeg{0, 256, rows, dwy + main_col, (long long)ldw, 1};
+    if (p.aux_w > 0) r.seg[y][1] = WgSeg{256, 256 + p.aux_w, rows, dwy + aux_col, (long long)ldw, 1};
+    if (p.db) r.seg[y][2] = WgSeg{319, 320, rows, p.db + 128 * y, 1, 0};
+  }
+  k_wgrad_reduce<<<dim3((kPartCols * kPartRows + 255) / 256, mb), 256, 0, st>>>(r);
   NSOS_CHECK_CUDA(cudaGetLastError());
   return NSOS_OK;
 }

@@ -601,8 +601,9 @@ def test_wgrad_building_block(Mo, main, aux_w, P):
     aux_col, main_col = 2, 2 + aux_w
     db = torch.randn(Mo, generator=g).to(DEV)
     db0 = db.clone()
+    scr = torch.empty(L.nsos_selftest_wgrad_scratch_bytes(), dtype=torch.uint8, device=DEV)     # per-CTA partial sums
     _lib.check(L.nsos_selftest_wgrad(_lib.ptr(dy), Mo, Mo, _lib.ptr(x), 256, main_col, _lib.ptr(e), 64, aux_w, aux_col, _lib.ptr(dw), ldw,
-                                     _lib.ptr(db), P, None), "wgrad")
+                                     _lib.ptr(db), P, _lib.ptr(scr), scr.numel(), None), "wgrad")
     torch.cuda.synchronize()
     refb = db0.double() + dy.double().sum(0)                               # bias gradient from the constant-one feature
     assert (db.double() - refb).abs().max().item() <= 3e-5 * refb.abs().max().item()
