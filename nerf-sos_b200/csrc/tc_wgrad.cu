@@ -31,8 +31,9 @@ namespace {
 using namespace ptx;
 
 constexpr int kWgWorkers = 256, kWgThreads = 288, kWgMmaWarp = 8;   // k_wgrad_gen: 8 fill warps + an issuer warp
-constexpr int kSemThreads = 256;   // k_sem_wgrad: 8 fill warps (two sets of 14 loads per lane, 255 registers); warp 0 also issues the MMAs
-                                   // (a ninth warp would cost every thread 87 registers: allocation is per 4 warps)
+constexpr int kSemWarps = 16, kSemThreads = 32 * kSemWarps;   // k_sem_wgrad: 16 fill warps (two sets of 14 loads per lane, 128 registers):
+                                   // 8 warps at 255 registers issued one instruction per 8 cycles (ncu: 75 % of cycles without an eligible warp);
+                                   // the warp that completes a half also issues its MMAs
 constexpr int kHalfPts = 32;                       // points per fill / MMA unit: half of a 64-point tile
 constexpr int kSlabPts = 64;
 constexpr int kRowsA = 128, kRowsB = 320, kRowsB2 = 16;
@@ -80,13 +81,15 @@ struct WgParams {
   float* part;       // [gridDim.x][kPartCols][128] partial sums of this launch (k_wgrad_reduce adds them to the gradients)
   long long P;
   int C, enc_dim, enc_ld, sem_dim, sem_coord, ld0;
+  int trace;         // NSOS_WG_TRACE=1: CTA 0 prints a timeline of its first halves (debug)
   int enc_blocked;   // gamma rows: blocked like h / s0 (saved by the training forward) or row-major with pitch enc_ld (k_encode_pts)
 };
 
 struct WgSmem {
   uint8_t *a[2], *a2[2], *b[2], *b2[2];   // [plane]: 0 = hi, 1 = lo
   float* w2;                              // [4][128]
-  uint64_t *ready, *done;                 // [2] each: one pair per tile half
+  uint64_t *ready, *done;                 // [2] each: one pair per tile half (k_sem_wgrad counts arrivals in `cnt` instead of ready)
+  uint32_t* cnt;                          // [2] fill warps that have finished the half
   uint32_t* tmem_ptr;
 };
 __host__ __device__ inline size_t wg_carve(uint8_t* base, WgSmem* s) {
@@ -97,10 +100,10 @@ __host__ __device__ inline size_t wg_carve(uint8_t* base, WgSmem* s) {
   for (int p = 0; p < 2; ++p) oa2[p] = take(kRowsA * 128, 1024);
   for (int p = 0; p < 2; ++p) ob[p] = take(kRowsB * 128, 1024);
   for (int p = 0; p < 2; ++p) ob2[p] = take(kRowsB2 * 128, 1024);
-  size_t ow = take(sizeof(float) * 4 * 128, 16), obar = take(32, 8), otp = take(16, 16);
+  size_t ow = take(sizeof(float) * 4 * 128, 16), obar = take(32, 8), otp = take(16, 16), ocnt = take(8, 8);
   if (s) {
     for (int p = 0; p < 2; ++p) { s->a[p] = base + oa[p]; s->a2[p] = base + oa2[p]; s->b[p] = base + ob[p]; s->b2[p] = base + ob2[p]; }
-    s->w2 = (float*)(base + ow); s->ready = (uint64_t*)(base + obar); s->done = s->ready + 2; s->tmem_ptr = (uint32_t*)(base + otp);
+    s->w2 = (float*)(base + ow); s->ready = (uint64_t*)(base + obar); s->done = s->ready + 2; s->tmem_ptr = (uint32_t*)(base + otp); s->cnt = (uint32_t*)(base + ocnt);
   }
   return off;
 }
@@ -145,11 +148,12 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, bool valid,
   }
 }
 
+constexpr int kSemH = 128 / kSemWarps, kSemE = 32 / kSemWarps, kSemS = 64 / kSemWarps;   // loads per lane: h, gamma, s0 (2 features per instruction)
 // One lane's share of a 32-point half slab: TWO neighbouring points (2m, 2m+1; m = lane & 15) of the features
-// f = base + 2k + (lane >> 4): 16 h features, 4 gamma features, 8 s0 units of fill warp e (28 independent 8-byte loads), and the
+// f = base + 2k + (lane >> 4): 256/NW h features, 64/NW gamma features, 128/NW s0 units of fill warp e (14 independent 8-byte loads), and the
 // two points' semantic-logit gradients.  A neighbouring pair is one 32-bit word of a K-major bf16 tile row: no shuffles.
 struct SemLoads {
-  float hx[16], hy[16], ex[4], ey[4], sx[8], sy[8];     // .x = point 2m, .y = point 2m+1
+  float hx[kSemH], hy[kSemH], ex[kSemE], ey[kSemE], sx[kSemS], sy[kSemS];     // .x = point 2m, .y = point 2m+1
   float gs0[4], gs1[4];
   bool valid0, valid1;
 };
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
   const long long nhalf = (P.P + kHalfPts - 1) / kHalfPts;
   const long long my_n = (nhalf - blockIdx.x + gridDim.x - 1) / gridDim.x;     // >= 1 (grid <= nhalf)
   if (t == 0) {
-    for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(&sm.ready[h]), kWgWorkers); mbar_init(smem_u32(&sm.done[h]), 1); }
+    for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(&sm.done[h]), 1); sm.cnt[h] = 0u; }
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
@@ -188,15 +192,17 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *sm.tmem_ptr;
+  __shared__ long long tr[4][24];      // [issue begin, issue end, warp-0 done-wait begin, end][half]
+  const bool trace = P.trace && blockIdx.x == 0;
 
   const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, a2[2] = {smem_u32(sm.a2[0]), smem_u32(sm.a2[1])};
   const uint32_t b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])}, b2[2] = {smem_u32(sm.b2[0]), smem_u32(sm.b2[1])};
   const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64), id16 = make_idesc_bf16(16);
-  // 3 x 2 x 3 MMAs per half (hi.hi, lo.hi, hi.lo; M=128, N=256/64/16, K=16), issued by warp 0 once all 256 threads have arrived
+  // 3 x 2 x 3 MMAs per half (hi.hi, lo.hi, hi.lo; M=128, N=256/64/16, K=16), issued by the warp that finished the half last
   auto issue = [&](int half, long long it) {
-    mbar_wait(smem_u32(&sm.ready[half]), (uint32_t)((it >> 1) & 1), 700 + half);
     tc_fence_after();
     if (elect_one()) {
+      if (trace && it < 24) tr[0][it] = clock64();
 #pragma unroll
       for (int pass = 0; pass < 3; ++pass) {
         const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;     // hi.hi, lo.hi, hi.lo
@@ -211,6 +217,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
         }
       }
       umma_commit(smem_u32(&sm.done[half]));
+      if (trace && it < 24) tr[1][it] = clock64();
     }
     __syncwarp();
   };
@@ -227,95 +234,112 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
       const long long p = grp * kHalfPts + 2 * m;
       const bool v0 = p < P.P, v1 = p + 1 < P.P;
       L.valid0 = v0; L.valid1 = v1;
+      // NOTHING here may consume a loaded value (a warp issues in order: one dependent select behind every load serialises the
+      // loads -- that, not bandwidth, held rounds 1-2 of this kernel at 2 TB/s): predicated loads into zeroed registers; the odd
+      // tail point (valid0 && !valid1, last pair of an odd point count) is masked when the values are used
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        L.gs0[c] = (v0 && c < P.sem_dim) ? __ldg(&P.g_raw[p * P.C + 4 + c]) : 0.f;
-        L.gs1[c] = (v1 && c < P.sem_dim) ? __ldg(&P.g_raw[(p + 1) * P.C + 4 + c]) : 0.f;
+        L.gs0[c] = 0.f; L.gs1[c] = 0.f;
+        if (v0 && c < P.sem_dim) L.gs0[c] = __ldg(&P.g_raw[p * P.C + 4 + c]);
+        if (v1 && c < P.sem_dim) L.gs1[c] = __ldg(&P.g_raw[(p + 1) * P.C + 4 + c]);
       }
       // both points or none: groups are whole inside the buffers
 #define NSOS_LD2(X, Y, PTR)                                                              \
   {                                                                                      \
-    const float2 v_ = v0 ? __ldg(reinterpret_cast<const float2*>(PTR)) : make_float2(0.f, 0.f); \
-    X = v_.x; Y = v1 ? v_.y : 0.f;                                                       \
+    float2 v_ = make_float2(0.f, 0.f);                                                   \
+    if (v0) v_ = __ldg(reinterpret_cast<const float2*>(PTR));                            \
+    X = v_.x; Y = v_.y;                                                                  \
   }
-      const float* hb = P.h + (grp * 256 + e * 32 + fb) * kHalfPts + 2 * m;
+      const float* hb = P.h + (grp * 256 + e * (2 * kSemH) + fb) * kHalfPts + 2 * m;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) NSOS_LD2(L.hx[k], L.hy[k], hb + 2 * k * kHalfPts)
+      for (int k = 0; k < kSemH; ++k) NSOS_LD2(L.hx[k], L.hy[k], hb + 2 * k * kHalfPts)
       if (!P.sem_coord) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { L.ex[k] = 0.f; L.ey[k] = 0.f; }
+        for (int k = 0; k < kSemE; ++k) { L.ex[k] = 0.f; L.ey[k] = 0.f; }
       } else if (P.enc_blocked) {
-        const float* eb = P.enc + (grp * P.enc_ld + e * 8 + fb) * kHalfPts + 2 * m;
+        const float* eb = P.enc + (grp * P.enc_ld + e * (2 * kSemE) + fb) * kHalfPts + 2 * m;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) NSOS_LD2(L.ex[k], L.ey[k], eb + 2 * k * kHalfPts)
+        for (int k = 0; k < kSemE; ++k) NSOS_LD2(L.ex[k], L.ey[k], eb + 2 * k * kHalfPts)
       } else {                                           // row-major gamma (k_encode_pts, replay path)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float* er = P.enc + p * P.enc_ld + e * 8 + fb + 2 * k;
-          L.ex[k] = v0 ? __ldg(er) : 0.f; L.ey[k] = v1 ? __ldg(er + P.enc_ld) : 0.f;
+        for (int k = 0; k < kSemE; ++k) {
+          const float* er = P.enc + p * P.enc_ld + e * (2 * kSemE) + fb + 2 * k;
+          L.ex[k] = 0.f; L.ey[k] = 0.f;
+          if (v0) L.ex[k] = __ldg(er);
+          if (v1) L.ey[k] = __ldg(er + P.enc_ld);
         }
       }
-      const float* sb = P.s0 + (grp * 128 + e * 16 + fb) * kHalfPts + 2 * m;
+      const float* sb = P.s0 + (grp * 128 + e * (2 * kSemS) + fb) * kHalfPts + 2 * m;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) NSOS_LD2(L.sx[k], L.sy[k], sb + 2 * k * kHalfPts)
+      for (int k = 0; k < kSemS; ++k) NSOS_LD2(L.sx[k], L.sy[k], sb + 2 * k * kHalfPts)
 #undef NSOS_LD2
     };
     // Tile row R = 8*r8 + 2*(k & 3) + fb of a K-major SWIZZLE_128B tile; this lane's word is point pair 16*half + m:
     // byte offset = r8*1024 + (R & 7)*128 + (((4*half + (m >> 2)) ^ (R & 7)) << 4) + (m & 3)*4
     auto fill = [&](SemLoads& L, int half, long long it) {
       // the MMAs that read this half two iterations ago have completed
+      if (trace && t == 0 && it < 24) tr[2][it] = clock64();
       if (it >= 2) { mbar_wait(smem_u32(&sm.done[half]), (uint32_t)(((it >> 1) - 1) & 1), 710 + half); tc_fence_after(); }
-      uint32_t off[4];                                   // per (k & 3): everything of the offset except r8*1024
+      if (trace && t == 0 && it < 24) tr[3][it] = clock64();
+      const int xk = 4 * half + (m >> 2);               // 16-byte chunk of this lane's word before the swizzle
+      auto offs = [&](int r7) { return (uint32_t)(r7 * 128 + ((xk ^ r7) << 4) + (m & 3) * 4); };
+      uint32_t off[4];                                   // per (k & 3), rows 2*(k & 3) + fb: everything of the offset except r8*1024
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r7 = 2 * j + fb;
-        off[j] = (uint32_t)(r7 * 128 + (((4 * half + (m >> 2)) ^ r7) << 4) + (m & 3) * 4);
-      }
-      auto put = [&](uint8_t* hi_tile, uint8_t* lo_tile, int r8, int k, float x, float y) {
+      for (int j = 0; j < 4; ++j) off[j] = offs(2 * j + fb);
+      const bool v1 = L.valid1;
+      auto put = [&](uint8_t* hi_tile, uint8_t* lo_tile, int r8, uint32_t o, float x, float y) {
         uint32_t hi, lo;
-        split_pair_bf16(make_float2(x, y), hi, lo);
-        *reinterpret_cast<uint32_t*>(hi_tile + (size_t)r8 * 1024 + off[k & 3]) = hi;
-        *reinterpret_cast<uint32_t*>(lo_tile + (size_t)r8 * 1024 + off[k & 3]) = lo;
+        split_pair_bf16(make_float2(x, v1 ? y : 0.f), hi, lo);          // (odd tail point: its slot in the padded group holds garbage)
+        *reinterpret_cast<uint32_t*>(hi_tile + (size_t)r8 * 1024 + o) = hi;
+        *reinterpret_cast<uint32_t*>(lo_tile + (size_t)r8 * 1024 + o) = lo;
       };
-      // ---- B rows 0..255: h (feature 32e + 2k + fb)
+      // ---- B rows 0..255: h (feature 2*kSemH*e + 2k + fb)
 #pragma unroll
-      for (int k = 0; k < 16; ++k) put(sm.b[0], sm.b[1], 4 * e + (k >> 2), k, L.hx[k], L.hy[k]);
-      // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0); feature 8e + 2k + fb
+      for (int k = 0; k < kSemH; ++k) put(sm.b[0], sm.b[1], (2 * kSemH / 8) * e + (k >> 2), off[k & 3], L.hx[k], L.hy[k]);
+      // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0); feature 2*kSemE*e + 2k + fb
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int f = e * 8 + 2 * k + fb;
+      for (int k = 0; k < kSemE; ++k) {
+        const int f = e * (2 * kSemE) + 2 * k + fb;
         float x = L.ex[k], y = L.ey[k];
         if (f >= P.enc_dim) { x = 0.f; y = 0.f; }
         if (f == 63) { x = L.valid0 ? 1.f : 0.f; y = L.valid1 ? 1.f : 0.f; }
-        put(sm.b[0], sm.b[1], 32 + e, k, x, y);
+        put(sm.b[0], sm.b[1], 32 + (f >> 3), offs(f & 7), x, y);
       }
-      // ---- A2 = s0^T and A = g_s0^T, unit 16e + 2k + fb
+      // ---- A2 = s0^T and A = g_s0^T, unit 2*kSemS*e + 2k + fb
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int u = e * 16 + 2 * k + fb;
-        put(sm.a2[0], sm.a2[1], 2 * e + (k >> 2), k, L.sx[k], L.sy[k]);
+      for (int k = 0; k < kSemS; ++k) {
+        const int u = e * (2 * kSemS) + 2 * k + fb, r8 = (2 * kSemS / 8) * e + (k >> 2);
+        put(sm.a2[0], sm.a2[1], r8, off[k & 3], L.sx[k], L.sy[k]);
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                    // zero rows beyond sem_dim
           const float wv = sm.w2[c * 128 + u];
           d0 = fmaf(L.gs0[c], wv, d0); d1 = fmaf(L.gs1[c], wv, d1);
         }
-        put(sm.a[0], sm.a[1], 2 * e + (k >> 2), k, L.sx[k] > 0.f ? d0 : 0.f, L.sy[k] > 0.f ? d1 : 0.f);
+        put(sm.a[0], sm.a[1], r8, off[k & 3], L.sx[k] > 0.f ? d0 : 0.f, (v1 && L.sy[k] > 0.f) ? d1 : 0.f);
       }
       // ---- B2 = g_sem^T (rows 0..3; rows >= sem_dim are zero, rows 4..15 were cleared once)
-      if (e == 7) {                                      // (warp 0 carries the MMA issue)
+      if (e == kSemWarps - 1) {
 #pragma unroll
         for (int k = 0; k < 2; ++k)                     // row c = 2k + fb
-          put(sm.b2[0], sm.b2[1], 0, k, fb ? L.gs0[2 * k + 1] : L.gs0[2 * k], fb ? L.gs1[2 * k + 1] : L.gs1[2 * k]);
+          put(sm.b2[0], sm.b2[1], 0, off[k], fb ? L.gs0[2 * k + 1] : L.gs0[2 * k], fb ? L.gs1[2 * k + 1] : L.gs1[2 * k]);
         if (fb == 0) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) gb2_acc[c] += L.gs0[c] + L.gs1[c];
         }
       }
+      // ---- the warp whose arrival completes the half issues its MMAs: nobody waits for a designated issuer
       fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&sm.ready[half]));
-      if (warp == 0) issue(half, it);
+      __syncwarp();
+      uint32_t last = 0;
+      if (lane == 0) {
+        uint32_t old;
+        asm volatile("atom.shared.acq_rel.cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&sm.cnt[half])) : "memory");
+        last = (old == (uint32_t)(kSemWarps - 1)) ? 1u : 0u;
+        if (last) sm.cnt[half] = 0u;                    // next use: two halves on, after done[half]
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) { tc_fence_before(); issue(half, it); }
     };
     SemLoads L0, L1;
     load(L0, 0);
@@ -329,25 +353,26 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
     // cols 0..318 dW0, 319 db0, 320..323 dW2^T, 324..327 db2 (row 0)
     mbar_wait(smem_u32(&sm.done[(my_n - 1) & 1]), (uint32_t)(((my_n - 1) >> 1) & 1), 720);     // the last commit covers every earlier MMA
     tc_fence_after();
+    constexpr int kColShare = 20 / (kSemWarps / 4);     // D1 chunks (16 columns) per warp of a lane quarter
     const int q4 = warp & 3, hf = warp >> 2;
     const int u = q4 * 32 + lane;
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
     float* part = P.part + (size_t)blockIdx.x * kPartFloatsPerCta + u;
-    for (int c = hf * 10; c < hf * 10 + 10; ++c) {
+    for (int c = hf * kColShare; c < hf * kColShare + kColShare; ++c) {
       uint32_t r[16];
       tmem_ld16(tm_lane + kColD1 + c * 16, r);
       tmem_wait_ld_fence16(r);
 #pragma unroll
       for (int j = 0; j < 16; ++j) part[(size_t)(c * 16 + j) * kPartRows] = __uint_as_float(r[j]);
     }
-    if (hf == 1) {
+    if (hf == kSemWarps / 4 - 1) {
       uint32_t r[16];
       tmem_ld16(tm_lane + kColD2, r);
       tmem_wait_ld_fence16(r);
 #pragma unroll
       for (int c = 0; c < 4; ++c) part[(size_t)(320 + c) * kPartRows] = __uint_as_float(r[c]);
     }
-    if (e == 7) {
+    if (e == kSemWarps - 1) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float s = gb2_acc[c];
@@ -359,6 +384,10 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (trace && t == 0)
+    for (int i = 0; i < 24 && i < my_n; ++i)
+      printf("[wg] half %2d: fill starts %7lld, done(it-2) seen %7lld, issue %7lld .. %7lld\n", i, tr[2][i] - tr[2][0], tr[3][i] - tr[2][0],
+             tr[0][i] - tr[2][0], tr[1][i] - tr[2][0]);
   if (warp == 0) tmem_dealloc(tm, kWgTmemCols);
 }
 
@@ -538,6 +567,7 @@ int tc_sem_wgrad(const NetGeom& g, const float* prm, float* grads, const float* 
   const int grid = (int)std::min<long long>(nhalf, std::min(sms, kPartMaxCtas));
   const size_t need = wg_carve(nullptr, nullptr) + 1024;
   p.part = (float*)part;
+  if (const char* e = getenv("NSOS_WG_TRACE")) p.trace = atoi(e);
   NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_sem_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   k_sem_wgrad<<<grid, kSemThreads, need, st>>>(p);
   WgReduceParams r;
