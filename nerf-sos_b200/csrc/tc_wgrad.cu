@@ -150,7 +150,8 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, bool valid,
 
 constexpr int kSemH = 128 / kSemWarps, kSemE = 32 / kSemWarps, kSemS = 64 / kSemWarps;   // loads per lane: h, gamma, s0 (2 features per instruction)
 // One lane's share of a 32-point half slab: TWO neighbouring points (2m, 2m+1; m = lane & 15) of the features
-// f = base + 2k + (lane >> 4): 256/NW h features, 64/NW gamma features, 128/NW s0 units of fill warp e (14 independent 8-byte loads), and the
+// f = base + 8*(k >> 2) + (k & 3) + 4*(lane >> 4) (h, s0; gamma: base + 2k + (lane >> 4)): 256/NW h features, 64/NW gamma features,
+// 128/NW s0 units of fill warp e (14 independent 8-byte loads), and the
 // two points' semantic-logit gradients.  A neighbouring pair is one 32-bit word of a K-major bf16 tile row: no shuffles.
 struct SemLoads {
   float hx[kSemH], hy[kSemH], ex[kSemE], ey[kSemE], sx[kSemS], sy[kSemS];     // .x = point 2m, .y = point 2m+1
@@ -250,9 +251,10 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
     if (v0) v_ = __ldg(reinterpret_cast<const float2*>(PTR));                            \
     X = v_.x; Y = v_.y;                                                                  \
   }
-      const float* hb = P.h + (grp * 256 + e * (2 * kSemH) + fb) * kHalfPts + 2 * m;
+      // lanes 16-31 take the feature FOUR rows further: tile rows r and r+4 sit in different bank halves (conflict-free stores)
+      const float* hb = P.h + (grp * 256 + e * (2 * kSemH) + 4 * fb) * kHalfPts + 2 * m;
 #pragma unroll
-      for (int k = 0; k < kSemH; ++k) NSOS_LD2(L.hx[k], L.hy[k], hb + 2 * k * kHalfPts)
+      for (int k = 0; k < kSemH; ++k) NSOS_LD2(L.hx[k], L.hy[k], hb + (8 * (k >> 2) + (k & 3)) * kHalfPts)
       if (!P.sem_coord) {
 #pragma unroll
         for (int k = 0; k < kSemE; ++k) { L.ex[k] = 0.f; L.ey[k] = 0.f; }
@@ -269,9 +271,9 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
           if (v1) L.ey[k] = __ldg(er + P.enc_ld);
         }
       }
-      const float* sb = P.s0 + (grp * 128 + e * (2 * kSemS) + fb) * kHalfPts + 2 * m;
+      const float* sb = P.s0 + (grp * 128 + e * (2 * kSemS) + 4 * fb) * kHalfPts + 2 * m;
 #pragma unroll
-      for (int k = 0; k < kSemS; ++k) NSOS_LD2(L.sx[k], L.sy[k], sb + 2 * k * kHalfPts)
+      for (int k = 0; k < kSemS; ++k) NSOS_LD2(L.sx[k], L.sy[k], sb + (8 * (k >> 2) + (k & 3)) * kHalfPts)
 #undef NSOS_LD2
     };
     // Tile row R = 8*r8 + 2*(k & 3) + fb of a K-major SWIZZLE_128B tile; this lane's word is point pair 16*half + m:
@@ -279,13 +281,20 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
     auto fill = [&](SemLoads& L, int half, long long it) {
       // the MMAs that read this half two iterations ago have completed
       if (trace && t == 0 && it < 24) tr[2][it] = clock64();
-      if (it >= 2) { mbar_wait(smem_u32(&sm.done[half]), (uint32_t)(((it >> 1) - 1) & 1), 710 + half); tc_fence_after(); }
+      if (it >= 2) {                                     // (polling warps back off: they share schedulers with the warps still converting)
+        const uint32_t bar = smem_u32(&sm.done[half]), par = (uint32_t)(((it >> 1) - 1) & 1);
+        for (uint32_t spins = 0; !mbar_try_wait(bar, par); ++spins) {
+          __nanosleep(40);
+          if (spins > (1u << 24)) { printf("[nerfsos] k_sem_wgrad: done[%d] timed out\n", half); __trap(); }
+        }
+        tc_fence_after();
+      }
       if (trace && t == 0 && it < 24) tr[3][it] = clock64();
       const int xk = 4 * half + (m >> 2);               // 16-byte chunk of this lane's word before the swizzle
       auto offs = [&](int r7) { return (uint32_t)(r7 * 128 + ((xk ^ r7) << 4) + (m & 3) * 4); };
-      uint32_t off[4];                                   // per (k & 3), rows 2*(k & 3) + fb: everything of the offset except r8*1024
+      uint32_t off[4];                                   // per (k & 3), rows (k & 3) + 4*fb: everything of the offset except r8*1024
 #pragma unroll
-      for (int j = 0; j < 4; ++j) off[j] = offs(2 * j + fb);
+      for (int j = 0; j < 4; ++j) off[j] = offs(j + 4 * fb);
       const bool v1 = L.valid1;
       auto put = [&](uint8_t* hi_tile, uint8_t* lo_tile, int r8, uint32_t o, float x, float y) {
         uint32_t hi, lo;
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
         *reinterpret_cast<uint32_t*>(hi_tile + (size_t)r8 * 1024 + o) = hi;
         *reinterpret_cast<uint32_t*>(lo_tile + (size_t)r8 * 1024 + o) = lo;
       };
-      // ---- B rows 0..255: h (feature 2*kSemH*e + 2k + fb)
+      // ---- B rows 0..255: h (feature 2*kSemH*e + 8*(k >> 2) + (k & 3) + 4*fb)
 #pragma unroll
       for (int k = 0; k < kSemH; ++k) put(sm.b[0], sm.b[1], (2 * kSemH / 8) * e + (k >> 2), off[k & 3], L.hx[k], L.hy[k]);
       // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0); feature 2*kSemE*e + 2k + fb
@@ -305,10 +314,10 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
         if (f == 63) { x = L.valid0 ? 1.f : 0.f; y = L.valid1 ? 1.f : 0.f; }
         put(sm.b[0], sm.b[1], 32 + (f >> 3), offs(f & 7), x, y);
       }
-      // ---- A2 = s0^T and A = g_s0^T, unit 2*kSemS*e + 2k + fb
+      // ---- A2 = s0^T and A = g_s0^T, unit 2*kSemS*e + 8*(k >> 2) + (k & 3) + 4*fb
 #pragma unroll
       for (int k = 0; k < kSemS; ++k) {
-        const int u = e * (2 * kSemS) + 2 * k + fb, r8 = (2 * kSemS / 8) * e + (k >> 2);
+        const int u = e * (2 * kSemS) + 8 * (k >> 2) + (k & 3) + 4 * fb, r8 = (2 * kSemS / 8) * e + (k >> 2);
         put(sm.a2[0], sm.a2[1], r8, off[k & 3], L.sx[k], L.sy[k]);
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
       if (e == kSemWarps - 1) {
 #pragma unroll
         for (int k = 0; k < 2; ++k)                     // row c = 2k + fb
-          put(sm.b2[0], sm.b2[1], 0, off[k], fb ? L.gs0[2 * k + 1] : L.gs0[2 * k], fb ? L.gs1[2 * k + 1] : L.gs1[2 * k]);
+          put(sm.b2[0], sm.b2[1], 0, offs(2 * k + fb), fb ? L.gs0[2 * k + 1] : L.gs0[2 * k], fb ? L.gs1[2 * k + 1] : L.gs1[2 * k]);
         if (fb == 0) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) gb2_acc[c] += L.gs0[c] + L.gs1[c];
