@@ -131,8 +131,10 @@ def render_video(model, dataset, device, save_dir, suffix="", fps=30, quality=8,
     if writer is None:
         try:
             import imageio
-            writer = imageio.mimwrite
+            writer = getattr(imageio, "mimwrite", None)            # (a stub module without it counts as absent)
         except ImportError:
+            writer = None
+        if writer is None:
             writer = lambda path, frames, **kw: np.save(os.path.splitext(path)[0] + ".npy", frames)
     os.makedirs(save_dir, exist_ok=True)
     name = lambda k: os.path.join(save_dir, f"{k}{'_' + suffix if suffix else ''}.mp4")
