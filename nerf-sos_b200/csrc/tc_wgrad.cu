@@ -296,15 +296,17 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
 #pragma unroll
       for (int j = 0; j < 4; ++j) off[j] = offs(j + 4 * fb);
       const bool v1 = L.valid1;
-      auto put = [&](uint8_t* hi_tile, uint8_t* lo_tile, int r8, uint32_t o, float x, float y) {
+      // 32-bit shared-window addresses: tile base + 8-row group + swizzled offset (generic 64-bit pointer arithmetic per store
+      // was a third of the fill's instructions)
+      auto put = [&](const uint32_t (&tile)[2], int r8, uint32_t o, float x, float y) {
         uint32_t hi, lo;
         split_pair_bf16(make_float2(x, v1 ? y : 0.f), hi, lo);          // (odd tail point: its slot in the padded group holds garbage)
-        *reinterpret_cast<uint32_t*>(hi_tile + (size_t)r8 * 1024 + o) = hi;
-        *reinterpret_cast<uint32_t*>(lo_tile + (size_t)r8 * 1024 + o) = lo;
+        st_shared_u32(tile[0] + (uint32_t)r8 * 1024u + o, hi);
+        st_shared_u32(tile[1] + (uint32_t)r8 * 1024u + o, lo);
       };
       // ---- B rows 0..255: h (feature 2*kSemH*e + 8*(k >> 2) + (k & 3) + 4*fb)
 #pragma unroll
-      for (int k = 0; k < kSemH; ++k) put(sm.b[0], sm.b[1], (2 * kSemH / 8) * e + (k >> 2), off[k & 3], L.hx[k], L.hy[k]);
+      for (int k = 0; k < kSemH; ++k) put(b, (2 * kSemH / 8) * e + (k >> 2), off[k & 3], L.hx[k], L.hy[k]);
       // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0); feature 2*kSemE*e + 2k + fb
 #pragma unroll
       for (int k = 0; k < kSemE; ++k) {
@@ -312,26 +314,26 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
         float x = L.ex[k], y = L.ey[k];
         if (f >= P.enc_dim) { x = 0.f; y = 0.f; }
         if (f == 63) { x = L.valid0 ? 1.f : 0.f; y = L.valid1 ? 1.f : 0.f; }
-        put(sm.b[0], sm.b[1], 32 + (f >> 3), offs(f & 7), x, y);
+        put(b, 32 + (f >> 3), offs(f & 7), x, y);
       }
       // ---- A2 = s0^T and A = g_s0^T, unit 2*kSemS*e + 8*(k >> 2) + (k & 3) + 4*fb
 #pragma unroll
       for (int k = 0; k < kSemS; ++k) {
         const int u = e * (2 * kSemS) + 8 * (k >> 2) + (k & 3) + 4 * fb, r8 = (2 * kSemS / 8) * e + (k >> 2);
-        put(sm.a2[0], sm.a2[1], r8, off[k & 3], L.sx[k], L.sy[k]);
+        put(a2, r8, off[k & 3], L.sx[k], L.sy[k]);
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                    // zero rows beyond sem_dim
           const float wv = sm.w2[c * 128 + u];
           d0 = fmaf(L.gs0[c], wv, d0); d1 = fmaf(L.gs1[c], wv, d1);
         }
-        put(sm.a[0], sm.a[1], r8, off[k & 3], L.sx[k] > 0.f ? d0 : 0.f, (v1 && L.sy[k] > 0.f) ? d1 : 0.f);
+        put(a, r8, off[k & 3], L.sx[k] > 0.f ? d0 : 0.f, (v1 && L.sy[k] > 0.f) ? d1 : 0.f);
       }
       // ---- B2 = g_sem^T (rows 0..3; rows >= sem_dim are zero, rows 4..15 were cleared once)
       if (e == kSemWarps - 1) {
 #pragma unroll
         for (int k = 0; k < 2; ++k)                     // row c = 2k + fb
-          put(sm.b2[0], sm.b2[1], 0, offs(2 * k + fb), fb ? L.gs0[2 * k + 1] : L.gs0[2 * k], fb ? L.gs1[2 * k + 1] : L.gs1[2 * k]);
+          put(b2, 0, offs(2 * k + fb), fb ? L.gs0[2 * k + 1] : L.gs0[2 * k], fb ? L.gs1[2 * k + 1] : L.gs1[2 * k]);
         if (fb == 0) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) gb2_acc[c] += L.gs0[c] + L.gs1[c];

@@ -30,9 +30,15 @@ from .. import parallel as P
 from ..utils.image import get_similarity_matrix, img2mse, mse2psnr
 
 
+_NORM = {}
+
+
 def normalize_batch(batch):
-    mean = batch.new_tensor([0.485, 0.456, 0.406]).view(-1, 1, 1)
-    std = batch.new_tensor([0.229, 0.224, 0.225]).view(-1, 1, 1)
+    """trainer.py:24-29 (ImageNet mean / std); the two constants live on the device once instead of two pageable host copies per step."""
+    key = (batch.device, batch.dtype)
+    if key not in _NORM:
+        _NORM[key] = (batch.new_tensor([0.485, 0.456, 0.406]).view(-1, 1, 1), batch.new_tensor([0.229, 0.224, 0.225]).view(-1, 1, 1))
+    mean, std = _NORM[key]
     return (batch - mean) / std
 
 
@@ -135,7 +141,8 @@ def train_one_step(batch, model, optimizer, scheduler, train_loader, global_step
             if coords is None:                                         # shared by all ranks: seeded with the step
                 gen = torch.Generator().manual_seed(1_000_003 * int(global_step) + 17)
                 shp = (2, 2, Bg, correlation_loss.feature_samples, correlation_loss.feature_samples, 2)
-                coords = (torch.rand(shp, generator=gen) * 2 - 1).to(device, non_blocking=True)
+                pin = torch.device(device).type == "cuda"                  # pinned source: no staging copy (the CPU tests have no driver)
+                coords = torch.rand(shp, generator=gen, pin_memory=pin).mul_(2).sub_(1).to(device, non_blocking=True)
             for i, s_all in enumerate((s0_all, s1_all)):
                 pend.append((i, correlation_loss.begin(feat_all, s_all, sim, q0, Bl, coords=(coords[i][0], coords[i][1]))))
         if use_geo:

@@ -29,10 +29,15 @@ def img2mse(x, y, reduction='mean'):
     return diff
 
 
+_LOG10 = {}
+
+
 def mse2psnr(x):
     if isinstance(x, float):
         x = torch.tensor([x])
-    return -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))
+    if x.device not in _LOG10:                         # log(10) as the reference forms it (fp32 tensor), created once per device
+        _LOG10[x.device] = torch.log(torch.tensor([10.], device=x.device))
+    return -10. * torch.log(x) / _LOG10[x.device]
 
 
 def get_similarity_matrix(x):
