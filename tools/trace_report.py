@@ -8,7 +8,11 @@ os.environ["NSOS_TRACE"] = "1"
 import nerfsos_b200
 from tools_common import make_net, load_golden   # noqa
 mode = sys.argv[1] if len(sys.argv) > 1 else "exact"
+train = "train" in sys.argv[2:]              # training kwargs (perturb = 1, raw_noise_std = 1, retraw) under no_grad
 net = make_net(mode)
+if train:
+    net.train()
+    net.render_kwargs_train.update(perturb=1.0, raw_noise_std=1.0)
 g = load_golden("flower_eval_256")
 rays = torch.from_numpy(np.tile(g["rays"], (1, 16, 1))).cuda()
 with torch.no_grad():
