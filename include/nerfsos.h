@@ -178,6 +178,12 @@ size_t nsos_mlp_workspace_bytes(const NsosNetDesc* net, int64_t n_pts);
 int nsos_mlp_query(const NsosNetDesc* net, const float* params, const float* pts, const float* viewdirs,
                    float* raw, void* workspace, size_t workspace_bytes, int64_t n_pts, void* stream);
 
+/* The same query on the tensor cores for points that share ONE view direction -- export_density's case (engines/eval.py:290-297:
+ * a regular grid, viewdirs = zeros): pts [P,3] (device), viewdir = HOST array of 3 floats used as given (not normalised),
+ * packed = nsos_pack_weights image of the net for `mode` (NSOS_MODE_TC_EXACT / _FAST) -> raw [P, 4+sem_dim].  No workspace. */
+int nsos_mlp_query_dir(const NsosNetDesc* net, const void* packed, const float* pts, const float* viewdir, float* raw,
+                       int32_t mode, int64_t n_pts, void* stream);
+
 /* ---- kernel B: patch-wise correlation losses ------------------------------------------------- */
 /* GeoCorrelationLoss.forward (utils/image.py:448-482) without materialising the P^2 x P^2 pair
  * matrices.  xyz [B,3,M] (= ray_o + ray_d*depth after the caller's depth clip, :455/:443),

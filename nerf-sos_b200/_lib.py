@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         "nsos_selftest_rowgemm": (C.c_int, [vp, i64, i32, vp, i64, i64, vp, i64, i32, vp, i64, vp, C.c_int, C.c_int, i64, vp, sz, vp]),
         "nsos_selftest_wgrad": (C.c_int, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, vp, i64, vp, i64, vp, C.c_size_t, vp]),
         "nsos_selftest_wgrad_scratch_bytes": (C.c_size_t, []),
+        "nsos_mlp_query_dir": (C.c_int, [C.POINTER(NetDesc), vp, vp, C.POINTER(C.c_float), vp, i32, i64, vp]),
         "nsos_selftest_umma": (C.c_int, [vp, vp, vp, i32, i32, C.c_int, C.c_int, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
@@ -123,7 +124,7 @@ EXPORTS = ["nsos_abi_version", "nsos_last_error", "nsos_param_count", "nsos_para
            "nsos_render_bwd", "nsos_invert_cdf", "nsos_mlp_workspace_bytes", "nsos_mlp_query",
            "nsos_geo_corr_workspace_bytes", "nsos_geo_corr_loss", "nsos_app_corr_workspace_bytes", "nsos_app_corr_loss",
            "nsos_geo_corr_loss_sharded", "nsos_app_corr_loss_sharded", "nsos_adam_multi", "nsos_selftest_umma", "nsos_selftest_rowgemm",
-           "nsos_selftest_wgrad", "nsos_selftest_wgrad_scratch_bytes"]
+           "nsos_selftest_wgrad", "nsos_selftest_wgrad_scratch_bytes", "nsos_mlp_query_dir"]
 
 
 def check(rc: int, what: str):

@@ -167,6 +167,15 @@ int nsos_adam_multi(const NsosAdamTensor* tensors, int32_t n_tensors, float lr, 
   return adam_multi(tensors, n_tensors, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
 }
 
+int nsos_mlp_query_dir(const NsosNetDesc* net, const void* packed, const float* pts, const float* viewdir, float* raw, int32_t mode,
+                       int64_t n_pts, void* stream) {
+  NSOS_REQUIRE(net && packed && pts && viewdir && raw, NSOS_ERR_BAD_ARG, "nsos_mlp_query_dir: null argument");
+  NSOS_REQUIRE(mode == NSOS_MODE_TC_EXACT || mode == NSOS_MODE_TC_FAST, NSOS_ERR_UNSUPPORTED, "nsos_mlp_query_dir: tcgen05 modes only");
+  NSOS_REQUIRE(tc_net_supported(*net), NSOS_ERR_UNSUPPORTED, "nsos_mlp_query_dir: net geometry not supported by the tcgen05 path");
+  NSOS_REQUIRE(net->use_viewdirs, NSOS_ERR_UNSUPPORTED, "nsos_mlp_query_dir: the net takes no view direction");
+  return tc_mlp_query_dir(*net, packed, pts, viewdir, raw, mode, n_pts, (cudaStream_t)stream);
+}
+
 int nsos_selftest_umma(const float* a, const float* w, float* d, int32_t N, int32_t K, int a_in_tmem, int mode, void* scratch,
                        size_t scratch_bytes, void* stream) {
   NSOS_REQUIRE(a && w && d && scratch, NSOS_ERR_BAD_ARG, "nsos_selftest_umma: null argument");

@@ -32,6 +32,8 @@ bool tc_net_supported(const NsosNetDesc& net);
 int tc_render_replay(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
                      const float* z0, const float* z1, float* raw0, float* raw1, float* h0, float* s00, float* h1, float* s01,
                      int64_t n_rays, cudaStream_t st);
+int tc_mlp_query_dir(const NsosNetDesc& net, const void* packed, const float* pts, const float* dir, float* raw, int mode, int64_t n_pts,
+                     cudaStream_t st);
 int tc_render_replay_all(const NsosRenderCfg& cfg, const void* packed_c, const void* packed_f, const float* rays_o, const float* rays_d,
                          const float* z0, const float* z1, float* const raw[2], float* const* const h_all[2], float* const hv[2],
                          float* const s0[2], int64_t n_rays, cudaStream_t st);

@@ -304,6 +304,11 @@ struct TcParams {
   float* dump_all[2][kMaxStages];   // [layer][n_rays*S, W]  relu(pts_linears[layer]); entries may be null
   float* dump_hv[2];                // [n_rays*S, W/2] relu(views_linears.0)
   float* dump_enc[2];               // [n_rays*S, 64]  gamma(x) (training forward: the semantic-head weight gradients read it)
+  // Point query (nsos_mlp_query_dir, MODE 2 only): row q of a tile is point `ray*S + i` of pts_in [n_pts,3], evaluated with ONE
+  // view direction qdir for all points (used as given, not normalised); no rays, no depths.
+  const float* pts_in;
+  long long n_pts;
+  float qdir[3];
   // Layout of dump_h / dump_s0 / dump_enc per pass.  0: row-major [point][feature].  1: blocked -- groups of 32 consecutive points,
   // feature-major inside a group: element (pt, f) of an F-wide tensor sits at ((pt >> 5) * F + f) * 32 + (pt & 31).  The 32 lanes of
   // an epilogue warp hold 32 consecutive points, so one store instruction covers one 128-byte line (row-major: 32 lines), and
@@ -824,11 +829,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
         bool valid = pair_valid && r < P.n_rays;
         long long rr = (r < P.n_rays) ? r : pair * 2;
         float* rp = sm.rayp + t * kRayP;
-        float d0 = P.rays_d[rr * 3], d1 = P.rays_d[rr * 3 + 1], d2 = P.rays_d[rr * 3 + 2];
-        rp[0] = P.rays_o[rr * 3]; rp[1] = P.rays_o[rr * 3 + 1]; rp[2] = P.rays_o[rr * 3 + 2];
+        const bool query = REPLAY && P.pts_in != nullptr;                 // point query: no rays, the direction is given
+        float d0 = query ? P.qdir[0] : P.rays_d[rr * 3], d1 = query ? P.qdir[1] : P.rays_d[rr * 3 + 1], d2 = query ? P.qdir[2] : P.rays_d[rr * 3 + 2];
+        rp[0] = query ? 0.f : P.rays_o[rr * 3]; rp[1] = query ? 0.f : P.rays_o[rr * 3 + 1]; rp[2] = query ? 0.f : P.rays_o[rr * 3 + 2];
         rp[3] = d0; rp[4] = d1; rp[5] = d2;
         rp[6] = REPLAY ? 0.f : P.near[rr]; rp[7] = REPLAY ? 1.f : P.far[rr];
-        float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+        float nrm = query ? 1.f : sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
         rp[8] = nrm; rp[9] = valid ? 1.f : 0.f;
         rp[10] = __fdiv_rn(d0, nrm); rp[11] = __fdiv_rn(d1, nrm); rp[12] = __fdiv_rn(d2, nrm);   // nerf_net.py:165
       }
@@ -899,7 +905,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           {
             float z;
             if (REPLAY) {
-              z = (rowvalid && rp[9] > 0.f) ? P.z_in[pass][ray * S + i] : 1.f;
+              z = (rowvalid && rp[9] > 0.f && !P.pts_in) ? P.z_in[pass][ray * S + i] : 1.f;
             } else if (pass == 0) {
               const bool pert = P.perturb > 0.f;
               float tr = 0.f;
@@ -910,6 +916,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
               z = sm.zf[rl * P.Sf + i];
             }
             float x[3] = {pt_coord(rp[0], rp[3], z), pt_coord(rp[1], rp[4], z), pt_coord(rp[2], rp[5], z)};
+            if (REPLAY && P.pts_in) {                                        // point query: the row's point is read, not sampled
+              const long long pt = ray * S + i;
+              const bool pv = rowvalid && pt < P.n_pts;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) x[k] = pv ? P.pts_in[pt * 3 + k] : 0.f;
+            }
             float e[32];
             if (hf == 0) encode_half<0>(x, pg.Lp, pg.enc, rowvalid, e); else encode_half<1>(x, pg.Lp, pg.enc, rowvalid, e);
             store_halfrow_sw128(sm.g_hi, sm.g_lo, row, hf, e, EXACT);
@@ -987,6 +999,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_tc(const __grid_constant
           // ---- emit the raw outputs of this row: [rgb(3), sigma, sem...] (nerf_mlp.py:94)
           float* graw = (pass == 0 && P.fine) ? P.out.raw0 : P.out.raw;
           float* gr_row = (graw && rp[9] > 0.f) ? graw + ((size_t)ray * S + i) * P.C : nullptr;
+          if (REPLAY && P.pts_in && ray * S + i >= P.n_pts) gr_row = nullptr;        // tail of a point query
           if (pg.st[pg.nst - 1].epi == EPI_SEM_RGB) {
             // merged head stage: worker half 1 owns the rgb sums, half 0 the semantic sums; the sigma share of half 1 was
             // exchanged after the last trunk layer (at least one named barrier ago), so no barrier is needed here and the
@@ -1343,6 +1356,9 @@ struct ReplayIO {
   float* dump_s0[2];
   float* const* dump_all[2] = {nullptr, nullptr};   // [layer] per pass (all-parameter backward) or null
   float* dump_hv[2] = {nullptr, nullptr};
+  const float* pts_in = nullptr;                    // point query (tc_mlp_query_dir): points, count, the one view direction
+  long long n_pts = 0;
+  float qdir[3] = {0.f, 0.f, 0.f};
 };
 
 // common launcher of k_render_tc: forward (replay == nullptr) or backward recompute on given sample depths
@@ -1374,6 +1390,8 @@ int tc_launch(const NsosRenderCfg& cfg, const void* packed_c, const void* packed
   if (replay) {
     for (int i = 0; i < 2; ++i) {
       P.z_in[i] = replay->z_in[i]; P.dump_h[i] = replay->dump_h[i]; P.dump_s0[i] = replay->dump_s0[i]; P.dump_hv[i] = replay->dump_hv[i];
+      P.pts_in = replay->pts_in; P.n_pts = replay->n_pts;
+      for (int k = 0; k < 3; ++k) P.qdir[k] = replay->qdir[k];
       if (replay->dump_all[i]) for (int l = 0; l < kMaxStages; ++l) P.dump_all[i][l] = replay->dump_all[i][l];
     }
   } else if (fine) {
@@ -1466,6 +1484,25 @@ int tc_render_replay(const NsosRenderCfg& cfg, const void* packed_c, const void*
   const bool fine = cfg.n_importance > 0;
   if (fine) { out.raw0 = raw0; out.raw = raw1; } else { out.raw = raw0; }
   return tc_launch(cfg, packed_c, packed_f, rays_o, rays_d, nullptr, nullptr, nullptr, 0, out, &io, nullptr, 0, n_rays, st);
+}
+
+// NeRFMLP.forward (nerf_mlp.py:179-215) for points that share ONE view direction (export_density, eval.py:290-297: zeros) on the
+// tensor cores: the replay mode of the render kernel with the tile rows read from `pts` instead of sampled along rays.
+// `dir` (host, 3 floats) is used as given.  raw [n_pts, 4+sem_dim].
+int tc_mlp_query_dir(const NsosNetDesc& net, const void* packed, const float* pts, const float* dir, float* raw, int mode, int64_t n_pts,
+                     cudaStream_t st) {
+  if (n_pts <= 0) return NSOS_OK;
+  NsosRenderCfg cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.coarse = net; cfg.fine = net; cfg.n_samples = 64; cfg.n_importance = 0; cfg.mode = mode;
+  ReplayIO io{{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  io.pts_in = pts; io.n_pts = n_pts;
+  for (int k = 0; k < 3; ++k) io.qdir[k] = dir[k];
+  NsosRenderOut out;
+  memset(&out, 0, sizeof(out));
+  out.raw = raw;
+  const int64_t n_rays = (n_pts + cfg.n_samples - 1) / cfg.n_samples;      // 64 consecutive points per "ray", two per tile
+  return tc_launch(cfg, packed, packed, nullptr, nullptr, nullptr, nullptr, nullptr, 0, out, &io, nullptr, 0, n_rays, st);
 }
 
 // C[P,N] (=|+=) epi(A[P,K] . B),  B(k,n) = B[k*b_rs + n*b_cs].  scratch: >= tc_rowgemm_scratch_bytes(K, N).

@@ -154,7 +154,8 @@ def export_density(model, extents=(2.0, 2.0, 2.0), voxel_size=2. / 256., save_di
     """eval.py:279-304: queries `model.nerf_fine` on a regular grid (x14, zero view directions) and returns
     relu(raw[..., -1]) as a numpy volume [W, H, D] -- the LAST raw channel, exactly as the reference does (with a segmentation
     head that is the last semantic logit, not sigma: raw = [rgb(3), sigma, sem...], nerf_mlp.py:94; use `channel=` semantics by
-    slicing `model.nerf_fine(pts, viewdirs=...)` yourself if sigma is wanted).  The query runs through nsos_mlp_query in slices
+    slicing `model.nerf_fine(pts, viewdirs=...)` yourself if sigma is wanted).  The query runs through nsos_mlp_query_dir (tensor cores;
+    nsos_mlp_query for mode='simt') in slices
     of `chunk` points; `density.npy` is written when `save_dir` is given (the reference's .mrc / .ply writers need mrc / open3d)."""
     model.eval()
     device = device or next(model.parameters()).device
@@ -165,9 +166,13 @@ def export_density(model, extents=(2.0, 2.0, 2.0), voxel_size=2. / 256., save_di
         pts = pts * 14
         flat = pts.reshape(-1, 3)
         sig = torch.empty(flat.shape[0], device=device)
+        mode = model.resolve_mode() if hasattr(model, "resolve_mode") else 0
         for i in range(0, flat.shape[0], chunk):
             x = flat[i:i + chunk]
-            raw = model.nerf_fine(x, viewdirs=torch.zeros_like(x))
+            if mode != 0 and hasattr(model.nerf_fine, "query_dir"):      # one view direction for all points: the tcgen05 query
+                raw = model.nerf_fine.query_dir(x, (0.0, 0.0, 0.0), mode)
+            else:
+                raw = model.nerf_fine(x, viewdirs=torch.zeros_like(x))
             sig[i:i + chunk] = raw[..., -1].clamp_min(0)
         sigma = sig.reshape(pts.shape[:-1]).cpu().numpy()
     if save_dir:

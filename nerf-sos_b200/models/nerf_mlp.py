@@ -10,6 +10,8 @@ sem_with_geo=False, conv_embed=False, use_embed=True (anything else raises NotIm
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.nn as nn
 
@@ -162,6 +164,28 @@ class NeRFMLP(nn.Module):
             _lib.check(L.nsos_pack_weights(d, _lib.ptr(flat), _lib.ptr(buf), mode, _lib.cur_stream(flat.device)), "nsos_pack_weights")
         self._packed[mode] = (ver, buf)
         return buf
+
+    # ---- the same query for points that share ONE view direction, on the tensor cores --------------
+    @torch.no_grad()
+    def query_dir(self, inputs, viewdir=(0.0, 0.0, 0.0), mode: int = _lib.MODE_TC_EXACT):
+        """forward(inputs, viewdirs=viewdir.expand_as(inputs)) through the tcgen05 render kernel's replay mode
+        (nsos_mlp_query_dir): what export_density (engines/eval.py:290-297) asks for -- a grid of points with viewdirs = 0.
+        `viewdir` is used as given (the caller normalises, as for forward).  Raises NsosError for net geometries the
+        tcgen05 path does not cover (use forward then)."""
+        if not self.mlp.use_viewdirs:
+            raise _lib.NsosError("query_dir: the net takes no view direction")
+        flat = self.flat_params()
+        pk = self.packed(mode, flat=flat)
+        sh = inputs.shape
+        pts = inputs.reshape(-1, 3).to(flat.device, torch.float32).contiguous()
+        n = pts.shape[0]
+        Cc = 4 + (self.mlp.sem_dim if self.mlp.use_semantics else 0)
+        out = torch.empty(n, Cc, dtype=torch.float32, device=flat.device)
+        vd = (C.c_float * 3)(*[float(v) for v in viewdir])
+        with torch.cuda.device(flat.device):
+            _lib.check(_lib.lib().nsos_mlp_query_dir(self.desc(), _lib.ptr(pk), _lib.ptr(pts), vd, _lib.ptr(out), mode, n,
+                                                     _lib.cur_stream(flat.device)), "nsos_mlp_query_dir")
+        return out.reshape(*sh[:-1], Cc)
 
     # ---- NeRFMLP.forward (nerf_mlp.py:179-215): raw network query ---------------------------------
     @torch.no_grad()

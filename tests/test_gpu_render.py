@@ -533,6 +533,32 @@ def test_mlp_query_matches_oracle():
     close(raw, ref, rtol=1e-4, atol=5e-4)
 
 
+@pytest.mark.parametrize("mode,tol", [("exact", 1e-4), ("fast", 2e-2)])
+def test_mlp_query_dir_on_tensor_cores(mode, tol):
+    """nsos_mlp_query_dir (export_density's query: many points, ONE view direction) through the tcgen05 replay mode, against the
+    numpy oracle's MLP and against the fp32 CUDA-core query; ragged point count (tail of the last 64-point group)."""
+    from oracle import nerf_oracle as O
+    _lib, _ = _imports()
+    net = flower_net(mode).eval()
+    g = torch.Generator().manual_seed(5)
+    n = 64 * 37 + 19
+    pts = (torch.rand(n, 3, generator=g) * 2 - 1) * 3
+    for vd in ((0.0, 0.0, 0.0), (0.6, -0.48, 0.64)):
+        raw = net.nerf_fine.query_dir(pts.to(DEV), vd, _lib.MODES[mode])
+        vdt = torch.tensor(vd).expand(n, 3).contiguous()
+        _, fine = O.split_state_dict(load_golden("flower_weights")["sd"])
+        ref = O.mlp_forward(fine, O.encode(pts.numpy(), 10), O.encode(vdt.numpy(), 4))
+        simt = net.nerf_fine(pts.to(DEV), viewdirs=vdt.to(DEV))
+        assert raw.shape == (n, 6)
+        scale = np.abs(ref).max(0)
+        err = (raw.cpu().numpy() - ref) / np.maximum(scale, 1.0)
+        assert np.abs(err).max() <= tol * 5, np.abs(err).max()              # per channel, relative to the channel's range
+        close(simt, ref, rtol=1e-4, atol=5e-4)
+    # shape handling like forward: leading dims are kept
+    grid = pts[:60].reshape(3, 4, 5, 3).to(DEV)
+    assert net.nerf_fine.query_dir(grid, (0.0, 0.0, 0.0), _lib.MODES[mode]).shape == (3, 4, 5, 6)
+
+
 def test_cpu_tensors_fail_loudly():
     _lib, NeRFNet = _imports()
     net = NeRFNet(netdepth=2, netwidth=64, netdepth_fine=2, netwidth_fine=64, N_samples=8, N_importance=0)
