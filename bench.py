@@ -478,12 +478,34 @@ def main():
             fn()
         barrier()
         e2e.append(time.perf_counter() - t0)
+    # ---- the same round trip as ONE captured CUDA graph (NeRFNet.capture_eval: H2D copy + render launch + D2H copy per replay) ----
+    graph_s = 0.0
+    if not image:
+        try:
+            cap = net.capture_eval(n_local, NEAR, FAR)
+            cap.rays_host.copy_(rays_host)
+
+            def step_graph():
+                cap.replay()
+                torch.cuda.current_stream().synchronize()
+            for _ in range(3):
+                step_graph()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_graph()
+            barrier()
+            graph_s = time.perf_counter() - t0
+        except Exception as e:                                           # an optional figure must not cost the line
+            print(f"[bench] capture_eval failed: {e!r}", file=sys.stderr)
+            if dist is not None:
+                raise
     clk = clocks.stop() if rank == 0 else None
 
-    tt = torch.tensor([total_ms] + e2e, dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms] + e2e + [graph_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, e2e_dropin_s = tt.tolist()
+    total_ms, e2e_s, e2e_dropin_s, graph_s = tt.tolist()
     # ---- secondary measurement in the same run: the shipped training step (north_star's collective path: packed all-gather,
     # old_mean / code-gradient / parameter-gradient all-reduces) with the real train_one_step, 8 patches per GPU
     train = None
@@ -495,7 +517,7 @@ def main():
             if dist is not None:
                 raise
     if rank == 0:
-        m = dict(total_ms=total_ms, e2e_s=e2e_s, e2e_dropin_s=e2e_dropin_s, n_total=n_total, n_local=n_local, t_wall=t_wall, clk=clk,
+        m = dict(total_ms=total_ms, e2e_s=e2e_s, e2e_dropin_s=e2e_dropin_s, e2e_graph_s=graph_s, n_total=n_total, n_local=n_local, t_wall=t_wall, clk=clk,
                  h2d=int(rays_host.numel() * 4), d2h=int(maps_host.numel() * 4))
         line = eval_line(m, args, world, image, train)
         # parity beside the speed (BASELINE metric: "rays/sec ...; PSNR vs ref"): the same net and mode on the 256 rays whose
@@ -572,6 +594,10 @@ def eval_line(m, args, world, image, train):
         "clocks": m["clk"],
         "wall_s_timed_region": m["t_wall"],
     }
+    if m.get("e2e_graph_s"):
+        line["e2e_graph"] = {"value": m["n_total"] * args.steps / m["e2e_graph_s"], "unit": "rays/s",
+                             "note": "the e2e round trip as one captured CUDA graph (NeRFNet.capture_eval: pinned rays -> H2D, render launch, "
+                                     "D2H -> pinned maps per replay); an extension of the drop-in surface, not the reference's call"}
     if train is not None:
         line["train"] = train
     return line

@@ -559,6 +559,26 @@ def test_mlp_query_dir_on_tensor_cores(mode, tol):
     assert net.nerf_fine.query_dir(grid, (0.0, 0.0, 0.0), _lib.MODES[mode]).shape == (3, 4, 5, 6)
 
 
+def test_capture_eval_graph_replays_the_direct_call():
+    """NeRFNet.capture_eval: H2D + render + D2H as one CUDA graph; replays give the bits of the direct call, for new rays too."""
+    net = flower_net("exact").eval()
+    g = load_golden("flower_eval_256")
+    rays = torch.from_numpy(g["rays"])                                    # [2, 256, 3]
+    cap = net.capture_eval(256, 1.2, 12.0)
+    for shift in (0.0, 0.05):
+        r = rays.clone()
+        r[0] += shift
+        cap.rays_host.copy_(r)
+        cap.replay()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            direct = net(r.to(DEV), (1.2, 12.0), retraw=False, retmaps=True)["maps"]
+        assert torch.equal(cap.maps_host, direct.cpu())
+    net.train()
+    with pytest.raises(ValueError):
+        net.capture_eval(256, 1.2, 12.0)
+
+
 def test_cpu_tensors_fail_loudly():
     _lib, NeRFNet = _imports()
     net = NeRFNet(netdepth=2, netwidth=64, netdepth_fine=2, netwidth_fine=64, N_samples=8, N_importance=0)
