@@ -137,6 +137,19 @@ def train_one_step(batch, model, optimizer, scheduler, train_loader, global_step
             sim = get_similarity_matrix(cls_all)
         # ---- phase 1 of every loss call (row means of my query patches), then ONE all-reduce of the old_mean sums
         pend = []
+        # random negatives (rand_neg, or no similarity matrix) must be the same on every rank: drawn from a step-seeded host
+        # generator, one permutation per loss call like the reference (image.py:349-356); the argmin choice needs nothing
+        ngen = torch.Generator().manual_seed(1_000_003 * int(global_step) + 29)
+
+        def shared_neg(mod):
+            rand = bool(getattr(mod, "rand_neg", False))
+            if not (rand or sim is None):
+                return None
+            perm = torch.randperm(Bg, generator=ngen)
+            if not rand:                                               # super_perm: no patch is its own negative
+                perm[perm == torch.arange(Bg)] += 1
+                perm = perm % Bg
+            return perm.to(device)
         if use_app:
             if coords is None:                                         # shared by all ranks: seeded with the step
                 gen = torch.Generator().manual_seed(1_000_003 * int(global_step) + 17)
@@ -144,10 +157,12 @@ def train_one_step(batch, model, optimizer, scheduler, train_loader, global_step
                 pin = torch.device(device).type == "cuda"                  # pinned source: no staging copy (the CPU tests have no driver)
                 coords = torch.rand(shp, generator=gen, pin_memory=pin).mul_(2).sub_(1).to(device, non_blocking=True)
             for i, s_all in enumerate((s0_all, s1_all)):
-                pend.append((i, correlation_loss.begin(feat_all, s_all, sim, q0, Bl, coords=(coords[i][0], coords[i][1]))))
+                pend.append((i, correlation_loss.begin(feat_all, s_all, sim, q0, Bl, coords=(coords[i][0], coords[i][1]),
+                                                       neg=shared_neg(correlation_loss))))
         if use_geo:
             for i, s_all in enumerate((s0_all, s1_all)):                # the FINE depth for both (trainer.py:159-160)
-                pend.append((2 + i, geoCorrelation_loss.begin(dep_all.clone(), s_all, [ro_all, rd_all, None], sim, q0, Bl)))
+                pend.append((2 + i, geoCorrelation_loss.begin(dep_all.clone(), s_all, [ro_all, rd_all, None], sim, q0, Bl,
+                                                              neg=shared_neg(geoCorrelation_loss))))
         if pend:
             sums = torch.stack([p.sums for _, p in pend])
             P.all_reduce_sum_(sums, group)

@@ -173,8 +173,9 @@ class CorrelationLoss(nn.Module):
             neg = torch.randperm(sim_matrix.shape[0], device=device, dtype=torch.long)
         return neg
 
-    def _sampled(self, orig_feats, orig_code, sim_matrix, coords, rows):
-        """The four sampled tensors of image.py:343-362 for the query patches `rows` (slice) of the batch."""
+    def _sampled(self, orig_feats, orig_code, sim_matrix, coords, rows, neg=None):
+        """The four sampled tensors of image.py:343-362 for the query patches `rows` (slice) of the batch.
+        `neg` [B]: negatives chosen by the caller (data-parallel training: random choices must agree on all ranks)."""
         B = orig_feats.shape[0]
         shape = [B, self.feature_samples, self.feature_samples, 2]
         if coords is None:
@@ -182,7 +183,7 @@ class CorrelationLoss(nn.Module):
             coords2 = torch.rand(shape, device=orig_feats.device) * 2 - 1
         else:
             coords1, coords2 = coords
-        neg = self._neg_index(sim_matrix, B, orig_feats.device)[rows]
+        neg = (self._neg_index(sim_matrix, B, orig_feats.device) if neg is None else neg.to(orig_feats.device))[rows]
         c1, c2 = coords1[rows], coords2[rows]
         with torch.no_grad():
             feats = self.sample(orig_feats[rows], c1)
@@ -198,11 +199,11 @@ class CorrelationLoss(nn.Module):
 
     # ---- sharded evaluation (data-parallel training): begin() on every rank, all-reduce the `sums` of all pending calls in
     # one collective, finish() -> this rank's share of the loss (sum over ranks == forward() on the global batch)
-    def begin(self, orig_feats, orig_code, sim_matrix, q0, nq, coords=None):
-        """orig_feats / orig_code / sim_matrix / coords describe the GLOBAL batch (gathered); this rank's queries are
+    def begin(self, orig_feats, orig_code, sim_matrix, q0, nq, coords=None, neg=None):
+        """orig_feats / orig_code / sim_matrix / coords (/ neg) describe the GLOBAL batch (gathered); this rank's queries are
         the patches [q0, q0+nq)."""
         L = _lib.lib()
-        t = self._sampled(orig_feats, orig_code, sim_matrix, coords, slice(q0, q0 + nq))
+        t = self._sampled(orig_feats, orig_code, sim_matrix, coords, slice(q0, q0 + nq), neg)
         B, Cf, Cc, S = nq, t[0].shape[1], t[2].shape[1], t[0].shape[2] * t[0].shape[3]
         p = _Pending()
         p.kind, p.args, p.q0, p.nq, p.B_total = "app", t, q0, nq, orig_feats.shape[0]
@@ -252,13 +253,13 @@ class GeoCorrelationLoss(CorrelationLoss):
         params = (self.self_shift, self.self_weight, self.neg_shift, self.neg_weight)
         return _GeoCorrFn.apply(xyz, orig_code, neg, params)
 
-    def begin(self, orig_feats, orig_code, batch_rays, sim_matrix, q0, nq):
-        """Sharded evaluation, see CorrelationLoss.begin: depth / code / rays / sim describe the GLOBAL batch."""
+    def begin(self, orig_feats, orig_code, batch_rays, sim_matrix, q0, nq, neg=None):
+        """Sharded evaluation, see CorrelationLoss.begin: depth / code / rays / sim (/ neg) describe the GLOBAL batch."""
         L = _lib.lib()
         xyz = self._points(orig_feats, batch_rays)
         B, Cc = orig_code.shape[0], orig_code.shape[1]
         M = orig_code.shape[2] * orig_code.shape[3]
-        neg = self._neg_index(sim_matrix, B, orig_code.device).to(torch.int64).contiguous()
+        neg = (self._neg_index(sim_matrix, B, orig_code.device) if neg is None else neg.to(orig_code.device)).to(torch.int64).contiguous()
         p = _Pending()
         p.kind, p.args, p.q0, p.nq, p.B_total = "geo", (xyz, orig_code, neg), q0, nq, B
         p.params = (self.self_shift, self.self_weight, self.neg_shift, self.neg_weight)

@@ -82,3 +82,33 @@ def test_five_steps_match_the_reference_trainer(mode, tol):
         if p.requires_grad:
             d = np.abs(p.detach().cpu().numpy() - g["final"][n])
             assert (d <= 2e-5).mean() >= 0.98 and d.max() <= 5e-3, (n, (d <= 2e-5).mean(), d.max())
+
+
+def test_random_negatives_are_step_seeded():
+    """--rand_neg (image.py:349-356): the permutation of negatives comes from a step-seeded host generator so that every rank of
+    a data-parallel run picks the same ones: same step -> same loss terms, another step -> another permutation."""
+    import dist_gpu_worker as W
+    dev = torch.device("cuda:0")
+    a = W.Args()
+    a.use_correlation = True
+    a.rand_neg = True
+    g = W.load_golden("flower_eval_256")
+    B, Ps = 4, a.patch_size
+    n = B * Ps * Ps
+    rays = torch.from_numpy(g["rays"]).repeat(1, (n + 255) // 256, 1)[:, :n].permute(1, 0, 2).reshape(B, Ps * Ps, 2, 3).contiguous()
+    rays[..., 0, :] += torch.linspace(0, 0.3, B).view(B, 1, 1)               # four different patches
+    gt = torch.rand(B, Ps * Ps, 3, generator=torch.Generator().manual_seed(0))
+    from nerfsos_b200.engines.lr import LRScheduler
+    from nerfsos_b200.engines.optim import FusedAdam
+
+    def geo_terms(step):
+        net = W.make_net(dev)
+        opt = FusedAdam([p for p in net.parameters() if p.requires_grad], lr=0.0)
+        losses = [None, None, W.CorrelationLoss(a), W.GeoCorrelationLoss(a)]
+        torch.manual_seed(0)
+        out = W.train_one_step((rays, gt), [net, W.FakeDino()], opt, LRScheduler(opt, 0.0, 0.1, 250000), W.Loader(), step, losses, dev, a)
+        return [out[k].item() for k in ("corr0", "corr1", "geo_corr0", "geo_corr1")]
+
+    t1, t1b, t2 = geo_terms(1), geo_terms(1), geo_terms(2)
+    assert t1 == t1b
+    assert any(abs(x - y) > 1e-7 for x, y in zip(t1, t2))

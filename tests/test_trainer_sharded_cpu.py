@@ -74,7 +74,7 @@ class ToyCorr:
         fd = self._fd(feats, neg, rows)
         return self._loss(fd, fd.mean(), code, neg, rows, feats.shape[0])
 
-    def begin(self, feats, code, sim, q0, nq, coords=None):
+    def begin(self, feats, code, sim, q0, nq, coords=None, neg=None):
         p = _Pend()
         p.neg, p.rows, p.code, p.B = self._neg(sim), slice(q0, q0 + nq), code, feats.shape[0]
         p.fd = self._fd(feats, p.neg, p.rows)
@@ -90,7 +90,7 @@ class ToyGeo(ToyCorr):
     def __call__(self, depth, code, rays, sim):
         return super().__call__(rays[0] + rays[1] * depth, code, sim)
 
-    def begin(self, depth, code, rays, sim, q0, nq):
+    def begin(self, depth, code, rays, sim, q0, nq, neg=None):
         return super().begin(rays[0] + rays[1] * depth, code, sim, q0, nq)
 
 
