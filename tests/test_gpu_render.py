@@ -312,13 +312,14 @@ def test_flower_all_parameter_gradients(mode):
         assert err <= 1e-3 * max(np.abs(ref).max(), 1e-8), (n, err, np.abs(ref).max())
 
 
-def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypatch):
-    """--fix_backbone backward at a size that crosses the 4096-ray chunk with an odd tail.  Three implementations of the
+@pytest.mark.parametrize("n,ns,ni", [(4096 + 37, 64, 128), (333, 40, 25)])
+def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypatch, n, ns, ni):
+    """--fix_backbone backward at a size that crosses the 4096-ray chunk with an odd tail, and at sample counts whose point totals
+    (333 x 40, 333 x 65 -- odd) end inside a 32-point group of the saved activations' blocked layout.  Three implementations of the
     same gradients: (tc) activations saved by the forward kernel + weight gradients on tcgen05, (replay) trunk replayed on
     tcgen05 in backward + the same weight-gradient kernel, (wsimt) trunk replay on tcgen05 + fp32 CUDA-core GEMMs, (simt)
     everything recomputed in fp32 on CUDA cores."""
     g = load_golden("flower_eval_256")
-    n = 4096 + 37
     rays = torch.from_numpy(g["rays"]).to(DEV)
     rays = rays.repeat(1, n // rays.shape[1] + 1, 1)[:, :n].contiguous()
     rays[1] += 0.01 * torch.randn(n, 3, device=DEV, generator=torch.Generator(DEV).manual_seed(3))
@@ -334,7 +335,7 @@ def test_semantic_head_backward_tensor_core_paths_match_fp32_recompute(monkeypat
         for nme, p in net.named_parameters():
             p.requires_grad_("semantic_linear" in nme)
         torch.manual_seed(11)                       # same Philox seed for all runs
-        out = net(rays, (1.2, 12.0))
+        out = net(rays, (1.2, 12.0), N_samples=ns, N_importance=ni)
         ((out["semantics"] * gsem).sum() + (out["semantics0"] * gsem0).sum()).backward()
         grads[which] = {nme: p.grad.clone() for nme, p in net.named_parameters() if p.grad is not None}
         if env:
