@@ -480,7 +480,7 @@ def main():
         e2e.append(time.perf_counter() - t0)
     # ---- the same round trip as ONE captured CUDA graph (NeRFNet.capture_eval: H2D copy + render launch + D2H copy per replay) ----
     graph_s = 0.0
-    if not image:
+    if not image and dist is None:        # single process only: no collective may sit inside this optional block
         try:
             cap = net.capture_eval(n_local, NEAR, FAR)
             cap.rays_host.copy_(rays_host)
@@ -498,8 +498,7 @@ def main():
             graph_s = time.perf_counter() - t0
         except Exception as e:                                           # an optional figure must not cost the line
             print(f"[bench] capture_eval failed: {e!r}", file=sys.stderr)
-            if dist is not None:
-                raise
+            graph_s = 0.0
     clk = clocks.stop() if rank == 0 else None
 
     tt = torch.tensor([total_ms] + e2e + [graph_s], dtype=torch.float64, device=dev)

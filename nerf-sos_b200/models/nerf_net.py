@@ -371,7 +371,7 @@ class CapturedEval:
             torch.cuda.current_stream(dev).wait_stream(stream)
             self.maps_host = torch.empty(out["maps"].shape).pin_memory()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):     # other threads (NCCL watchdog, data loaders) may call CUDA
                 self._rays.copy_(self.rays_host, non_blocking=True)
                 out = net(self._rays, (near, far), **kwargs)
                 self.maps_host.copy_(out["maps"], non_blocking=True)
