@@ -47,6 +47,25 @@ def get_similarity_matrix(x):
 _WS = {}
 
 
+class NeRFContrastive(nn.Module):
+    """image.py:192-218 -- the optional contrast term of trainer.py:168-170 on the DINO class tokens [B, D]: with the largest and
+    the smallest off-diagonal cosine similarity of the batch, loss = -log(max / (max + min)).  Plain PyTorch (B x B, off the hot
+    path); only the min/max variant exists in the reference."""
+
+    def __init__(self, temperature=1, device=None, verbose=False, min_max_contrast=True):
+        super().__init__()
+        if not min_max_contrast:
+            raise NotImplementedError("only min_max_contrast=True is implemented (as in the reference)")
+        self.device, self.verbose = device, verbose
+        self.register_buffer("temperature", torch.tensor(temperature))
+
+    def forward(self, embeddings):
+        sim = F.cosine_similarity(embeddings.unsqueeze(1), embeddings.unsqueeze(0), dim=2)
+        off = sim[~torch.eye(sim.shape[0], dtype=torch.bool, device=sim.device)]
+        hi, lo = off.max(), off.min()
+        return -torch.log(hi / (hi + lo))
+
+
 def _workspace(nbytes, device):
     ws = _WS.get(device)
     if ws is None or ws.numel() < nbytes:

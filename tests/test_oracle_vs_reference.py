@@ -80,3 +80,17 @@ def test_oracle_losses_match_reference_on_fresh_inputs():
     mine_g, _ = O.geo_correlation_loss(depth.numpy(), code.numpy(), ray_o.numpy(), ray_d.numpy(), sim.numpy(),
                                        tuple(_LossArgs.geo_corr_params))
     assert abs(mine_g - lg) <= 1e-4 * max(1.0, abs(lg)), (mine_g, lg)
+
+
+def test_contrast_loss_matches_reference_module():
+    """utils/image.py:192-218 (NeRFContrastive, the optional contrast term of the trainer) against the reference class."""
+    import torch
+    from utils.image import NeRFContrastive as Ref
+    import nerfsos_b200  # noqa: F401
+    from nerfsos_b200.utils.image import NeRFContrastive
+    x = torch.randn(8, 384, generator=torch.Generator().manual_seed(0)).requires_grad_(True)
+    a = NeRFContrastive(device="cpu")(x)
+    g1, = torch.autograd.grad(a, x)
+    b = Ref(device="cpu")(x)
+    g2, = torch.autograd.grad(b, x)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-7) and torch.allclose(g1, g2, rtol=1e-5, atol=1e-7)
