@@ -33,7 +33,7 @@ using namespace ptx;
 constexpr int kWgWorkers = 256, kWgThreads = 288, kWgMmaWarp = 8;   // k_wgrad_gen: 8 fill warps + an issuer warp
 constexpr int kSemWarps = 16, kSemThreads = 32 * kSemWarps;   // k_sem_wgrad: 16 fill warps (two sets of 14 loads per lane, 128 registers):
                                    // 8 warps at 255 registers issued one instruction per 8 cycles (ncu: 75 % of cycles without an eligible warp);
-                                   // the warp that completes a half also issues its MMAs
+                                   // the MMA issue rotates over the warps
 constexpr int kHalfPts = 32;                       // points per fill / MMA unit: half of a 64-point tile
 constexpr int kSlabPts = 64;
 constexpr int kRowsA = 128, kRowsB = 320, kRowsB2 = 16;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
   const long long nhalf = (P.P + kHalfPts - 1) / kHalfPts;
   const long long my_n = (nhalf - blockIdx.x + gridDim.x - 1) / gridDim.x;     // >= 1 (grid <= nhalf)
   if (t == 0) {
-    for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(&sm.done[h]), 1); sm.cnt[h] = 0u; }
+    for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(&sm.ready[h]), kSemWarps); mbar_init(smem_u32(&sm.done[h]), 1); }
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
@@ -194,12 +194,13 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
   tc_fence_after();
   const uint32_t tm = *sm.tmem_ptr;
   __shared__ long long tr[4][24];      // [issue begin, issue end, warp-0 done-wait begin, end][half]
+  __shared__ long long tw[16][4][4];   // [warp][half 8..11][fill start, done seen, h stored, fill end]
   const bool trace = P.trace && blockIdx.x == 0;
 
   const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, a2[2] = {smem_u32(sm.a2[0]), smem_u32(sm.a2[1])};
   const uint32_t b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])}, b2[2] = {smem_u32(sm.b2[0]), smem_u32(sm.b2[1])};
   const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64), id16 = make_idesc_bf16(16);
-  // 3 x 2 x 3 MMAs per half (hi.hi, lo.hi, hi.lo; M=128, N=256/64/16, K=16), issued by the warp that finished the half last
+  // 3 x 2 x 3 MMAs per half (hi.hi, lo.hi, hi.lo; M=128, N=256/64/16, K=16), issued by the half's designated warp once all have arrived
   auto issue = [&](int half, long long it) {
     tc_fence_after();
     if (elect_one()) {
@@ -281,6 +282,8 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
     auto fill = [&](SemLoads& L, int half, long long it) {
       // the MMAs that read this half two iterations ago have completed
       if (trace && t == 0 && it < 24) tr[2][it] = clock64();
+      const bool tw_on = trace && lane == 0 && it >= 8 && it < 12;
+      if (tw_on) tw[warp][it - 8][0] = clock64();
       if (it >= 2) {                                     // (polling warps back off: they share schedulers with the warps still converting)
         const uint32_t bar = smem_u32(&sm.done[half]), par = (uint32_t)(((it >> 1) - 1) & 1);
         for (uint32_t spins = 0; !mbar_try_wait(bar, par); ++spins) {
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
         tc_fence_after();
       }
       if (trace && t == 0 && it < 24) tr[3][it] = clock64();
+      if (tw_on) tw[warp][it - 8][1] = clock64();
       const int xk = 4 * half + (m >> 2);               // 16-byte chunk of this lane's word before the swizzle
       auto offs = [&](int r7) { return (uint32_t)(r7 * 128 + ((xk ^ r7) << 4) + (m & 3) * 4); };
       uint32_t off[4];                                   // per (k & 3), rows (k & 3) + 4*fb: everything of the offset except r8*1024
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
       // ---- B rows 0..255: h (feature 2*kSemH*e + 8*(k >> 2) + (k & 3) + 4*fb)
 #pragma unroll
       for (int k = 0; k < kSemH; ++k) put(b, (2 * kSemH / 8) * e + (k >> 2), off[k & 3], L.hx[k], L.hy[k]);
+      if (tw_on) tw[warp][it - 8][2] = clock64();
       // ---- B rows 256..319: gamma (63) and the constant-one feature (-> db0); feature 2*kSemE*e + 2k + fb
 #pragma unroll
       for (int k = 0; k < kSemE; ++k) {
@@ -339,18 +344,17 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
           for (int c = 0; c < 4; ++c) gb2_acc[c] += L.gs0[c] + L.gs1[c];
         }
       }
-      // ---- the warp whose arrival completes the half issues its MMAs: nobody waits for a designated issuer
+      // ---- one arrival per warp; the half's MMAs are issued by warp (it mod 16): the duty ROTATES.  (With "whoever arrives last
+      // issues", the ~1.1 k cycles of issuing made the same warp the last one again and again -- per-warp timeline, NSOS_WG_TRACE=1,
+      // profiles/r02_notes.md: one warp 7 k cycles behind the other fifteen.)
+      if (tw_on) tw[warp][it - 8][3] = clock64();
       fence_proxy_async_smem();
       __syncwarp();
-      uint32_t last = 0;
-      if (lane == 0) {
-        uint32_t old;
-        asm volatile("atom.shared.acq_rel.cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&sm.cnt[half])) : "memory");
-        last = (old == (uint32_t)(kSemWarps - 1)) ? 1u : 0u;
-        if (last) sm.cnt[half] = 0u;                    // next use: two halves on, after done[half]
+      if (lane == 0) mbar_arrive(smem_u32(&sm.ready[half]));
+      if (warp == (int)(it % kSemWarps)) {
+        mbar_wait(smem_u32(&sm.ready[half]), (uint32_t)((it >> 1) & 1), 700 + half);
+        issue(half, it);
       }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) { tc_fence_before(); issue(half, it); }
     };
     SemLoads L0, L1;
     load(L0, 0);
@@ -395,6 +399,13 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (trace && t == 0 && my_n >= 12)
+    for (int w = 0; w < kSemWarps; ++w)                 // per-warp timeline of halves 8..11: fill start, done seen, h stored, fill end
+      printf("[ww] warp %2d: h8 %lld %lld %lld %lld | h9 %lld %lld %lld %lld | h10 %lld %lld %lld %lld | h11 %lld %lld %lld %lld\n", w,
+             tw[w][0][0] - tr[2][8], tw[w][0][1] - tr[2][8], tw[w][0][2] - tr[2][8], tw[w][0][3] - tr[2][8],
+             tw[w][1][0] - tr[2][8], tw[w][1][1] - tr[2][8], tw[w][1][2] - tr[2][8], tw[w][1][3] - tr[2][8],
+             tw[w][2][0] - tr[2][8], tw[w][2][1] - tr[2][8], tw[w][2][2] - tr[2][8], tw[w][2][3] - tr[2][8],
+             tw[w][3][0] - tr[2][8], tw[w][3][1] - tr[2][8], tw[w][3][2] - tr[2][8], tw[w][3][3] - tr[2][8]);
   if (trace && t == 0)
     for (int i = 0; i < 24 && i < my_n; ++i)
       printf("[wg] half %2d: fill starts %7lld, done(it-2) seen %7lld, issue %7lld .. %7lld\n", i, tr[2][i] - tr[2][0], tr[3][i] - tr[2][0],
