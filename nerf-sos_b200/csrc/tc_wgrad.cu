@@ -31,7 +31,7 @@ namespace {
 using namespace ptx;
 
 constexpr int kWgWorkers = 256, kWgThreads = 288, kWgMmaWarp = 8;   // k_wgrad_gen: 8 fill warps + an issuer warp
-constexpr int kSemWarps = 16, kSemThreads = 32 * kSemWarps;   // k_sem_wgrad: 16 fill warps (two sets of 14 loads per lane, 128 registers):
+constexpr int kSemWarps = 8, kSemIssuer = kSemWarps, kSemThreads = 32 * (kSemWarps + 4);   // 8 fill warps + the issuer's warpgroup (3 of its warps idle)   // k_sem_wgrad: 16 fill warps (two sets of 14 loads per lane, 128 registers):
                                    // 8 warps at 255 registers issued one instruction per 8 cycles (ncu: 75 % of cycles without an eligible warp);
                                    // the MMA issue rotates over the warps
 constexpr int kHalfPts = 32;                       // points per fill / MMA unit: half of a 64-point tile
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
   tc_fence_after();
   const uint32_t tm = *sm.tmem_ptr;
   __shared__ long long tr[4][24];      // [issue begin, issue end, warp-0 done-wait begin, end][half]
-  __shared__ long long tw[16][4][4];   // [warp][half 8..11][fill start, done seen, h stored, fill end]
+  __shared__ long long tw[kSemWarps][4][4];   // [warp][half 8..11][fill start, done seen, h stored, fill end]
   const bool trace = P.trace && blockIdx.x == 0;
 
   const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, a2[2] = {smem_u32(sm.a2[0]), smem_u32(sm.a2[1])};
@@ -223,8 +223,21 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
     }
     __syncwarp();
   };
-  {
+  if (warp >= kSemWarps) {
+    // ================= issuer warpgroup: warp 8 issues every half's MMAs, warps 9-11 only give their registers away ==========
+    // 12 warps launch at 168 registers; this group drops to 24 (frees 128 x 144), the 8 fill warps grow to 240 (take 256 x 72).
+    // A fill warp that also issues -- ~1.1 k cycles per half -- falls behind the others and becomes what every half waits for
+    // (per-warp timelines in profiles/r02_notes.md).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == kSemIssuer)
+      for (long long it = 0; it < my_n; ++it) {
+        const int half = (int)(it & 1);
+        mbar_wait(smem_u32(&sm.ready[half]), (uint32_t)((it >> 1) & 1), 700 + half);
+        issue(half, it);
+      }
+  } else {
     // ================= fill warps =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
     const int e = warp;                                  // feature eighth: h 32e.., gamma 8e.., s0 units 16e..
     float gb2_acc[4] = {0.f, 0.f, 0.f, 0.f};
     // h / s0 (and gamma when the forward pass saved it) arrive in the blocked layout (internal.h: sem_saves_blocked): the half is
@@ -351,10 +364,6 @@ __global__ void __launch_bounds__(kSemThreads, 1) k_sem_wgrad(const __grid_const
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sm.ready[half]));
-      if (warp == (int)(it % kSemWarps)) {
-        mbar_wait(smem_u32(&sm.ready[half]), (uint32_t)((it >> 1) & 1), 700 + half);
-        issue(half, it);
-      }
     };
     SemLoads L0, L1;
     load(L0, 0);
