@@ -1239,19 +1239,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
     const int nka = P.K / 16, nkc = P.N / 16;            // 16-column chunks of A (K) and of C (N)
     uint32_t it_acc = 0;
-    for (long long it = 0; it < my_tiles; ++it) {
-      const long long r = ((long long)blockIdx.x + it * gridDim.x) * 128 + row;
-      const bool valid = r < P.P;
-      const uint32_t dbuf = (uint32_t)(it & 1) * kBufCols, abuf = dbuf ^ kBufCols;
-      // ---- A rows -> bf16 hi/lo -> TMEM (K-step c: hi pairs at columns 16c.., lo pairs at 16c+8..)
-      const float* arow = P.A + r * P.lda;
-      for (int c = hf * (nka / 2); c < (hf + 1) * (nka / 2); ++c) {
-        float v[16];
+    // Loads are batched so that a thread has 16 independent 16-byte loads in flight (round 2 first version: 4 per 16-column chunk,
+    // each chunk's conversion directly behind its loads -- a warp issues in order, so every chunk paid a full memory latency:
+    // ~15 us per 128-row tile).  The first A batch of the NEXT tile and the ReLU mask of this tile (compressed to one bit per
+    // column) are requested before the wait for the accumulator, i.e. under the tile's MMAs.
+    const int cba = hf * (nka / 2), cea = (hf + 1) * (nka / 2);       // this thread's 16-column chunks of A
+    const int cbc = hf * (nkc / 2), cec = (hf + 1) * (nkc / 2);       // ... and of C
+    auto load_batch = [&](float4 (&buf)[16], const float* arow, bool vld, int c0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 t4 = valid ? __ldg(reinterpret_cast<const float4*>(arow + 16 * c) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
-        }
+      for (int i = 0; i < 16; ++i) {
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vld && c0 + (i >> 2) < cea) buf[i] = __ldg(reinterpret_cast<const float4*>(arow + 16 * (c0 + (i >> 2))) + (i & 3));
+      }
+    };
+    auto store_batch = [&](const float4 (&buf)[16], uint32_t abuf, int c0) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (c0 + cc >= cea) break;
+        const float v[16] = {buf[4 * cc].x, buf[4 * cc].y, buf[4 * cc].z, buf[4 * cc].w, buf[4 * cc + 1].x, buf[4 * cc + 1].y, buf[4 * cc + 1].z,
+                             buf[4 * cc + 1].w, buf[4 * cc + 2].x, buf[4 * cc + 2].y, buf[4 * cc + 2].z, buf[4 * cc + 2].w, buf[4 * cc + 3].x,
+                             buf[4 * cc + 3].y, buf[4 * cc + 3].z, buf[4 * cc + 3].w};
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
@@ -1259,24 +1266,71 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
           hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
           lo[j >> 1] = pack_bf16x2(v[j] - __bfloat162float(h0), v[j + 1] - __bfloat162float(h1));
         }
-        tmem_st8(tm_lane + abuf + 16 * c, hi);
-        tmem_st8(tm_lane + abuf + 16 * c + kALo, lo);
+        tmem_st8(tm_lane + abuf + 16 * (c0 + cc), hi);
+        tmem_st8(tm_lane + abuf + 16 * (c0 + cc) + kALo, lo);
+      }
+    };
+    float4 a0[16];                                        // first batch of the tile about to be processed
+    {
+      const long long r0 = (long long)blockIdx.x * 128 + row;
+      load_batch(a0, P.A + r0 * P.lda, my_tiles > 0 && r0 < P.P, cba);
+    }
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long r = ((long long)blockIdx.x + it * gridDim.x) * 128 + row;
+      const bool valid = r < P.P;
+      const uint32_t dbuf = (uint32_t)(it & 1) * kBufCols, abuf = dbuf ^ kBufCols;
+      // ---- A rows -> bf16 hi/lo -> TMEM (K-step c: hi pairs at columns 16c.., lo pairs at 16c+8..)
+      const float* arow = P.A + r * P.lda;
+      store_batch(a0, abuf, cba);
+      for (int c0 = cba + 4; c0 < cea; c0 += 4) {
+        float4 ab[16];
+        load_batch(ab, arow, valid, c0);
+        store_batch(ab, abuf, c0);
       }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(smem_u32(sm.g_ready));
       for (int j = 0; j < kMaxASlabs; ++j) mbar_arrive(smem_u32(&sm.a_ready[j]));
+      // ---- under the MMAs: the ReLU mask of this thread's C columns as bits, then the next tile's first A batch
+      const float* mrow = P.mask ? P.mask + r * P.mask_ld : nullptr;
+      uint32_t mbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};     // bit (c - cbc) * 16 + column
+      if (mrow && valid) {
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {                   // two batches of 16 loads
+          float4 mb[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            mb[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (cbc + 4 * hb + (i >> 2) < cec) mb[i] = __ldg(reinterpret_cast<const float4*>(mrow + 16 * (cbc + 4 * hb + (i >> 2))) + (i & 3));
+          }
+#pragma unroll
+          for (int w2 = 0; w2 < 2; ++w2) {
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 m4 = mb[8 * w2 + i];
+              bits |= (m4.x > 0.f ? 1u : 0u) << (4 * i) | (m4.y > 0.f ? 1u : 0u) << (4 * i + 1) | (m4.z > 0.f ? 1u : 0u) << (4 * i + 2) |
+                      (m4.w > 0.f ? 1u : 0u) << (4 * i + 3);
+            }
+            mbits[2 * hb + w2] = bits;
+          }
+        }
+      }
+      if (it + 1 < my_tiles) {
+        const long long rn = ((long long)blockIdx.x + (it + 1) * gridDim.x) * 128 + row;
+        load_batch(a0, P.A + rn * P.lda, rn < P.P, cba);
+      }
       mbar_wait(smem_u32(sm.acc_full), it_acc & 1u, 600);
       ++it_acc;
       tc_fence_after();
       // ---- epilogue: D -> (+bias) (relu) (mask) (+C) -> global
       float* crow = P.C + r * P.ldc;
-      const float* mrow = P.mask ? P.mask + r * P.mask_ld : nullptr;
-      for (int c = hf * (nkc / 2); c < (hf + 1) * (nkc / 2); ++c) {
+      for (int c = cbc; c < cec; ++c) {
         uint32_t vr[16];
         tmem_ld16(tm_lane + dbuf + 16 * c, vr);
         tmem_wait_ld_fence16(vr);
         if (!valid) continue;
+        const uint32_t mword = mbits[(c - cbc) >> 1] >> (16 * ((c - cbc) & 1));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float x[4];
@@ -1285,13 +1339,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
             x[i] = __uint_as_float(vr[4 * q + i]);
             if (P.bias) x[i] += __ldg(&P.bias[16 * c + 4 * q + i]);
             if (P.relu) x[i] = fmaxf(x[i], 0.f);
-          }
-          if (mrow) {
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + 16 * c) + q);
-            if (!(m4.x > 0.f)) x[0] = 0.f;
-            if (!(m4.y > 0.f)) x[1] = 0.f;
-            if (!(m4.z > 0.f)) x[2] = 0.f;
-            if (!(m4.w > 0.f)) x[3] = 0.f;
+            if (!((mword >> (4 * q + i)) & 1u)) x[i] = 0.f;
           }
           float4* dst = reinterpret_cast<float4*>(crow + 16 * c) + q;
           if (P.accumulate) { const float4 o = *dst; x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
