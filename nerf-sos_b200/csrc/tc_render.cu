@@ -1237,71 +1237,85 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
   } else {
     const int q4 = warp & 3, hf = warp >> 2, row = q4 * 32 + lane;
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
-    const int nka = P.K / 16, nkc = P.N / 16;            // 16-column chunks of A (K) and of C (N)
     uint32_t it_acc = 0;
-    // Loads are batched so that a thread has 16 independent 16-byte loads in flight (round 2 first version: 4 per 16-column chunk,
-    // each chunk's conversion directly behind its loads -- a warp issues in order, so every chunk paid a full memory latency:
-    // ~15 us per 128-row tile).  The first A batch of the NEXT tile and the ReLU mask of this tile (compressed to one bit per
-    // column) are requested before the wait for the accumulator, i.e. under the tile's MMAs.
-    const int cba = hf * (nka / 2), cea = (hf + 1) * (nka / 2);       // this thread's 16-column chunks of A
-    const int cbc = hf * (nkc / 2), cec = (hf + 1) * (nkc / 2);       // ... and of C
-    auto load_batch = [&](float4 (&buf)[16], const float* arow, bool vld, int c0) {
+    // Row-major operands, row-owning threads: a thread owns a ROW of the tile (its TMEM lane), so direct 16-byte accesses of a warp
+    // touch 32 different 128-byte lines each (8192 L1 tag cycles per operand and tile where 1024 do).  Every 64-column slab of A and
+    // of C therefore passes through a 32 KB staging image in shared memory (the gamma tile's space, unused here): warps move whole
+    // rows between global and shared memory (one row = 256 bytes per 16 lanes), lanes pick up / drop their own row from the image.
+    // Image: row r at r*256 bytes, its 16-byte unit u at ((u ^ (r & 15)) << 4): both access patterns are conflict-free.
+    // Loads are issued ahead: slab j+1 of A while slab j is converted, slab 0 of the next tile and the ReLU mask (one bit per
+    // column) under the tile's MMAs.
+    const int t = threadIdx.x;                                   // 0..255: the worker warps are warps 0..7
+    uint8_t* S = sm.g_hi;                                        // 32 KB: g_hi and g_lo are adjacent
+    const int nsa = P.K / 64, nsc = P.N / 64;
+    const long long tile0 = (long long)blockIdx.x * 128;
+    // cooperative piece i of this thread: row (t + 256 i) >> 4 of the tile, unit (t & 15)
+    auto g2r = [&](float4 (&buf)[8], const float* base, long long ld, long long trow0, int col0) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 8; ++i) {
+        const long long rr = trow0 + ((t + 256 * i) >> 4);
         buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vld && c0 + (i >> 2) < cea) buf[i] = __ldg(reinterpret_cast<const float4*>(arow + 16 * (c0 + (i >> 2))) + (i & 3));
+        if (rr < P.P) buf[i] = __ldg(reinterpret_cast<const float4*>(base + rr * ld + col0) + (t & 15));
       }
     };
-    auto store_batch = [&](const float4 (&buf)[16], uint32_t abuf, int c0) {
+    auto r2s = [&](const float4 (&buf)[8]) {
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        if (c0 + cc >= cea) break;
-        const float v[16] = {buf[4 * cc].x, buf[4 * cc].y, buf[4 * cc].z, buf[4 * cc].w, buf[4 * cc + 1].x, buf[4 * cc + 1].y, buf[4 * cc + 1].z,
-                             buf[4 * cc + 1].w, buf[4 * cc + 2].x, buf[4 * cc + 2].y, buf[4 * cc + 2].z, buf[4 * cc + 2].w, buf[4 * cc + 3].x,
-                             buf[4 * cc + 3].y, buf[4 * cc + 3].z, buf[4 * cc + 3].w};
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
-          hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          lo[j >> 1] = pack_bf16x2(v[j] - __bfloat162float(h0), v[j + 1] - __bfloat162float(h1));
-        }
-        tmem_st8(tm_lane + abuf + 16 * (c0 + cc), hi);
-        tmem_st8(tm_lane + abuf + 16 * (c0 + cc) + kALo, lo);
+      for (int i = 0; i < 8; ++i) {
+        const int rr = (t + 256 * i) >> 4;
+        *reinterpret_cast<float4*>(S + rr * 256 + (((t & 15) ^ (rr & 15)) << 4)) = buf[i];
       }
     };
-    float4 a0[16];                                        // first batch of the tile about to be processed
-    {
-      const long long r0 = (long long)blockIdx.x * 128 + row;
-      load_batch(a0, P.A + r0 * P.lda, my_tiles > 0 && r0 < P.P, cba);
-    }
+    const uint8_t* Srow = S + row * 256;
+    auto unit = [&](int u) { return *reinterpret_cast<const float4*>(Srow + ((u ^ (row & 15)) << 4)); };
+    float4 nxt[8];                                               // the slab requested ahead
+    g2r(nxt, P.A, P.lda, tile0, 0);
     for (long long it = 0; it < my_tiles; ++it) {
-      const long long r = ((long long)blockIdx.x + it * gridDim.x) * 128 + row;
+      const long long trow0 = tile0 + it * (long long)gridDim.x * 128;
+      const long long r = trow0 + row;
       const bool valid = r < P.P;
       const uint32_t dbuf = (uint32_t)(it & 1) * kBufCols, abuf = dbuf ^ kBufCols;
-      // ---- A rows -> bf16 hi/lo -> TMEM (K-step c: hi pairs at columns 16c.., lo pairs at 16c+8..)
-      const float* arow = P.A + r * P.lda;
-      store_batch(a0, abuf, cba);
-      for (int c0 = cba + 4; c0 < cea; c0 += 4) {
-        float4 ab[16];
-        load_batch(ab, arow, valid, c0);
-        store_batch(ab, abuf, c0);
+      // ---- A slabs -> staging image -> this thread's row, columns [32 hf, 32 hf + 32) of the slab -> bf16 hi/lo -> TMEM
+      for (int j = 0; j < nsa; ++j) {
+        r2s(nxt);
+        if (j + 1 < nsa) g2r(nxt, P.A, P.lda, trow0, 64 * (j + 1));
+        named_bar_sync(1, kWorkers);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t4 = unit(8 * hf + 4 * cc + q);
+            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int k2 = 0; k2 < 16; k2 += 2) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[k2]), h1 = __float2bfloat16_rn(v[k2 + 1]);
+            hi[k2 >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[k2 >> 1] = pack_bf16x2(v[k2] - __bfloat162float(h0), v[k2 + 1] - __bfloat162float(h1));
+          }
+          const int c = 4 * j + 2 * hf + cc;                     // 16-column K-step chunk of A
+          tmem_st8(tm_lane + abuf + 16 * c, hi);
+          tmem_st8(tm_lane + abuf + 16 * c + kALo, lo);
+        }
+        named_bar_sync(1, kWorkers);                             // the image is free again
       }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(smem_u32(sm.g_ready));
       for (int j = 0; j < kMaxASlabs; ++j) mbar_arrive(smem_u32(&sm.a_ready[j]));
-      // ---- under the MMAs: the ReLU mask of this thread's C columns as bits, then the next tile's first A batch
+      // ---- under the MMAs: the ReLU mask of this thread's C columns (slab j: [64 j + 32 hf, +32)) as bits, the next tile's slab 0
       const float* mrow = P.mask ? P.mask + r * P.mask_ld : nullptr;
-      uint32_t mbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};     // bit (c - cbc) * 16 + column
+      uint32_t mbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};     // word j: the 32 columns of slab j
       if (mrow && valid) {
 #pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {                   // two batches of 16 loads
+        for (int hb = 0; hb < 2; ++hb) {                         // two batches of 16 loads (slabs 2 hb, 2 hb + 1)
           float4 mb[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             mb[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (cbc + 4 * hb + (i >> 2) < cec) mb[i] = __ldg(reinterpret_cast<const float4*>(mrow + 16 * (cbc + 4 * hb + (i >> 2))) + (i & 3));
+            const int j = 2 * hb + (i >> 3);
+            if (j < nsc) mb[i] = __ldg(reinterpret_cast<const float4*>(mrow + 64 * j + 32 * hf) + (i & 7));
           }
 #pragma unroll
           for (int w2 = 0; w2 < 2; ++w2) {
@@ -1316,35 +1330,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
           }
         }
       }
-      if (it + 1 < my_tiles) {
-        const long long rn = ((long long)blockIdx.x + (it + 1) * gridDim.x) * 128 + row;
-        load_batch(a0, P.A + rn * P.lda, rn < P.P, cba);
-      }
+      if (it + 1 < my_tiles) g2r(nxt, P.A, P.lda, trow0 + (long long)gridDim.x * 128, 0);
       mbar_wait(smem_u32(sm.acc_full), it_acc & 1u, 600);
       ++it_acc;
       tc_fence_after();
-      // ---- epilogue: D -> (+bias) (relu) (mask) (+C) -> global
-      float* crow = P.C + r * P.ldc;
-      for (int c = cbc; c < cec; ++c) {
-        uint32_t vr[16];
-        tmem_ld16(tm_lane + dbuf + 16 * c, vr);
-        tmem_wait_ld_fence16(vr);
-        if (!valid) continue;
-        const uint32_t mword = mbits[(c - cbc) >> 1] >> (16 * ((c - cbc) & 1));
+      // ---- epilogue per 64-column slab: D -> (+bias) (relu) (mask) -> staging image -> whole rows (+C) -> global
+      for (int j = 0; j < nsc; ++j) {
+        const uint32_t mword = j == 0 ? mbits[0] : j == 1 ? mbits[1] : j == 2 ? mbits[2] : mbits[3];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float x[4];
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 4 * j + 2 * hf + cc;                     // 16-column chunk of D
+          uint32_t vr[16];
+          tmem_ld16(tm_lane + dbuf + 16 * c, vr);
+          tmem_wait_ld_fence16(vr);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            x[i] = __uint_as_float(vr[4 * q + i]);
-            if (P.bias) x[i] += __ldg(&P.bias[16 * c + 4 * q + i]);
-            if (P.relu) x[i] = fmaxf(x[i], 0.f);
-            if (!((mword >> (4 * q + i)) & 1u)) x[i] = 0.f;
+          for (int q = 0; q < 4; ++q) {
+            float x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              x[i] = __uint_as_float(vr[4 * q + i]);
+              if (P.bias) x[i] += __ldg(&P.bias[16 * c + 4 * q + i]);
+              if (P.relu) x[i] = fmaxf(x[i], 0.f);
+              if (!((mword >> (16 * cc + 4 * q + i)) & 1u)) x[i] = 0.f;
+            }
+            *reinterpret_cast<float4*>(S + row * 256 + (((8 * hf + 4 * cc + q) ^ (row & 15)) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
           }
-          float4* dst = reinterpret_cast<float4*>(crow + 16 * c) + q;
-          if (P.accumulate) { const float4 o = *dst; x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
-          *dst = make_float4(x[0], x[1], x[2], x[3]);
         }
+        named_bar_sync(1, kWorkers);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = (t + 256 * i) >> 4;
+          const long long gr = trow0 + rr;
+          if (gr < P.P) {
+            float4 o = *reinterpret_cast<const float4*>(S + rr * 256 + (((t & 15) ^ (rr & 15)) << 4));
+            float4* dst = reinterpret_cast<float4*>(P.C + gr * P.ldc + 64 * j) + (t & 15);
+            if (P.accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            *dst = o;
+          }
+        }
+        named_bar_sync(1, kWorkers);                             // the image is free again
       }
       tc_fence_before();
       named_bar_sync(1, kWorkers);          // every worker is done with D(it) before anyone refills that buffer as A(it+1)
@@ -1556,7 +1580,7 @@ int tc_mlp_query_dir(const NsosNetDesc& net, const void* packed, const float* pt
 // C[P,N] (=|+=) epi(A[P,K] . B),  B(k,n) = B[k*b_rs + n*b_cs].  scratch: >= tc_rowgemm_scratch_bytes(K, N).
 size_t tc_rowgemm_scratch_bytes(int K, int N) { return (size_t)((K + 63) / 64) * 2 * N * 128 + 1024; }
 bool tc_rowgemm_supported(int K, int N, int64_t lda, int64_t ldc, int64_t mask_ld) {
-  return K >= 64 && K <= 256 && K % 32 == 0 && N >= 32 && N <= 256 && N % 32 == 0 && lda % 4 == 0 && ldc % 4 == 0 && mask_ld % 4 == 0;
+  return K >= 64 && K <= 256 && K % 64 == 0 && N >= 64 && N <= 256 && N % 64 == 0 && lda % 4 == 0 && ldc % 4 == 0 && mask_ld % 4 == 0;
 }
 int tc_rowgemm(const float* A, int64_t lda, int K, const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int N,
                const float* mask, int64_t mask_ld, const float* bias, int relu, int accumulate, int64_t P, void* scratch,
