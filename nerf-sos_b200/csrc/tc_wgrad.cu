@@ -567,6 +567,212 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen(const __grid_consta
   if (warp == kWgMmaWarp) tmem_dealloc(tm, kWgTmemCols);
 }
 
+
+// ---- k_wgrad_gen, second version: rows staged through shared memory with cp.async ---------------------------------------------
+// k_wgrad_gen's fill threads own a POINT (a row of the row-major operands), so each of their 16-byte loads touches 32 different
+// 128-byte lines per warp instruction: 6 k L1 tag cycles per 64-point slab against 2 k cycles of MMAs, and the loads of a slab are
+// only requested once the previous slab has been converted.  Here the operands of a 32-point HALF slab (main 1 KB + dY 512 B +
+// aux 256 B per point) are copied by all 256 fill threads with coalesced 16-byte cp.async (a warp instruction = 512 contiguous
+// bytes of one row, zero-filled beyond P) into a staging image of pitch kStRow = 1808 bytes (113 16-byte units: unit c of row r
+// sits in bank group (r + c) mod 8, so lanes that read the same unit of consecutive rows do not conflict).  Two images: while
+// half u is converted, half u+1 is in flight; the request for half u+2 goes out as soon as every thread has picked its values up.
+// A lane converts TWO points of four features at a time (cvt.rn.bf16x2: one 32-bit word of a K-major tile row per plane, no
+// shuffles).  The contraction runs over points, so their order inside a half is free as long as A and B agree: K position 2m
+// holds staging row m, 2m+1 row m+16 (rows m / m+16 of consecutive lanes are conflict-free; 2m / 2m+1 would be 2-way).
+// Lanes 0-15 write tile rows 8k..8k+3, lanes 16-31 rows 8k+4..8k+7 of the same 16 words: their swizzled chunks differ in bit 2,
+// all 32 banks.  Tiles are filled and consumed per half (K-steps 0-1 / 2-3) with a ready / done barrier pair each, like k_sem_wgrad.
+constexpr int kStRow = 1808, kStDy = 1024, kStAux = 1536;
+constexpr int kStHalf = 32 * kStRow;
+struct WgGen2Smem {
+  uint8_t *a[2], *b[2], *st[2];
+  uint64_t *ready, *done;       // [2] each: one pair per half
+  uint32_t* tmem_ptr;
+};
+__host__ __device__ inline size_t wgg2_carve(uint8_t* base, WgGen2Smem* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; size_t o = off; off += bytes; return o; };
+  size_t oa[2], ob[2], os[2];
+  for (int p = 0; p < 2; ++p) oa[p] = take(kRowsA * 128, 1024);
+  for (int p = 0; p < 2; ++p) ob[p] = take(kRowsB * 128, 1024);
+  for (int p = 0; p < 2; ++p) os[p] = take(kStHalf, 16);
+  size_t obar = take(32, 8), otp = take(16, 16);
+  if (s) {
+    for (int p = 0; p < 2; ++p) { s->a[p] = base + oa[p]; s->b[p] = base + ob[p]; s->st[p] = base + os[p]; }
+    s->ready = (uint64_t*)(base + obar); s->done = s->ready + 2; s->tmem_ptr = (uint32_t*)(base + otp);
+  }
+  return off;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {     // src_bytes 0: 16 zero bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// four features x two points -> four words per plane; toff[i] = byte offset of tile row (8k + 4g + i)'s word inside 8-row group 0
+__device__ __forceinline__ void put_quad(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t grp_off, const uint32_t (&toff)[4], float4 xa, float4 xb) {
+  uint32_t hi, lo;
+  split_pair_bf16(make_float2(xa.x, xb.x), hi, lo);
+  *reinterpret_cast<uint32_t*>(hi_tile + grp_off + toff[0]) = hi; *reinterpret_cast<uint32_t*>(lo_tile + grp_off + toff[0]) = lo;
+  split_pair_bf16(make_float2(xa.y, xb.y), hi, lo);
+  *reinterpret_cast<uint32_t*>(hi_tile + grp_off + toff[1]) = hi; *reinterpret_cast<uint32_t*>(lo_tile + grp_off + toff[1]) = lo;
+  split_pair_bf16(make_float2(xa.z, xb.z), hi, lo);
+  *reinterpret_cast<uint32_t*>(hi_tile + grp_off + toff[2]) = hi; *reinterpret_cast<uint32_t*>(lo_tile + grp_off + toff[2]) = lo;
+  split_pair_bf16(make_float2(xa.w, xb.w), hi, lo);
+  *reinterpret_cast<uint32_t*>(hi_tile + grp_off + toff[3]) = hi; *reinterpret_cast<uint32_t*>(lo_tile + grp_off + toff[3]) = lo;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen2(const __grid_constant__ WgGenParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  WgGen2Smem sm;
+  wgg2_carve(base, &sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+  const int m0 = blockIdx.y * 128;
+  const long long nslabs = (P.P + kSlabPts - 1) / kSlabPts;
+  const long long my_slabs = (nslabs - blockIdx.x + gridDim.x - 1) / gridDim.x;     // >= 1 (grid.x <= nslabs)
+  const long long nunits = 2 * my_slabs;                                            // 32-point halves
+  const bool has_main = P.main != nullptr, has_aux = P.aux != nullptr || P.db != nullptr;     // the bias column lives in the aux block
+  if (t == 0) {
+    for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(sm.ready + h), kWgWorkers); mbar_init(smem_u32(sm.done + h), 1); }
+    fence_mbar_init();
+  }
+  if (warp == kWgMmaWarp) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *sm.tmem_ptr;
+
+  if (warp == kWgMmaWarp) {
+    const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])};
+    const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64);
+    for (long long u = 0; u < nunits; ++u) {
+      const int h = (int)(u & 1);
+      mbar_wait(smem_u32(sm.ready + h), (uint32_t)((u >> 1) & 1), 731);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;     // hi.hi, lo.hi, hi.lo
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const int ks = 2 * h + k2;                                      // K-steps of this half
+            const uint32_t acc = (u > 0 || pass > 0 || k2 > 0) ? 1u : 0u;
+            const uint64_t da = make_sw128_desc(a[pa] + ks * 32);
+            if (has_main) umma_ss(tm + kColD1, da, make_sw128_desc(b[pb] + ks * 32), id256, acc);
+            if (has_aux) umma_ss(tm + kColD1b, da, make_sw128_desc(b[pb] + 256 * 128 + ks * 32), id64, acc);
+          }
+        }
+        umma_commit(smem_u32(sm.done + h));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int m = lane & 15, g = lane >> 4, e = warp;        // point pair (staging rows m, m+16), tile-row half, feature eighth
+    const bool aux_rows = P.aux != nullptr;
+    // requests of half u: thread t moves unit (t + 256 i) of the main / dY / aux block (64 / 32 / 16 units per row)
+    auto request = [&](long long u) {
+      if (u < nunits) {
+        const long long p0 = ((long long)blockIdx.x + (u >> 1) * gridDim.x) * kSlabPts + 32 * (u & 1);
+        const uint32_t S = smem_u32(sm.st[0]) + (uint32_t)(u & 1) * kStHalf;       // the two images are adjacent
+        if (has_main) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = t + 256 * i, r = idx >> 6, c = idx & 63;
+            const long long p = p0 + r;
+            const bool v = p < P.P;
+            cp_async16(S + r * kStRow + 16 * c, P.main + (v ? p : 0) * P.ld_main + 4 * c, v ? 16u : 0u);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = t + 256 * i, r = idx >> 5, c = idx & 31;
+          const long long p = p0 + r;
+          const bool v = p < P.P;
+          cp_async16(S + r * kStRow + kStDy + 16 * c, P.dY + (v ? p : 0) * P.ldy + m0 + 4 * c, v ? 16u : 0u);
+        }
+        if (aux_rows) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int idx = t + 256 * i, r = idx >> 4, c = idx & 15;
+            const long long p = p0 + r;
+            const bool v = p < P.P;
+            cp_async16(S + r * kStRow + kStAux + 16 * c, P.aux + (v ? p : 0) * P.ld_aux + 4 * c, v ? 16u : 0u);
+          }
+        }
+      }
+      cp_async_commit();             // (an empty group past the end keeps the group count uniform)
+    };
+    request(0);
+    request(1);
+    for (long long u = 0; u < nunits; ++u) {
+      const int h = (int)(u & 1);
+      const long long it = u >> 1;
+      cp_async_wait_but_one();                               // this thread's pieces of half u have landed
+      named_bar_sync(1, kWgWorkers);                         // ... and everybody else's
+      const uint8_t* ra = sm.st[0] + h * kStHalf + m * kStRow + 16 * g;    // rows m / m+16; the lane's 16-byte unit of an 8-feature group: 2k + g
+      const uint8_t* rb = ra + 16 * kStRow;
+      float4 xa[7], xb[7];                                   // 4 main groups, 2 dY groups, 1 aux group of this warp
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xa[k] = *reinterpret_cast<const float4*>(ra + 32 * (4 * e + k));
+        xb[k] = *reinterpret_cast<const float4*>(rb + 32 * (4 * e + k));
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        xa[4 + k] = *reinterpret_cast<const float4*>(ra + kStDy + 32 * (2 * e + k));
+        xb[4 + k] = *reinterpret_cast<const float4*>(rb + kStDy + 32 * (2 * e + k));
+      }
+      xa[6] = *reinterpret_cast<const float4*>(ra + kStAux + 32 * e);
+      xb[6] = *reinterpret_cast<const float4*>(rb + kStAux + 32 * e);
+      named_bar_sync(1, kWgWorkers);                         // the image is free again
+      request(u + 2);
+      if (has_aux) {                                         // aux features 8e + 4g + i: zero beyond aux_w, constant one in feature 63
+        const long long p0 = ((long long)blockIdx.x + it * gridDim.x) * kSlabPts + 32 * h;
+        const int f0 = 8 * e + 4 * g;
+        float va[4] = {xa[6].x, xa[6].y, xa[6].z, xa[6].w}, vb[4] = {xb[6].x, xb[6].y, xb[6].z, xb[6].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!aux_rows || f0 + i >= P.aux_w) { va[i] = 0.f; vb[i] = 0.f; }
+          if (P.db && f0 + i == 63) { va[i] = (p0 + m < P.P) ? 1.f : 0.f; vb[i] = (p0 + m + 16 < P.P) ? 1.f : 0.f; }
+        }
+        xa[6] = make_float4(va[0], va[1], va[2], va[3]);
+        xb[6] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+      }
+      if (it > 0) { mbar_wait(smem_u32(sm.done + h), (uint32_t)((it - 1) & 1), 741); tc_fence_after(); }
+      uint32_t toff[4];                                      // word (16 h + m) of tile rows 4g + i inside an 8-row group
+#pragma unroll
+      for (int i = 0; i < 4; ++i) toff[i] = (uint32_t)((4 * g + i) * 128 + ((((4 * h + (m >> 2)) ^ (4 * g + i)) << 4) + ((m & 3) << 2)));
+      if (has_main) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) put_quad(sm.b[0], sm.b[1], (uint32_t)(4 * e + k) * 1024u, toff, xa[k], xb[k]);
+      }
+      if (has_aux) put_quad(sm.b[0], sm.b[1], (uint32_t)(32 + e) * 1024u, toff, xa[6], xb[6]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) put_quad(sm.a[0], sm.a[1], (uint32_t)(2 * e + k) * 1024u, toff, xa[4 + k], xb[4 + k]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(smem_u32(sm.ready + h));
+    }
+    // ---- epilogue: TMEM partial sums -> this CTA's slice of the scratch buffer (column-major; rows >= Mo - m0 are never read)
+    for (int h = 0; h < 2; ++h) mbar_wait(smem_u32(sm.done + h), (uint32_t)((my_slabs - 1) & 1), 751);
+    tc_fence_after();
+    const int q4 = warp & 3, hf = warp >> 2;
+    const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
+    for (int c = hf * 10; c < hf * 10 + 10; ++c) {
+      if (c < 16 ? !has_main : !has_aux) continue;
+      uint32_t r[16];
+      tmem_ld16(tm_lane + kColD1 + c * 16, r);
+      tmem_wait_ld_fence16(r);
+      float* part = P.part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kPartFloatsPerCta + (q4 * 32 + lane);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) part[(size_t)(c * 16 + j) * kPartRows] = __uint_as_float(r[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWgMmaWarp) tmem_dealloc(tm, kWgTmemCols);
+}
+
 }  // namespace
 
 bool sem_saves_blocked(const NetGeom& gc, const NetGeom& gf) {
@@ -642,8 +848,17 @@ int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_
   const size_t need = wgg_carve(nullptr, nullptr) + 1024;
   p.part = (float*)part;
   NSOS_REQUIRE(mb >= 1 && mb <= 2, NSOS_ERR_UNSUPPORTED, "tc_wgrad_gen: at most 256 output rows");
-  NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-  k_wgrad_gen<<<dim3(gx, mb), kWgThreads, need, st>>>(p);
+  // second version (rows staged with cp.async): needs 16-byte aligned rows of every operand and full 64-float aux rows
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool v2 = !getenv("NSOS_WGRAD_V1") && al16(dY) && (!main || al16(main)) && (!p.aux || (al16(p.aux) && ld_aux % 4 == 0 && ld_aux >= 64));
+  if (v2) {
+    const size_t need2 = wgg2_carve(nullptr, nullptr) + 1024;
+    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_gen2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need2));
+    k_wgrad_gen2<<<dim3(gx, mb), kWgThreads, need2, st>>>(p);
+  } else {
+    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    k_wgrad_gen<<<dim3(gx, mb), kWgThreads, need, st>>>(p);
+  }
   WgReduceParams r;
   memset(&r, 0, sizeof(r));
   r.part = p.part; r.ncta = gx;
