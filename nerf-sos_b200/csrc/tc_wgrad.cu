@@ -586,6 +586,7 @@ constexpr int kStHalf = 32 * kStRow;
 struct WgGen2Smem {
   uint8_t *a[2], *b[2], *st[2];
   uint64_t *ready, *done;       // [2] each: one pair per half
+  uint64_t *full, *empty;       // [2] each: staging images (loader-warp variant)
   uint32_t* tmem_ptr;
 };
 __host__ __device__ inline size_t wgg2_carve(uint8_t* base, WgGen2Smem* s) {
@@ -595,15 +596,19 @@ __host__ __device__ inline size_t wgg2_carve(uint8_t* base, WgGen2Smem* s) {
   for (int p = 0; p < 2; ++p) oa[p] = take(kRowsA * 128, 1024);
   for (int p = 0; p < 2; ++p) ob[p] = take(kRowsB * 128, 1024);
   for (int p = 0; p < 2; ++p) os[p] = take(kStHalf, 16);
-  size_t obar = take(32, 8), otp = take(16, 16);
+  size_t obar = take(64, 8), otp = take(16, 16);
   if (s) {
     for (int p = 0; p < 2; ++p) { s->a[p] = base + oa[p]; s->b[p] = base + ob[p]; s->st[p] = base + os[p]; }
-    s->ready = (uint64_t*)(base + obar); s->done = s->ready + 2; s->tmem_ptr = (uint32_t*)(base + otp);
+    s->ready = (uint64_t*)(base + obar); s->done = s->ready + 2; s->full = s->ready + 4; s->empty = s->ready + 6;
+    s->tmem_ptr = (uint32_t*)(base + otp);
   }
   return off;
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {     // src_bytes 0: 16 zero bytes
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {       // the arrival is one of the barrier's expected count (noinc)
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -621,7 +626,16 @@ __device__ __forceinline__ void put_quad(uint8_t* hi_tile, uint8_t* lo_tile, uin
   *reinterpret_cast<uint32_t*>(hi_tile + grp_off + toff[3]) = hi; *reinterpret_cast<uint32_t*>(lo_tile + grp_off + toff[3]) = lo;
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen2(const __grid_constant__ WgGenParams P) {
+// NW fill warps (8 or 16: warp e converts the feature groups [e*32/NW, (e+1)*32/NW) of main, e*16/NW.. of dY and, for e < 8, aux
+// group e) + the issuer warp.  With 16 warps every scheduler has four fill warps to choose from instead of two.
+// NL = 0: the fill threads request the next halves themselves (cp.async groups + named barriers).  NL = 4: four LOADER warps own
+// the requests and hand the images over through mbarriers (full: cp.async.mbarrier.arrive of the loader threads; empty: the fill
+// threads after their reads) -- no fill thread then has copies in flight when it executes fence.proxy.async (MEMBAR.ALL.CTA in
+// SASS) at the end of a half.
+template <int NW, int NL>
+__global__ void __launch_bounds__(32 * (NW + 1 + NL), 1) k_wgrad_gen2(const __grid_constant__ WgGenParams P) {
+  constexpr int NT = 32 * NW, GM = 32 / NW, GD = 16 / NW;
+  constexpr int RT = NL ? 32 * NL : NT;                      // threads that issue the requests
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   WgGen2Smem sm;
@@ -633,16 +647,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen2(const __grid_const
   const long long nunits = 2 * my_slabs;                                            // 32-point halves
   const bool has_main = P.main != nullptr, has_aux = P.aux != nullptr || P.db != nullptr;     // the bias column lives in the aux block
   if (t == 0) {
-    for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(sm.ready + h), kWgWorkers); mbar_init(smem_u32(sm.done + h), 1); }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(smem_u32(sm.ready + h), NT); mbar_init(smem_u32(sm.done + h), 1);
+      mbar_init(smem_u32(sm.full + h), RT); mbar_init(smem_u32(sm.empty + h), NT);
+    }
     fence_mbar_init();
   }
-  if (warp == kWgMmaWarp) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
+  if (warp == NW) { tmem_alloc(smem_u32(sm.tmem_ptr), kWgTmemCols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *sm.tmem_ptr;
 
-  if (warp == kWgMmaWarp) {
+  if (warp == NW) {
     const uint32_t a[2] = {smem_u32(sm.a[0]), smem_u32(sm.a[1])}, b[2] = {smem_u32(sm.b[0]), smem_u32(sm.b[1])};
     const uint32_t id256 = make_idesc_bf16(256), id64 = make_idesc_bf16(64);
     for (long long u = 0; u < nunits; ++u) {
@@ -667,76 +684,113 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen2(const __grid_const
       __syncwarp();
     }
   } else {
-    const int m = lane & 15, g = lane >> 4, e = warp;        // point pair (staging rows m, m+16), tile-row half, feature eighth
-    const bool aux_rows = P.aux != nullptr;
-    // requests of half u: thread t moves unit (t + 256 i) of the main / dY / aux block (64 / 32 / 16 units per row)
-    auto request = [&](long long u) {
-      if (u < nunits) {
-        const long long p0 = ((long long)blockIdx.x + (u >> 1) * gridDim.x) * kSlabPts + 32 * (u & 1);
-        const uint32_t S = smem_u32(sm.st[0]) + (uint32_t)(u & 1) * kStHalf;       // the two images are adjacent
+    const bool loader = warp > NW;
+    const int rt = NL ? t - 32 * (NW + 1) : t;               // index among the requesting threads
+    const int m = lane & 15, g = lane >> 4, e = warp;        // point pair (staging rows m, m+16), tile-row half, feature share
+    const bool aux_rows = P.aux != nullptr, aux_warp = has_aux && e < 8;
+    // Requests of half u: requesting thread rt moves unit (rt + RT i) of the main / dY / aux block (64 / 32 / 16 units per row): a fixed unit
+    // column and rows RT/64 (RT/32, RT/16) apart, so the addresses are one pointer per block that advances by a constant.
+    const int rm = rt >> 6, rd = rt >> 5, rx = rt >> 4;         // first row of this thread in each block
+    const uint32_t dm = (uint32_t)(rm * kStRow + 16 * (rt & 63)), dd = (uint32_t)(rd * kStRow + kStDy + 16 * (rt & 31)),
+                   dx = (uint32_t)(rx * kStRow + kStAux + 16 * (rt & 15));
+    const float* const bm = has_main ? P.main + 4 * (rt & 63) : nullptr;
+    const float* const bd = P.dY + m0 + 4 * (rt & 31);
+    const float* const bx = aux_rows ? P.aux + 4 * (rt & 15) : nullptr;
+    const uint32_t S0 = smem_u32(sm.st[0]);
+    // halves are requested in order, so the request state is carried along: next half, its first point, one source pointer per
+    // block.  Rows beyond P are zero-filled (source size 0: nothing is read through the pointer).
+    long long rq_u = 0, rq_p0 = (long long)blockIdx.x * kSlabPts;
+    const int step_odd = (int)gridDim.x * kSlabPts - 32;     // points from an odd half to the next even one (pitches < 2^16: products fit 32 bits)
+    const int em[2] = {32 * (int)P.ld_main, step_odd * (int)P.ld_main}, ed[2] = {32 * (int)P.ldy, step_odd * (int)P.ldy},
+              ex[2] = {32 * (int)P.ld_aux, step_odd * (int)P.ld_aux};
+    const float* pm = bm + (rq_p0 + rm) * P.ld_main;
+    const float* pd = bd + (rq_p0 + rd) * P.ldy;
+    const float* px = bx + (rq_p0 + rx) * P.ld_aux;
+    auto request = [&]() {
+      if (rq_u < nunits) {
+        const long long left = P.P - rq_p0;
+        const int nv = left < 32 ? (left < 0 ? 0 : (int)left) : 32;                   // valid rows of this half
+        const uint32_t S = S0 + (uint32_t)(rq_u & 1) * kStHalf;                       // the two images are adjacent
         if (has_main) {
+          const float* src = pm;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int idx = t + 256 * i, r = idx >> 6, c = idx & 63;
-            const long long p = p0 + r;
-            const bool v = p < P.P;
-            cp_async16(S + r * kStRow + 16 * c, P.main + (v ? p : 0) * P.ld_main + 4 * c, v ? 16u : 0u);
+          for (int i = 0; i < 2048 / RT; ++i) {
+            cp_async16(S + dm + (uint32_t)((RT / 64) * i * kStRow), src, rm + (RT / 64) * i < nv ? 16u : 0u);
+            src += (RT / 64) * P.ld_main;
           }
         }
+        {
+          const float* src = pd;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = t + 256 * i, r = idx >> 5, c = idx & 31;
-          const long long p = p0 + r;
-          const bool v = p < P.P;
-          cp_async16(S + r * kStRow + kStDy + 16 * c, P.dY + (v ? p : 0) * P.ldy + m0 + 4 * c, v ? 16u : 0u);
+          for (int i = 0; i < 1024 / RT; ++i) {
+            cp_async16(S + dd + (uint32_t)((RT / 32) * i * kStRow), src, rd + (RT / 32) * i < nv ? 16u : 0u);
+            src += (RT / 32) * P.ldy;
+          }
         }
         if (aux_rows) {
+          const float* src = px;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int idx = t + 256 * i, r = idx >> 4, c = idx & 15;
-            const long long p = p0 + r;
-            const bool v = p < P.P;
-            cp_async16(S + r * kStRow + kStAux + 16 * c, P.aux + (v ? p : 0) * P.ld_aux + 4 * c, v ? 16u : 0u);
+          for (int i = 0; i < 512 / RT; ++i) {
+            cp_async16(S + dx + (uint32_t)((RT / 16) * i * kStRow), src, rx + (RT / 16) * i < nv ? 16u : 0u);
+            src += (RT / 16) * P.ld_aux;
           }
         }
       }
-      cp_async_commit();             // (an empty group past the end keeps the group count uniform)
+      if (NL) cp_async_arrive(smem_u32(sm.full + (rq_u & 1)));     // arrives once this thread's copies above have landed
+      else cp_async_commit();        // (an empty group past the end keeps the group count uniform)
+      const bool odd = (rq_u & 1) != 0;
+      rq_p0 += odd ? step_odd : 32; pm += odd ? em[1] : em[0]; pd += odd ? ed[1] : ed[0]; px += odd ? ex[1] : ex[0];
+      ++rq_u;
     };
-    request(0);
-    request(1);
+    if (NL && loader) {
+      for (long long u = 0; u < nunits; ++u) {
+        if (u >= 2) mbar_wait(smem_u32(sm.empty + (u & 1)), (uint32_t)(((u >> 1) - 1) & 1), 761);
+        request();
+      }
+    } else {
+    if (!NL) { request(); request(); }
     for (long long u = 0; u < nunits; ++u) {
       const int h = (int)(u & 1);
       const long long it = u >> 1;
-      cp_async_wait_but_one();                               // this thread's pieces of half u have landed
-      named_bar_sync(1, kWgWorkers);                         // ... and everybody else's
-      const uint8_t* ra = sm.st[0] + h * kStHalf + m * kStRow + 16 * g;    // rows m / m+16; the lane's 16-byte unit of an 8-feature group: 2k + g
+      if (NL) mbar_wait(smem_u32(sm.full + h), (uint32_t)(it & 1), 771);     // the loaders' copies of half u have landed
+      else {
+        cp_async_wait_but_one();                             // this thread's pieces of half u have landed
+        named_bar_sync(1, NT);                               // ... and everybody else's
+      }
+      const uint8_t* ra = sm.st[0] + h * kStHalf + m * kStRow + 16 * g;    // rows m / m+16; the lane's 16-byte unit of 8-feature group k: 2k + g
       const uint8_t* rb = ra + 16 * kStRow;
-      float4 xa[7], xb[7];                                   // 4 main groups, 2 dY groups, 1 aux group of this warp
+      float4 xa[GM + GD + 1], xb[GM + GD + 1];               // GM main groups, GD dY groups, one aux group
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        xa[k] = *reinterpret_cast<const float4*>(ra + 32 * (4 * e + k));
-        xb[k] = *reinterpret_cast<const float4*>(rb + 32 * (4 * e + k));
+      for (int k = 0; k < GM; ++k) {
+        xa[k] = *reinterpret_cast<const float4*>(ra + 32 * (GM * e + k));
+        xb[k] = *reinterpret_cast<const float4*>(rb + 32 * (GM * e + k));
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        xa[4 + k] = *reinterpret_cast<const float4*>(ra + kStDy + 32 * (2 * e + k));
-        xb[4 + k] = *reinterpret_cast<const float4*>(rb + kStDy + 32 * (2 * e + k));
+      for (int k = 0; k < GD; ++k) {
+        xa[GM + k] = *reinterpret_cast<const float4*>(ra + kStDy + 32 * (GD * e + k));
+        xb[GM + k] = *reinterpret_cast<const float4*>(rb + kStDy + 32 * (GD * e + k));
       }
-      xa[6] = *reinterpret_cast<const float4*>(ra + kStAux + 32 * e);
-      xb[6] = *reinterpret_cast<const float4*>(rb + kStAux + 32 * e);
-      named_bar_sync(1, kWgWorkers);                         // the image is free again
-      request(u + 2);
-      if (has_aux) {                                         // aux features 8e + 4g + i: zero beyond aux_w, constant one in feature 63
+      if (aux_warp) {
+        xa[GM + GD] = *reinterpret_cast<const float4*>(ra + kStAux + 32 * e);
+        xb[GM + GD] = *reinterpret_cast<const float4*>(rb + kStAux + 32 * e);
+      }
+      if (NL) mbar_arrive(smem_u32(sm.empty + h));           // the image is free again
+      else {
+        named_bar_sync(1, NT);
+        request();                                           // half u + 2
+      }
+      if (aux_warp) {                                        // aux features 8e + 4g + i: zero beyond aux_w, constant one in feature 63
         const long long p0 = ((long long)blockIdx.x + it * gridDim.x) * kSlabPts + 32 * h;
         const int f0 = 8 * e + 4 * g;
-        float va[4] = {xa[6].x, xa[6].y, xa[6].z, xa[6].w}, vb[4] = {xb[6].x, xb[6].y, xb[6].z, xb[6].w};
+        float va[4] = {xa[GM + GD].x, xa[GM + GD].y, xa[GM + GD].z, xa[GM + GD].w};
+        float vb[4] = {xb[GM + GD].x, xb[GM + GD].y, xb[GM + GD].z, xb[GM + GD].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (!aux_rows || f0 + i >= P.aux_w) { va[i] = 0.f; vb[i] = 0.f; }
           if (P.db && f0 + i == 63) { va[i] = (p0 + m < P.P) ? 1.f : 0.f; vb[i] = (p0 + m + 16 < P.P) ? 1.f : 0.f; }
         }
-        xa[6] = make_float4(va[0], va[1], va[2], va[3]);
-        xb[6] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+        xa[GM + GD] = make_float4(va[0], va[1], va[2], va[3]);
+        xb[GM + GD] = make_float4(vb[0], vb[1], vb[2], vb[3]);
       }
       if (it > 0) { mbar_wait(smem_u32(sm.done + h), (uint32_t)((it - 1) & 1), 741); tc_fence_after(); }
       uint32_t toff[4];                                      // word (16 h + m) of tile rows 4g + i inside an 8-row group
@@ -744,11 +798,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen2(const __grid_const
       for (int i = 0; i < 4; ++i) toff[i] = (uint32_t)((4 * g + i) * 128 + ((((4 * h + (m >> 2)) ^ (4 * g + i)) << 4) + ((m & 3) << 2)));
       if (has_main) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) put_quad(sm.b[0], sm.b[1], (uint32_t)(4 * e + k) * 1024u, toff, xa[k], xb[k]);
+        for (int k = 0; k < GM; ++k) put_quad(sm.b[0], sm.b[1], (uint32_t)(GM * e + k) * 1024u, toff, xa[k], xb[k]);
       }
-      if (has_aux) put_quad(sm.b[0], sm.b[1], (uint32_t)(32 + e) * 1024u, toff, xa[6], xb[6]);
+      if (aux_warp) put_quad(sm.b[0], sm.b[1], (uint32_t)(32 + e) * 1024u, toff, xa[GM + GD], xb[GM + GD]);
 #pragma unroll
-      for (int k = 0; k < 2; ++k) put_quad(sm.a[0], sm.a[1], (uint32_t)(2 * e + k) * 1024u, toff, xa[4 + k], xb[4 + k]);
+      for (int k = 0; k < GD; ++k) put_quad(sm.a[0], sm.a[1], (uint32_t)(GD * e + k) * 1024u, toff, xa[GM + k], xb[GM + k]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(sm.ready + h));
@@ -756,9 +810,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen2(const __grid_const
     // ---- epilogue: TMEM partial sums -> this CTA's slice of the scratch buffer (column-major; rows >= Mo - m0 are never read)
     for (int h = 0; h < 2; ++h) mbar_wait(smem_u32(sm.done + h), (uint32_t)((my_slabs - 1) & 1), 751);
     tc_fence_after();
+    constexpr int CPW = 20 / (NW / 4);                       // 16-column chunks per warp of a lane quarter
     const int q4 = warp & 3, hf = warp >> 2;
     const uint32_t tm_lane = tm + ((uint32_t)(q4 * 32) << 16);
-    for (int c = hf * 10; c < hf * 10 + 10; ++c) {
+    for (int c = hf * CPW; c < hf * CPW + CPW; ++c) {
       if (c < 16 ? !has_main : !has_aux) continue;
       uint32_t r[16];
       tmem_ld16(tm_lane + kColD1 + c * 16, r);
@@ -767,10 +822,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_gen2(const __grid_const
 #pragma unroll
       for (int j = 0; j < 16; ++j) part[(size_t)(c * 16 + j) * kPartRows] = __uint_as_float(r[j]);
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kWgMmaWarp) tmem_dealloc(tm, kWgTmemCols);
+  if (warp == NW) tmem_dealloc(tm, kWgTmemCols);
 }
 
 }  // namespace
@@ -850,11 +906,18 @@ int tc_wgrad_gen(const float* dY, int64_t ldy, int Mo, const float* main, int64_
   NSOS_REQUIRE(mb >= 1 && mb <= 2, NSOS_ERR_UNSUPPORTED, "tc_wgrad_gen: at most 256 output rows");
   // second version (rows staged with cp.async): needs 16-byte aligned rows of every operand and full 64-float aux rows
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  const bool v2 = !getenv("NSOS_WGRAD_V1") && al16(dY) && (!main || al16(main)) && (!p.aux || (al16(p.aux) && ld_aux % 4 == 0 && ld_aux >= 64));
+  const bool v2 = !getenv("NSOS_WGRAD_V1") && ldy < 65536 && ld_main < 65536 && ld_aux < 65536 && al16(dY) && (!main || al16(main)) && (!p.aux || (al16(p.aux) && ld_aux % 4 == 0 && ld_aux >= 64));
   if (v2) {
     const size_t need2 = wgg2_carve(nullptr, nullptr) + 1024;
-    NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_gen2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need2));
-    k_wgrad_gen2<<<dim3(gx, mb), kWgThreads, need2, st>>>(p);
+    auto go = [&](auto kern, int threads) -> int {
+      NSOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need2));
+      kern<<<dim3(gx, mb), threads, need2, st>>>(p);
+      return NSOS_OK;
+    };
+    const bool w8 = getenv("NSOS_WGRAD_W8") != nullptr, noloader = getenv("NSOS_WGRAD_NOLOADER") != nullptr;
+    int rc = w8 ? (noloader ? go(k_wgrad_gen2<8, 0>, 32 * 9) : go(k_wgrad_gen2<8, 4>, 32 * 13))
+                : (noloader ? go(k_wgrad_gen2<16, 0>, 32 * 17) : go(k_wgrad_gen2<16, 4>, 32 * 21));
+    if (rc) return rc;
   } else {
     NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     k_wgrad_gen<<<dim3(gx, mb), kWgThreads, need, st>>>(p);

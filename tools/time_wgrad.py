@@ -1,6 +1,6 @@
 """Launch time of the general weight-gradient kernel (dW[256, 320] += dY[P, 256]^T . [X[P, 256] | gamma[P, 64]]) on P = 1.5 M
-points (one 8192-ray chunk of the fine net), both versions: NSOS_WGRAD_V1=1 (row-owning threads) and the default (rows staged
-with cp.async).  Also checks that the two agree.  usage: python tools/time_wgrad.py [P]"""
+points (one 8192-ray chunk of the fine net), NSOS_WGRAD_V1=1 (row-owning threads) and the
+cp.async-staged version with 8 / 16 fill warps (NSOS_WGRAD_W8=1), requests by the fill threads (NSOS_WGRAD_NOLOADER=1) or by four loader warps (default).  Also checks that the two agree.  usage: python tools/time_wgrad.py [P]"""
 import os
 import sys
 
@@ -21,11 +21,14 @@ def main():
     scr = torch.empty(L.nsos_selftest_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     res = {}
-    for tag, env, aux_w in (("v1", "1", 0), ("v2", None, 0), ("v1+aux", "1", 63), ("v2+aux", None, 63)):
-        if env:
-            os.environ["NSOS_WGRAD_V1"] = env
-        else:
-            os.environ.pop("NSOS_WGRAD_V1", None)
+    variants = (("v1", ("NSOS_WGRAD_V1",)), ("v2 8w self", ("NSOS_WGRAD_W8", "NSOS_WGRAD_NOLOADER")), ("v2 16w self", ("NSOS_WGRAD_NOLOADER",)),
+                ("v2 8w+4ld", ("NSOS_WGRAD_W8",)), ("v2 16w+4ld", ()))
+    for tag, envs, aux_w in [(n, e, a) for a in (0, 63) for n, e in variants]:
+        tag = tag + ("+aux" if aux_w else "")
+        for k in ("NSOS_WGRAD_V1", "NSOS_WGRAD_W8", "NSOS_WGRAD_NOLOADER"):
+            os.environ.pop(k, None)
+        for k in envs:
+            os.environ[k] = "1"
         dw = torch.zeros(256, 320, device=dev)
         db = torch.zeros(256, device=dev)
         ts = []
@@ -43,12 +46,13 @@ def main():
                 ts.append(e0.elapsed_time(e1))
         ms = sum(ts) / len(ts)
         gb = P * (256 * 4 * 2 + (256 if aux_w else 0)) / 1e9          # algorithmic bytes: dY once, X once (+ gamma)
-        print(f"{tag:7s} {ms:7.3f} ms  {gb / ms:6.2f} TB/s algorithmic  (P = {P})")
+        print(f"{tag:16s} {ms:7.3f} ms  {gb / ms:6.2f} TB/s algorithmic  (P = {P})")
         res[tag] = (dw.clone(), db.clone())
-    for a, b in (("v1", "v2"), ("v1+aux", "v2+aux")):
-        d = (res[a][0] - res[b][0]).abs().max().item() / res[a][0].abs().max().item()
-        dbias = (res[a][1] - res[b][1]).abs().max().item() / max(res[a][1].abs().max().item(), 1e-30)
-        print(f"{a} vs {b}: dW rel diff {d:.2e}, db rel diff {dbias:.2e}")
+    for tag in res:
+        ref = res["v1+aux" if tag.endswith("+aux") else "v1"]
+        d = (ref[0] - res[tag][0]).abs().max().item() / ref[0].abs().max().item()
+        dbias = (ref[1] - res[tag][1]).abs().max().item() / max(ref[1].abs().max().item(), 1e-30)
+        print(f"v1 vs {tag}: dW rel diff {d:.2e}, db rel diff {dbias:.2e}")
 
 
 if __name__ == "__main__":
