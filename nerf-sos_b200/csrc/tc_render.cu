@@ -1191,6 +1191,8 @@ struct RowGemmParams {
   int accumulate, relu;
   long long P;
   int nslots;
+  int mask_rows;              // 1 (default): the row-owning threads read their mask rows themselves under the MMAs; 0 (NSOS_RG_MASK_BITS=1):
+                              // whole rows per half warp, sign bits by ballot through the C image
 };
 // B(k,n) = B[k*b_rs + n*b_cs]  ->  per 64-wide K slab: bf16 hi plane [N x 64] then lo plane, K-major SWIZZLE_128B
 __global__ void k_pack_b_bf16(const float* __restrict__ B, long long b_rs, long long b_cs, int K, int N, uint8_t* __restrict__ out) {
@@ -1207,6 +1209,29 @@ __global__ void k_pack_b_bf16(const float* __restrict__ B, long long b_rs, long 
     *reinterpret_cast<__nv_bfloat16*>(lo + byte) = l;
   }
 }
+// Shared memory of k_rowgemm: the weight ring, FOUR 32 KB staging images (three rotate over the A slabs requested ahead with cp.async,
+// the fourth carries the C slabs of the epilogue), barriers, the issuer's chunk table.
+constexpr int kRgImgBytes = 32768, kRgSlots = 3;
+__host__ __device__ inline size_t carve_rowgemm(uint8_t* base, int nslots, Smem* s, uint8_t** img) {
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; size_t o = off; off += bytes; return o; };
+  size_t o_ring = take((size_t)nslots * kSlotBytes, 1024);
+  size_t o_img = take((size_t)4 * kRgImgBytes, 1024);
+  size_t o_bar = take(sizeof(uint64_t) * (2 * kMaxSlots + 2 + kMaxASlabs), 8), o_tp = take(16, 16);
+  size_t o_ct = take(sizeof(uint32_t) * 2 * kCtabMax, 16);
+  if (s) {
+    *s = Smem{};
+    s->ring = base + o_ring; s->g_hi = base + o_img + 3 * kRgImgBytes; s->g_lo = s->g_hi + kGBytes;
+    s->full = (uint64_t*)(base + o_bar); s->empty = s->full + kMaxSlots; s->acc_full = s->empty + kMaxSlots;
+    s->g_ready = s->acc_full + 1; s->a_ready = s->g_ready + 1; s->tmem_ptr = (uint32_t*)(base + o_tp);
+    s->ctab = (uint32_t*)(base + o_ct);
+    *img = base + o_img;
+  }
+  return off;
+}
+__device__ __forceinline__ void rg_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {     // src_bytes 0: 16 zero bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
 }
@@ -1214,7 +1239,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Smem sm;
-  carve_smem(base, P.nslots, 2, 2, 8, &sm);
+  uint8_t* img0;
+  carve_rowgemm(base, P.nslots, &sm, &img0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   init_pipeline(sm, P.nslots, warp, 1);
   const uint32_t tm = *sm.tmem_ptr;
@@ -1240,51 +1266,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
     uint32_t it_acc = 0;
     // Row-major operands, row-owning threads: a thread owns a ROW of the tile (its TMEM lane), so direct 16-byte accesses of a warp
     // touch 32 different 128-byte lines each (8192 L1 tag cycles per operand and tile where 1024 do).  Every 64-column slab of A and
-    // of C therefore passes through a 32 KB staging image in shared memory (the gamma tile's space, unused here): warps move whole
-    // rows between global and shared memory (one row = 256 bytes per 16 lanes), lanes pick up / drop their own row from the image.
+    // of C therefore passes through a 32 KB staging image in shared memory: warps move whole rows between global and shared memory
+    // (one row = 256 bytes per 16 lanes), lanes pick up / drop their own row from the image.
     // Image: row r at r*256 bytes, its 16-byte unit u at ((u ^ (r & 15)) << 4): both access patterns are conflict-free.
-    // Loads are issued ahead: slab j+1 of A while slab j is converted, slab 0 of the next tile and the ReLU mask (one bit per
-    // column) under the tile's MMAs.
+    // A slabs are requested THREE ahead with cp.async into three rotating images (one commit group per slab, zero fill beyond P):
+    // 96 KB per SM are in flight under the MMAs and the epilogue of the previous tile, and a slab's image is requested again as soon
+    // as it has been converted.  (One slab ahead in registers left ~32 KB in flight per SM: the A fill waited for memory.)
     const int t = threadIdx.x;                                   // 0..255: the worker warps are warps 0..7
-    uint8_t* S = sm.g_hi;                                        // 32 KB: g_hi and g_lo are adjacent
+    uint8_t* S = sm.g_hi;                                        // the C image
     const int nsa = P.K / 64, nsc = P.N / 64;
     const long long tile0 = (long long)blockIdx.x * 128;
-    // cooperative piece i of this thread: row (t + 256 i) >> 4 of the tile, unit (t & 15)
-    auto g2r = [&](float4 (&buf)[8], const float* base, long long ld, long long trow0, int col0) {
+    const long long nslabs_total = my_tiles * nsa;
+    // request state: next slab to request (tile rq_it, slab rq_j), rotating image index
+    long long rq = 0, rq_it = 0;
+    int rq_j = 0, rq_img = 0;
+    const uint32_t img_u32 = smem_u32(img0);
+    auto request = [&]() {
+      if (rq < nslabs_total) {
+        const long long trow = tile0 + rq_it * (long long)gridDim.x * 128;
+        const uint32_t dst0 = img_u32 + (uint32_t)rq_img * kRgImgBytes;
+        const float* src0 = P.A + 64 * rq_j + 4 * (t & 15);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const long long rr = trow0 + ((t + 256 * i) >> 4);
-        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr < P.P) buf[i] = __ldg(reinterpret_cast<const float4*>(base + rr * ld + col0) + (t & 15));
+        for (int i = 0; i < 8; ++i) {
+          const int rr = (t + 256 * i) >> 4;
+          const long long gr = trow + rr;
+          const bool v = gr < P.P;
+          rg_cp_async16(dst0 + (uint32_t)(rr * 256 + (((t & 15) ^ (rr & 15)) << 4)), src0 + (v ? gr : 0) * P.lda, v ? 16u : 0u);
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");        // (an empty group past the end keeps the group count uniform)
+      ++rq;
+      if (++rq_j == nsa) { rq_j = 0; ++rq_it; }
+      if (++rq_img == 3) rq_img = 0;
     };
-    auto r2s = [&](const float4 (&buf)[8]) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = (t + 256 * i) >> 4;
-        *reinterpret_cast<float4*>(S + rr * 256 + (((t & 15) ^ (rr & 15)) << 4)) = buf[i];
-      }
-    };
-    const uint8_t* Srow = S + row * 256;
-    auto unit = [&](int u) { return *reinterpret_cast<const float4*>(Srow + ((u ^ (row & 15)) << 4)); };
-    float4 nxt[8];                                               // the slab requested ahead
-    g2r(nxt, P.A, P.lda, tile0, 0);
+    request(); request(); request();
+    int cur_img = 0;
     for (long long it = 0; it < my_tiles; ++it) {
       const long long trow0 = tile0 + it * (long long)gridDim.x * 128;
       const long long r = trow0 + row;
       const bool valid = r < P.P;
       const uint32_t dbuf = (uint32_t)(it & 1) * kBufCols, abuf = dbuf ^ kBufCols;
-      // ---- A slabs -> staging image -> this thread's row, columns [32 hf, 32 hf + 32) of the slab -> bf16 hi/lo -> TMEM
+      // ---- A slabs: staging image -> this thread's row, columns [32 hf, 32 hf + 32) of the slab -> bf16 hi/lo -> TMEM
       for (int j = 0; j < nsa; ++j) {
-        r2s(nxt);
-        if (j + 1 < nsa) g2r(nxt, P.A, P.lda, trow0, 64 * (j + 1));
-        named_bar_sync(1, kWorkers);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");     // this thread's pieces of the slab have landed
+        named_bar_sync(1, kWorkers);                             // ... and everybody else's
+        const uint8_t* Srow = img0 + cur_img * kRgImgBytes + row * 256;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           float v[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 t4 = unit(8 * hf + 4 * cc + q);
+            const float4 t4 = *reinterpret_cast<const float4*>(Srow + (((8 * hf + 4 * cc + q) ^ (row & 15)) << 4));
             v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
           }
           uint32_t hi[8], lo[8];
@@ -1299,6 +1331,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
           tmem_st8(tm_lane + abuf + 16 * c + kALo, lo);
         }
         named_bar_sync(1, kWorkers);                             // the image is free again
+        request();                                               // three slabs ahead, into the image just read
+        if (++cur_img == 3) cur_img = 0;
       }
       tmem_wait_st();
       tc_fence_before();
@@ -1307,7 +1341,49 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
       // ---- under the MMAs: the ReLU mask of this thread's C columns (slab j: [64 j + 32 hf, +32)) as bits, the next tile's slab 0
       const float* mrow = P.mask ? P.mask + r * P.mask_ld : nullptr;
       uint32_t mbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};     // word j: the 32 columns of slab j
-      if (mrow && valid) {
+      if (P.mask && !P.mask_rows) {
+        // Whole rows per half warp (a warp instruction = two rows x 256 bytes), one ballot per vector component: the 16 sign bits of
+        // a row's units land in the C image (free until the epilogue), 8 bytes per row and slab, and every thread picks its row up.
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {                         // two batches of 16 loads (slabs 2 hb, 2 hb + 1)
+          float4 mb[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            mb[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            const int j = 2 * hb + (i >> 3);
+            const long long gr = trow0 + ((t + 256 * (i & 7)) >> 4);
+            if (j < nsc && gr < P.P) mb[i] = __ldg(reinterpret_cast<const float4*>(P.mask + gr * P.mask_ld + 64 * j) + (t & 15));
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int j = 2 * hb + (i >> 3), rr = (t + 256 * (i & 7)) >> 4;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, mb[i].x > 0.f), b1 = __ballot_sync(0xffffffffu, mb[i].y > 0.f),
+                           b2 = __ballot_sync(0xffffffffu, mb[i].z > 0.f), b3 = __ballot_sync(0xffffffffu, mb[i].w > 0.f);
+            if ((lane & 15) == 0 && j < nsc) {                   // lane 0: row rr (low halves), lane 16: its row rr (high halves)
+              const int sh = lane;                               // 0 or 16
+              const uint32_t w0 = ((b0 >> sh) & 0xffffu) | (((b1 >> sh) & 0xffffu) << 16), w1 = ((b2 >> sh) & 0xffffu) | (((b3 >> sh) & 0xffffu) << 16);
+              *reinterpret_cast<uint2*>(S + (size_t)(j * 128 + rr) * 8) = make_uint2(w0, w1);
+            }
+          }
+        }
+        named_bar_sync(1, kWorkers);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nsc) {
+            const uint2 w = *reinterpret_cast<const uint2*>(S + (size_t)(j * 128 + row) * 8);
+            uint32_t bits = 0u;                                  // bit 16 cc + 4 q + i  <-  component i of unit 8 hf + 4 cc + q
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  bits |= ((((i < 2) ? w.x : w.y) >> (16 * (i & 1) + 8 * hf + 4 * cc + q)) & 1u) << (16 * cc + 4 * q + i);
+            mbits[j] = bits;
+          }
+        }
+        named_bar_sync(1, kWorkers);                             // everybody has its bits before the epilogue reuses the image
+      } else if (mrow && valid) {
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {                         // two batches of 16 loads (slabs 2 hb, 2 hb + 1)
           float4 mb[16];
@@ -1330,7 +1406,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_rowgemm(const __grid_constant__
           }
         }
       }
-      if (it + 1 < my_tiles) g2r(nxt, P.A, P.lda, trow0 + (long long)gridDim.x * 128, 0);
       mbar_wait(smem_u32(sm.acc_full), it_acc & 1u, 600);
       ++it_acc;
       tc_fence_after();
@@ -1600,7 +1675,8 @@ int tc_rowgemm(const float* A, int64_t lda, int K, const float* B, int64_t b_rs,
   k_pack_b_bf16<<<dim3(nsl, 8), 256, 0, st>>>(B, b_rs, b_cs, K, N, img);
   p.packed = img - kAuxBytes;          // producer_tile skips the aux header
   p.A = A; p.lda = lda; p.K = nsl * 64; p.C = C; p.ldc = ldc; p.N = N; p.mask = mask; p.mask_ld = mask_ld; p.bias = bias;
-  p.accumulate = accumulate; p.relu = relu; p.P = P; p.nslots = 5;
+  p.accumulate = accumulate; p.relu = relu; p.P = P; p.nslots = kRgSlots;
+  p.mask_rows = getenv("NSOS_RG_MASK_BITS") == nullptr;     // the ballot variant measured slower (2.18 vs 1.75 ms on 1.5 M rows): opt-in
   // a K that is not a multiple of 64 (e.g. 96) is zero-padded in B; A columns beyond K must not be read: require K % 64 == 0 there
   NSOS_REQUIRE(K % 64 == 0, NSOS_ERR_UNSUPPORTED, "tc_rowgemm: K must be a multiple of 64");
   int dev = 0, sms = 0;
@@ -1608,7 +1684,7 @@ int tc_rowgemm(const float* A, int64_t lda, int K, const float* B, int64_t b_rs,
   NSOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long ntiles = (P + 127) / 128;
   const int grid = (int)std::min<long long>(ntiles, sms);
-  const size_t need = carve_smem(nullptr, p.nslots, 2, 2, 8, nullptr) + 1024;
+  const size_t need = carve_rowgemm(nullptr, p.nslots, nullptr, nullptr) + 1024;
   NSOS_CHECK_CUDA(cudaFuncSetAttribute(k_rowgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   k_rowgemm<<<grid, kThreads, need, st>>>(p);
   NSOS_CHECK_CUDA(cudaGetLastError());

@@ -602,7 +602,10 @@ def test_wide_encodings_fail_loudly():
 
 
 @pytest.mark.parametrize("K,N,P,trans,opts", [(256, 256, 1000, True, "mask"), (128, 256, 300, True, "acc"), (256, 256, 64, False, "bias_relu"),
-                                              (64, 128, 129, False, "")])
+                                              (64, 128, 129, False, ""),
+                                              # several tiles per persistent CTA (148 x 128 rows = one wave): rotating A images, tail tile
+                                              (256, 256, 148 * 128 * 2 + 77, True, "mask"), (128, 256, 148 * 128 + 5, True, "acc"),
+                                              (192, 64, 148 * 128 * 3 + 130, False, "bias_relu")])
 def test_rowgemm_building_block(K, N, P, trans, opts):
     """tcgen05 row GEMM of the all-parameter backward (bf16 hi/lo, 3 MMAs per product) vs fp64."""
     _lib, _ = _imports()
