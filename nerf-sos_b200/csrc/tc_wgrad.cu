@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NL), 1) k_wgrad_gen2(const __gr
     const float* const bx = aux_rows ? P.aux + 4 * (rt & 15) : nullptr;
     const uint32_t S0 = smem_u32(sm.st[0]);
     // halves are requested in order, so the request state is carried along: next half, its first point, one source pointer per
-    // block.  Rows beyond P are zero-filled (source size 0: nothing is read through the pointer).
+    // block.  Rows beyond P are zero-filled (source size 0; the pointer is parked on row 0 of the block, which always exists).
     long long rq_u = 0, rq_p0 = (long long)blockIdx.x * kSlabPts;
     const int step_odd = (int)gridDim.x * kSlabPts - 32;     // points from an odd half to the next even one (pitches < 2^16: products fit 32 bits)
     const int em[2] = {32 * (int)P.ld_main, step_odd * (int)P.ld_main}, ed[2] = {32 * (int)P.ldy, step_odd * (int)P.ldy},
@@ -715,7 +715,8 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NL), 1) k_wgrad_gen2(const __gr
           const float* src = pm;
 #pragma unroll
           for (int i = 0; i < 2048 / RT; ++i) {
-            cp_async16(S + dm + (uint32_t)((RT / 64) * i * kStRow), src, rm + (RT / 64) * i < nv ? 16u : 0u);
+            const bool v = rm + (RT / 64) * i < nv;
+            cp_async16(S + dm + (uint32_t)((RT / 64) * i * kStRow), v ? src : bm, v ? 16u : 0u);
             src += (RT / 64) * P.ld_main;
           }
         }
@@ -723,7 +724,8 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NL), 1) k_wgrad_gen2(const __gr
           const float* src = pd;
 #pragma unroll
           for (int i = 0; i < 1024 / RT; ++i) {
-            cp_async16(S + dd + (uint32_t)((RT / 32) * i * kStRow), src, rd + (RT / 32) * i < nv ? 16u : 0u);
+            const bool v = rd + (RT / 32) * i < nv;
+            cp_async16(S + dd + (uint32_t)((RT / 32) * i * kStRow), v ? src : bd, v ? 16u : 0u);
             src += (RT / 32) * P.ldy;
           }
         }
@@ -731,7 +733,8 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NL), 1) k_wgrad_gen2(const __gr
           const float* src = px;
 #pragma unroll
           for (int i = 0; i < 512 / RT; ++i) {
-            cp_async16(S + dx + (uint32_t)((RT / 16) * i * kStRow), src, rx + (RT / 16) * i < nv ? 16u : 0u);
+            const bool v = rx + (RT / 16) * i < nv;
+            cp_async16(S + dx + (uint32_t)((RT / 16) * i * kStRow), v ? src : bx, v ? 16u : 0u);
             src += (RT / 16) * P.ld_aux;
           }
         }
