@@ -15,7 +15,8 @@
 //     A2 [128 units   x 64 pts] = s0^T        B2 [ 16       x 64 pts] = g_sem^T (rows >= sem_dim zero)
 // and one elected thread issues 3 x 4 x 3 tcgen05.mma (hi.hi + lo.hi + hi.lo; M=128, N=256/64/16, K=16) that accumulate
 // in TMEM for the whole life of the CTA:  D[:, 0:319] = dW0, D[:, 319] = db0 (the constant-one feature), D[:, 320:324] =
-// dW2^T.  At the end every CTA adds its partial sums to the flat gradient buffer with atomics.
+// dW2^T.  At the end every CTA stores its partial sums column-major into scratch memory and k_wgrad_reduce adds them to the flat
+// gradient buffer in a fixed order (round 1 used atomics: 148 CTAs x 41 k atomics on the same addresses per launch).
 // bf16 hi+lo carries 16 mantissa bits per operand with fp32 range (gradients can be far below the fp16 range).
 #include <cuda_bf16.h>
 
@@ -31,9 +32,11 @@ namespace {
 using namespace ptx;
 
 constexpr int kWgWorkers = 256, kWgThreads = 288, kWgMmaWarp = 8;   // k_wgrad_gen: 8 fill warps + an issuer warp
-constexpr int kSemWarps = 8, kSemIssuer = kSemWarps, kSemThreads = 32 * (kSemWarps + 4);   // 8 fill warps + the issuer's warpgroup (3 of its warps idle)   // k_sem_wgrad: 16 fill warps (two sets of 14 loads per lane, 128 registers):
-                                   // 8 warps at 255 registers issued one instruction per 8 cycles (ncu: 75 % of cycles without an eligible warp);
-                                   // the MMA issue rotates over the warps
+// k_sem_wgrad: 8 fill warps + the issuer's warpgroup (3 of its warps idle).  12 warps are launched at 168 registers; the issuer's group
+// drops to 24 and the fill warps grow to 240 with setmaxnreg (the pool is what the CTA's own warps release).  History: 8 warps at 255
+// registers with the issue duty inside a fill warp issued one instruction per 8 cycles (ncu: 75 % of cycles without an eligible warp);
+// 16 fill warps at 112 registers next to the issuer group measured the same as this split.
+constexpr int kSemWarps = 8, kSemIssuer = kSemWarps, kSemThreads = 32 * (kSemWarps + 4);
 constexpr int kHalfPts = 32;                       // points per fill / MMA unit: half of a 64-point tile
 constexpr int kSlabPts = 64;
 constexpr int kRowsA = 128, kRowsB = 320, kRowsB2 = 16;
