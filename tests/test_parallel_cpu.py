@@ -78,6 +78,10 @@ def _worker(rank, ws, port, q):
         out = P.render_sharded(Net(), rb, (1.0, 2.0))
         c_full, rgb_full = _toy_render(w0, rays.reshape(-1, 3))
         ok = ok and torch.equal(out["rgb"], rgb_full) and torch.equal(out["semantics"], c_full)
+        # fewer rays than ranks: the rank with an empty shard renders one ray for the shapes, contributes no rows and does not hang
+        near1, far1 = torch.full((1, 1), 1.0), torch.full((1, 1), 2.0)
+        out1 = P.render_sharded(Net(), rb[:, :1], (near1, far1))
+        ok = ok and out1["rgb"].shape == (1, 3) and torch.equal(out1["rgb"], rgb_full[:1]) and torch.equal(out1["semantics"], c_full[:1])
         q.put((rank, bool(ok), loss.item(), l_ref.item()))
     finally:
         dist.destroy_process_group()
